@@ -1,0 +1,465 @@
+"""CPU oracle for the GpRegressor hot path -- TEST INFRASTRUCTURE, never imported by the product.
+
+A functional numpy/scipy restatement of the arithmetic the reference performs on this path.  Every
+function cites the reference lines it follows (paths relative to /root/reference/inference/gp/).
+The third-party arithmetic (LAPACK dpotrf / dtrtrs through numpy.linalg.cholesky and
+scipy.linalg.solve_triangular, BLAS through `@`) is called exactly as the reference calls it; the
+difference to the reference is only structural: no (N,N,d) arrays are stored, covariance blocks are
+built on demand from x, so the same code runs at N = 16k-32k where the reference cannot allocate.
+
+Parity pinning: the reference holds no golden vectors for this path.  This
+restatement is pinned instead against outputs of the unmodified reference imported in the build
+container: tests/golden/make_golden.py generates tests/golden/*.npz from the live reference and
+tests/test_oracle_golden.py checks this module against those fixtures.
+
+Model description used throughout:
+    comps : sequence of kernel kinds, each one of "SE", "RQ", "WHITE", "HETERO"
+    mean  : "const" | "linear" | "quadratic"
+    theta : [mean params | cov params] (regression.py:150-155), cov params concatenated in
+            component order (covariance.py:61, 692-697)
+"""
+from __future__ import annotations
+
+import numpy as np
+from numpy.linalg import cholesky
+from scipy.linalg import solve_triangular
+from scipy.special import erf, erfcx
+
+EPS_JITTER = 1e-12  # covariance.py:221, 318
+
+
+# ----------------------------------------------------------------------------- parameter layout
+def n_cov_params(kind: str, n: int, d: int) -> int:
+    """covariance.py:222 (SE d+1), :319 (RQ d+2), :140 (White 1), :654 (Hetero N)."""
+    return {"SE": d + 1, "RQ": d + 2, "WHITE": 1, "HETERO": n}[kind]
+
+
+def n_mean_params(mean: str, d: int) -> int:
+    """mean.py:34 (1), :62 (1+d), :95 (1+2d)."""
+    return {"const": 1, "linear": 1 + d, "quadratic": 1 + 2 * d}[mean]
+
+
+def split_theta(theta, comps, mean, n, d):
+    theta = np.asarray(theta, dtype=float)
+    pm = n_mean_params(mean, d)
+    tm, tc = theta[:pm], theta[pm:]
+    parts, o = [], 0
+    for k in comps:
+        p = n_cov_params(k, n, d)
+        parts.append(tc[o:o + p])
+        o += p
+    assert o == tc.size, "wrong number of hyper-parameters"
+    return tm, parts
+
+
+# ----------------------------------------------------------------------------- covariance functions
+def _scaled_half_sqdist(u, v, ls):
+    """Z_ij = sum_k 0.5 (u_ik - v_jk)^2 / l_k^2, accumulated dimension by dimension in the same
+    order as numpy's `.sum(axis=2)` over the last axis (covariance.py:243-244, 339-340)."""
+    z = np.zeros((u.shape[0], v.shape[0]))
+    for k in range(u.shape[1]):
+        dk = u[:, k, None] - v[None, :, k]
+        z += (0.5 * dk**2) / ls[k] ** 2
+    return z
+
+
+def cross_cov(comps, parts, u, v):
+    """cov(u, v, theta): covariance.py:240-245 (SE), :335-341 (RQ); noise kernels return zeros
+    (:160-161, :671-672); composite = sum (:86-89)."""
+    out = np.zeros((u.shape[0], v.shape[0]))
+    for kind, th in zip(comps, parts):
+        if kind == "SE":
+            a, ls = np.exp(th[0]), np.exp(th[1:])
+            out += a**2 * np.exp(-_scaled_half_sqdist(u, v, ls))
+        elif kind == "RQ":
+            a, q, ls = np.exp(th[0]), np.exp(th[1]), np.exp(th[2:])
+            z = _scaled_half_sqdist(u, v, ls)
+            out += a**2 * (1 + z / q) ** (-q)
+    return out
+
+
+def prior_var(comps, parts):
+    """k(q,q): a^2 summed over the smooth components (noise kernels contribute 0)."""
+    return sum(np.exp(th[0]) ** 2 for kind, th in zip(comps, parts) if kind in ("SE", "RQ"))
+
+
+def train_cov_rows(comps, parts, x, r0, r1, noise_var=None):
+    """Rows [r0,r1) of K(theta)+sig on the training data: build_covariance (covariance.py:247-255,
+    343-348, 163-169, 674-680, 91-95) plus diag(y_err^2) (regression.py:239, 320).  The 1e-12
+    jitter is added before the a^2 scaling (covariance.py:254-255, 348)."""
+    n = x.shape[0]
+    blk = cross_cov(comps, parts, x[r0:r1], x)
+    idx = np.arange(r0, r1)
+    for kind, th in zip(comps, parts):
+        if kind in ("SE", "RQ"):
+            blk[idx - r0, idx] += np.exp(th[0]) ** 2 * EPS_JITTER
+        elif kind == "WHITE":
+            blk[idx - r0, idx] += np.exp(2 * th[0])
+        elif kind == "HETERO":
+            blk[idx - r0, idx] += np.exp(2 * th[r0:r1])
+    if noise_var is not None:
+        blk[idx - r0, idx] += noise_var[r0:r1]
+    assert blk.shape == (r1 - r0, n)
+    return blk
+
+
+def train_cov(comps, parts, x, noise_var=None, y_cov=None, block=2048):
+    n = x.shape[0]
+    k = np.empty((n, n))
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        k[r0:r1] = train_cov_rows(comps, parts, x, r0, r1, noise_var)
+    if y_cov is not None:
+        k += y_cov
+    return k
+
+
+def cov_and_grads(comps, parts, x):
+    """covariance_and_gradients WITHOUT sig: covariance.py:268-276 (SE), :350-365 (RQ), :171-175
+    (White), :682-686 (Hetero), :97-105 (sum).  Dense (small-N use only: tests)."""
+    n, d = x.shape
+    eye = np.eye(n)
+    ktot = np.zeros((n, n))
+    grads = []
+    for kind, th in zip(comps, parts):
+        if kind == "SE":
+            a, ls = np.exp(th[0]), np.exp(th[1:])
+            k = a**2 * (np.exp(-_scaled_half_sqdist(x, x, ls)) + EPS_JITTER * eye)
+            grads.append(2.0 * k)
+            for i in range(d):
+                dx2 = (x[:, i, None] - x[None, :, i]) ** 2
+                grads.append((dx2 / ls[i] ** 2) * k)
+        elif kind == "RQ":
+            a, q, ls = np.exp(th[0]), np.exp(th[1]), np.exp(th[2:])
+            z = _scaled_half_sqdist(x, x, ls)
+            f = 1 + z / q
+            lnf = np.log(f)
+            k = a**2 * (np.exp(-q * lnf) + EPS_JITTER * eye)
+            grads.append(2.0 * k)
+            grads.append(-k * (lnf * q - z / f))
+            g = 2 * k / f
+            for i in range(d):
+                grads.append(g * (0.5 * (x[:, i, None] - x[None, :, i]) ** 2 / ls[i] ** 2))
+        elif kind == "WHITE":
+            k = np.exp(2 * th[0]) * eye
+            grads.append(2.0 * k)
+        elif kind == "HETERO":
+            s2 = np.exp(2 * th)
+            k = np.diag(s2)
+            for i in range(n):
+                g = np.zeros((n, n))
+                g[i, i] = 2.0 * s2[i]
+                grads.append(g)
+        ktot = ktot + k
+    return ktot, grads
+
+
+# ----------------------------------------------------------------------------- mean functions
+def mean_vec(mean, tm, x, xbar=None):
+    """build_mean: mean.py:47-48, :77-78, :117-120.  xbar = column mean of the TRAINING x."""
+    if mean == "const":
+        return np.zeros(x.shape[0]) + tm[0]
+    d = x.shape[1]
+    dx = x - xbar[None, :]
+    if mean == "linear":
+        return tm[0] + dx @ tm[1:]
+    return tm[0] + dx @ tm[1:d + 1] + (dx**2) @ tm[d + 1:2 * d + 1]
+
+
+def mean_grads(mean, x, xbar=None):
+    """mean_and_gradients: mean.py:50-51, :80-83, :122-126."""
+    n, d = x.shape
+    g = [np.ones(n)]
+    if mean in ("linear", "quadratic"):
+        dx = x - xbar[None, :]
+        g.extend(dx.T)
+        if mean == "quadratic":
+            g.extend((dx**2).T)
+    return g
+
+
+# ----------------------------------------------------------------------------- fit / likelihood
+class Fit:
+    """State produced by set_hyperparameters (regression.py:218-244)."""
+
+    def __init__(self, x, y, comps, mean, theta, noise_var=None, y_cov=None):
+        self.x = np.ascontiguousarray(x, dtype=float)
+        if self.x.ndim == 1:
+            self.x = self.x.reshape(-1, 1)
+        self.y = np.asarray(y, dtype=float).squeeze()
+        self.n, self.d = self.x.shape
+        self.comps, self.mean = tuple(comps), mean
+        self.noise_var = None if noise_var is None else np.asarray(noise_var, dtype=float)
+        self.y_cov = y_cov
+        self.xbar = self.x.mean(axis=0)
+        self.theta = np.asarray(theta, dtype=float)
+        self.tm, self.parts = split_theta(theta, comps, mean, self.n, self.d)
+        k = train_cov(self.comps, self.parts, self.x, self.noise_var, y_cov)
+        self.mu = mean_vec(mean, self.tm, self.x, self.xbar)
+        self.L = cholesky(k)                                                       # regression.py:241
+        del k
+        self.alpha = solve_triangular(                                              # regression.py:242-244
+            self.L.T, solve_triangular(self.L, self.y - self.mu, lower=True))
+
+    # regression.py:188-216 -- one dtrtrs per query in the reference; here `chunk` RHS at a time
+    def predict(self, q, chunk=256):
+        q = self._points(q)
+        mu = np.empty(q.shape[0])
+        var = np.empty(q.shape[0])
+        kqq = prior_var(self.comps, self.parts)
+        for s in range(0, q.shape[0], chunk):
+            qq = q[s:s + chunk]
+            kqx = cross_cov(self.comps, self.parts, qq, self.x)
+            mu[s:s + chunk] = kqx @ self.alpha + mean_vec(self.mean, self.tm, qq, self.xbar)
+            v = solve_triangular(self.L, kqx.T, lower=True)
+            var[s:s + chunk] = kqq - (v**2).sum(axis=0)
+        return mu, np.sqrt(np.abs(var))
+
+    def _points(self, q):
+        q = np.asarray(q, dtype=float)
+        if q.ndim <= 1 and self.d == 1:
+            q = q.reshape(-1, 1)
+        elif q.ndim == 1 and q.size == self.d:
+            q = q.reshape(1, -1)
+        return q
+
+    def _se_theta(self):
+        if self.comps != ("SE",):
+            raise NotImplementedError("gradient_terms exists only for SquaredExponential (covariance.py:38-44, 257-266)")
+        th = self.parts[0]
+        return np.exp(th[0]), np.exp(th[1:])
+
+    # regression.py:351-385 with covariance.py:257-266.  R is a length-d vector broadcast over
+    # rows (reference behaviour, SURVEY.md section 7 "quirks"), reproduced as is.
+    def gradient(self, q):
+        a, ls = self._se_theta()
+        q = self._points(q)
+        means, covs = [], []
+        for pnt in q:
+            kqx = cross_cov(self.comps, self.parts, pnt[None, :], self.x)
+            A = ((self.x - pnt[None, :]) / ls[None, :] ** 2).T
+            R = (a / ls) ** 2
+            Q = solve_triangular(self.L, (A * kqx).T, lower=True)
+            means.append(A @ (kqx * self.alpha).T)
+            covs.append(R - Q.T @ Q)
+        return np.array(means).squeeze(), np.array(covs).squeeze()
+
+    # regression.py:387-419
+    def spatial_derivatives(self, q):
+        a, ls = self._se_theta()
+        q = self._points(q)
+        dmu, dvar = [], []
+        for pnt in q:
+            kqx = cross_cov(self.comps, self.parts, pnt[None, :], self.x)
+            A = ((self.x - pnt[None, :]) / ls[None, :] ** 2).T
+            Q = solve_triangular(self.L.T, solve_triangular(self.L, kqx.T, lower=True))
+            dmu.append(A @ (kqx * self.alpha).T)
+            dvar.append(-2 * (A * kqx[None, :]) @ Q)
+        return np.array(dmu).squeeze(), np.array(dvar).squeeze()
+
+    # regression.py:421-449
+    def posterior(self, q):
+        q = self._points(q)
+        kqx = cross_cov(self.comps, self.parts, q, self.x)
+        kqq = cross_cov(self.comps, self.parts, q, q)
+        mu = kqx @ self.alpha + mean_vec(self.mean, self.tm, q, self.xbar)
+        Q = solve_triangular(self.L, kqx.T, lower=True)
+        return mu, kqq - Q.T @ Q
+
+    # regression.py:451-466
+    def loo_predictions(self):
+        ik = solve_triangular(self.L, np.eye(self.n), lower=True)
+        ik = ik.T @ ik
+        var = 1.0 / np.diag(ik)
+        return self.y - self.alpha * var, np.sqrt(var)
+
+
+def marginal_likelihood(x, y, comps, mean, theta, noise_var=None, y_cov=None):
+    """regression.py:528-542 (value only; LinAlgError -> -1e50)."""
+    x = np.asarray(x, dtype=float)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    n, d = x.shape
+    tm, parts = split_theta(theta, comps, mean, n, d)
+    k = train_cov(comps, parts, x, noise_var, y_cov)
+    mu = mean_vec(mean, tm, x, x.mean(axis=0))
+    try:
+        L = cholesky(k)
+    except np.linalg.LinAlgError:
+        return -1e50
+    v = solve_triangular(L, y - mu, lower=True)
+    return -0.5 * (v @ v) - np.log(np.diagonal(L)).sum()
+
+
+def marginal_likelihood_gradient(x, y, comps, mean, theta, noise_var=None, y_cov=None):
+    """regression.py:544-567: explicit inverse through dtrtrs on the identity + `iK.T @ iK`,
+    Q = alpha alpha^T - K^-1, grad_i = 0.5 sum(Q * dK_i^T)."""
+    x = np.asarray(x, dtype=float)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    n, d = x.shape
+    tm, parts = split_theta(theta, comps, mean, n, d)
+    xbar = x.mean(axis=0)
+    k, grad_k = cov_and_grads(comps, parts, x)
+    if noise_var is not None:
+        k = k + np.diag(noise_var)
+    if y_cov is not None:
+        k = k + y_cov
+    mu = mean_vec(mean, tm, x, xbar)
+    grad_mu = mean_grads(mean, x, xbar)
+    L = cholesky(k)
+    ik = solve_triangular(L, np.eye(n), lower=True)
+    ik = ik.T @ ik
+    alpha = ik @ (y - mu)
+    lml = -0.5 * ((y - mu).T @ alpha) - np.log(np.diagonal(L)).sum()
+    grad = np.zeros(len(theta))
+    pm = len(tm)
+    grad[:pm] = [(alpha * g).sum() for g in grad_mu]
+    Q = alpha[:, None] * alpha[None, :] - ik
+    grad[pm:] = [0.5 * (Q * g.T).sum() for g in grad_k]
+    return lml, grad
+
+
+def loo_likelihood(x, y, comps, mean, theta, noise_var=None):
+    """regression.py:468-487."""
+    x = np.asarray(x, dtype=float)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    n, d = x.shape
+    tm, parts = split_theta(theta, comps, mean, n, d)
+    k = train_cov(comps, parts, x, noise_var)
+    mu = mean_vec(mean, tm, x, x.mean(axis=0))
+    try:
+        L = cholesky(k)
+    except np.linalg.LinAlgError:
+        return -1e50
+    ik = solve_triangular(L, np.eye(n), lower=True)
+    ik = ik.T @ ik
+    alpha = ik @ (y - mu)
+    var = 1.0 / np.diag(ik)
+    return -0.5 * (var * alpha**2 + np.log(var)).sum()
+
+
+def loo_likelihood_gradient(x, y, comps, mean, theta, noise_var=None):
+    """regression.py:489-526."""
+    x = np.asarray(x, dtype=float)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    n, d = x.shape
+    tm, parts = split_theta(theta, comps, mean, n, d)
+    xbar = x.mean(axis=0)
+    k, grad_k = cov_and_grads(comps, parts, x)
+    if noise_var is not None:
+        k = k + np.diag(noise_var)
+    mu = mean_vec(mean, tm, x, xbar)
+    grad_mu = mean_grads(mean, x, xbar)
+    L = cholesky(k)
+    ik = solve_triangular(L, np.eye(n), lower=True)
+    ik = ik.T @ ik
+    alpha = ik @ (y - mu)
+    var = 1.0 / np.diag(ik)
+    loo = -0.5 * (var * alpha**2 + np.log(var)).sum()
+    c1 = alpha * var
+    c2 = 0.5 * var * (1 + var * alpha**2)
+    grad = np.zeros(len(theta))
+    pm = len(tm)
+    grad[pm:] = [(c1 * ((ik @ g) @ alpha) - c2 * np.diag((ik @ g) @ ik)).sum() for g in grad_k]
+    grad[:pm] = [(c1 * (ik @ g)).sum() for g in grad_mu]
+    return loo, grad
+
+
+# ----------------------------------------------------------------------------- acquisition
+_IR2PI = 1 / np.sqrt(2 * np.pi)
+_IR2 = 1.0 / np.sqrt(2)
+_RPI2 = np.sqrt(0.5 * np.pi)
+_LN2PI = np.log(2 * np.pi)
+
+
+def expected_improvement(mu, sig, y_max):
+    """Vectorised ExpectedImprovement.__call__ (acquisition.py:76-86): branch at Z < -3."""
+    mu, sig = np.asarray(mu, dtype=float), np.asarray(sig, dtype=float)
+    Z = (mu - y_max) / sig
+    out = np.empty_like(Z)
+    lo = Z < -3
+    zl = Z[lo]
+    out[lo] = np.exp(np.log(1 + zl * _RPI2 * erfcx(-zl * _IR2)) - 0.5 * (zl**2 + _LN2PI) + np.log(sig[lo]))
+    zh = Z[~lo]
+    out[~lo] = sig[~lo] * (zh * 0.5 * (1.0 + erf(zh * _IR2)) + np.exp(-0.5 * zh**2) * _IR2PI)
+    return out
+
+
+def neg_log_ei(mu, sig, y_max):
+    """Vectorised ExpectedImprovement.opt_func (acquisition.py:88-97)."""
+    mu, sig = np.asarray(mu, dtype=float), np.asarray(sig, dtype=float)
+    Z = (mu - y_max) / sig
+    out = np.empty_like(Z)
+    lo = Z < -3
+    zl = Z[lo]
+    out[lo] = np.log(1 + zl * _RPI2 * erfcx(-zl * _IR2)) - 0.5 * (zl**2 + _LN2PI) + np.log(sig[lo])
+    zh = Z[~lo]
+    out[~lo] = np.log(sig[~lo] * (zh * 0.5 * (1.0 + erf(zh * _IR2)) + np.exp(-0.5 * zh**2) * _IR2PI))
+    return -out
+
+
+def neg_log_ei_gradient(mu, sig, dmu, dvar, y_max):
+    """Vectorised ExpectedImprovement.opt_func_gradient (acquisition.py:99-125).
+    mu, sig: (M,), dmu, dvar: (M,d) -> (-ln EI (M,), -grad ln EI (M,d))."""
+    mu, sig = np.asarray(mu, dtype=float), np.asarray(sig, dtype=float)
+    dmu = np.asarray(dmu, dtype=float).reshape(mu.size, -1)
+    dvar = np.asarray(dvar, dtype=float).reshape(mu.size, -1)
+    Z = (mu - y_max) / sig
+    val = np.empty_like(Z)
+    grad = np.empty_like(dmu)
+    for i in range(Z.size):
+        z, s = Z[i], sig[i]
+        if z < -3:
+            R = _RPI2 * erfcx(-z * _IR2)
+            H = 1 + z * R
+            val[i] = np.log(H) - 0.5 * (z**2 + _LN2PI) + np.log(s)
+            grad[i] = (0.5 * dvar[i] / s + R * dmu[i]) / (H * s)
+        else:
+            pdf = np.exp(-0.5 * z**2) * _IR2PI
+            cdf = 0.5 * (1.0 + erf(z * _IR2))
+            ei = s * (z * cdf + pdf)
+            val[i] = np.log(ei)
+            grad[i] = (0.5 * pdf * dvar[i] / s + dmu[i] * cdf) / ei
+    return -val, -grad
+
+
+# ----------------------------------------------------------------------------- bounds
+def cov_bounds(comps, x, y):
+    """estimate_hyperpar_bounds: covariance.py:228-238 (SE), :323-333 (RQ), :151-158 (White),
+    :662-669 (Hetero).  mean_ij|dx| is over all N^2 ordered pairs including the zero diagonal."""
+    n, d = x.shape
+    out = []
+    for kind in comps:
+        if kind in ("SE", "RQ"):
+            s = np.log(y.std())
+            out.append((s - 4, s + 4))
+            if kind == "RQ":
+                out.append((-2, 6))
+            for i in range(d):
+                col = x[:, i]
+                mad = 0.0
+                for r0 in range(0, n, 1024):
+                    mad += np.abs(col[r0:r0 + 1024, None] - col[None, :]).sum()
+                mad /= n * n
+                out.append((np.log(mad) - 4, np.log(col.max() - col.min()) + 2))
+        else:
+            s = np.log(np.ptp(y))
+            out.extend([(s - 8, s + 2)] * (1 if kind == "WHITE" else n))
+    return out
+
+
+def mean_bounds(mean, x, y):
+    """mean.py:40-42, :68-72, :104-109."""
+    w = y.max() - y.min()
+    if mean == "const":
+        return [(y.min() - w, y.max() + w)]
+    dx = x - x.mean(axis=0)[None, :]
+    gb = 10 * w / (dx.max(axis=0) - dx.min(axis=0))
+    out = [(y.min() - 2 * w, y.max() + 2 * w)]
+    out.extend([(-b, b) for b in gb])
+    if mean == "quadratic":
+        out.extend([(-b, b) for b in gb])
+    return out
