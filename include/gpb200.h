@@ -1,0 +1,113 @@
+/* gpb200 -- C ABI of the B200-native Gaussian-process regression engine (libgpb200.so).
+ *
+ * This is the drop-in boundary for the GpRegressor hot path of C-bowman/inference-tools.  The reference
+ * has no FFI: its boundary is Python (inference/gp/regression.py, covariance.py, mean.py,
+ * acquisition.py) calling numpy.linalg.cholesky / scipy.linalg.solve_triangular / BLAS.  Every entry
+ * point below names the reference interface it replaces (paths relative to inference/gp/).  The
+ * Python shim in inference_tools_b200/gp binds these with ctypes (INTEGRATION.md shows the binding a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - all array arguments are caller-owned C-order float64 HOST buffers unless the name ends in _dev
+ *     (then they are device pointers on the context's GPU);
+ *   - return value: 0 = ok; < 0 = CUDA / argument error, text in gpb_last_error();
+ *   - `info` out-parameters follow LAPACK dpotrf: 0 = positive definite, k > 0 = the leading minor of
+ *     order k is not positive definite (the shim raises numpy.linalg.LinAlgError exactly where the
+ *     reference would, regression.py:241, 537, 555);
+ *   - hyper-parameter vectors use the reference layout theta = [mean params | cov params]
+ *     (regression.py:150-155), cov params concatenated in component order (covariance.py:61, 692-697);
+ *   - a context owns all device memory, is bound to one GPU and is not re-entrant; calls release the
+ *     GIL when made through ctypes.  There is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef GPB200_H
+#define GPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpb_ctx gpb_ctx;
+
+/* covariance kinds: covariance.py:181 SquaredExponential, :282 RationalQuadratic, :108 WhiteNoise,
+ * :608 HeteroscedasticNoise; sums of them = CompositeCovariance (:47-105). */
+enum { GPB_COV_SE = 0, GPB_COV_RQ = 1, GPB_COV_WHITE = 2, GPB_COV_HETERO = 3 };
+/* mean kinds: mean.py:31 ConstantMean, :54 LinearMean, :86 QuadraticMean */
+enum { GPB_MEAN_CONST = 0, GPB_MEAN_LINEAR = 1, GPB_MEAN_QUADRATIC = 2 };
+/* gpb_get selectors: attributes GpRegressor exposes after set_hyperparameters (regression.py:239-244) */
+enum { GPB_GET_K_XX = 0, GPB_GET_L = 1, GPB_GET_ALPHA = 2, GPB_GET_MU = 3 };
+/* gpb_expected_improvement modes: ExpectedImprovement.__call__ (acquisition.py:76-86), opt_func
+ * (:88-97), opt_func_gradient (:99-125) */
+enum { GPB_EI_VALUE = 0, GPB_EI_NEG_LOG = 1, GPB_EI_NEG_LOG_GRAD = 2 };
+
+const char* gpb_last_error(void);
+int gpb_device_count(int* count);
+int64_t gpb_launch_count(void);           /* kernels launched by this library so far (process-wide) */
+double gpb_gemm_flops(void);              /* algorithmic flops issued through the DMMA GEMM so far */
+
+int gpb_ctx_create(int device, gpb_ctx** out);
+void gpb_ctx_destroy(gpb_ctx* ctx);
+
+/* GpRegressor.__init__ data intake (regression.py:94-133): x is n x d, y has n entries, noise_var =
+ * y_err**2 (the diagonal of `sig`, regression.py:320) or NULL (zeros, :322), y_cov = dense n x n `sig`
+ * (:293) or NULL. */
+int gpb_set_data(gpb_ctx* ctx, const double* x, int64_t n, int d, const double* y, const double* noise_var,
+                 const double* y_cov);
+/* kernel= / mean= arguments (regression.py:136-143): component kinds in sum order. */
+int gpb_set_model(gpb_ctx* ctx, const int* cov_kinds, int ncomp, int mean_kind);
+int gpb_num_hyperpars(gpb_ctx* ctx, int* n_mean, int* n_cov);
+
+/* CovarianceFunction.build_covariance(theta) (covariance.py:247-255, 343-348, 163-169, 674-680, 91-95);
+ * add_sig != 0 adds the data-error term as regression.py:239 does.  K_out is n x n. */
+int gpb_build_covariance(gpb_ctx* ctx, const double* theta_cov, int add_sig, double* K_out);
+/* CovarianceFunction.covariance_and_gradients(theta) (covariance.py:268-276, 350-365, 171-175, 682-686,
+ * 97-105): K_out n x n, dK_out n_cov x n x n. */
+int gpb_covariance_and_gradients(gpb_ctx* ctx, const double* theta_cov, double* K_out, double* dK_out);
+/* CovarianceFunction.__call__(u, v, theta) (covariance.py:240-245, 335-341, 160-161, 671-672, 86-89):
+ * out is m x n. */
+int gpb_cross_covariance(gpb_ctx* ctx, const double* u, int64_t m, const double* v, int64_t n,
+                         const double* theta_cov, double* out);
+
+/* GpRegressor.set_hyperparameters (regression.py:218-244): K_xx = K(theta)+sig, L = chol(K_xx),
+ * alpha = K_xx^-1 (y - mu).  State stays on the device until gpb_get. */
+int gpb_factor(gpb_ctx* ctx, const double* theta, int* info);
+int gpb_get(gpb_ctx* ctx, int which, double* out);
+/* GpRegressor.marginal_likelihood (regression.py:528-542); on info > 0 the shim returns -1e50 */
+int gpb_lml(gpb_ctx* ctx, const double* theta, double* lml, int* info);
+/* GpRegressor.marginal_likelihood_gradient (regression.py:544-567): grad has n_mean + n_cov entries */
+int gpb_lml_grad(gpb_ctx* ctx, const double* theta, double* lml, double* grad, int* info);
+/* GpRegressor.loo_likelihood / loo_likelihood_gradient / loo_predictions (regression.py:451-526) */
+int gpb_loo(gpb_ctx* ctx, const double* theta, double* loo, double* grad_or_null, int* info);
+int gpb_loo_predictions(gpb_ctx* ctx, double* mu, double* sigma);
+
+/* GpRegressor.__call__ (regression.py:188-216): q is m x d; mu, sig have m entries */
+int gpb_predict(gpb_ctx* ctx, const double* q, int64_t m, double* mu, double* sig);
+/* same with device-resident buffers (inputs already in HBM) */
+int gpb_predict_dev(gpb_ctx* ctx, const double* q_dev, int64_t m, double* mu_dev, double* sig_dev);
+/* GpRegressor.gradient (regression.py:351-385), SquaredExponential only: mean m x d, cov m x d x d */
+int gpb_gradient(gpb_ctx* ctx, const double* q, int64_t m, double* mean, double* cov);
+/* GpRegressor.spatial_derivatives (regression.py:387-419), SquaredExponential only: m x d each */
+int gpb_spatial_derivatives(gpb_ctx* ctx, const double* q, int64_t m, double* dmu, double* dvar);
+/* GpRegressor.build_posterior (regression.py:421-449): mu m, sigma m x m (NULL = mean_only) */
+int gpb_posterior(gpb_ctx* ctx, const double* q, int64_t m, double* mu, double* sigma_or_null);
+/* ExpectedImprovement over a batch of candidates (acquisition.py:76-125); grad (m x d) only for
+ * GPB_EI_NEG_LOG_GRAD (SquaredExponential only); argmax_or_null receives the index of the best value */
+int gpb_expected_improvement(gpb_ctx* ctx, const double* q, int64_t m, double y_max, int mode, double* out,
+                             double* grad_or_null, int64_t* argmax_or_null);
+
+/* CUDA-event phase timings (milliseconds) of the most recent call on this context:
+ * names is a ';'-separated list written into name_buf, ms[i] the matching durations. */
+int gpb_timers(gpb_ctx* ctx, char* name_buf, int name_buf_len, double* ms, int max_entries, int* n_entries);
+
+/* Device memory helpers for callers that keep inputs resident in HBM (bench.py `value` leg). */
+int gpb_dev_alloc(gpb_ctx* ctx, int64_t n_doubles, double** out_dev);
+int gpb_dev_free(gpb_ctx* ctx, double* p_dev);
+int gpb_dev_upload(gpb_ctx* ctx, double* dst_dev, const double* src_host, int64_t n_doubles);
+int gpb_dev_download(gpb_ctx* ctx, double* dst_host, const double* src_dev, int64_t n_doubles);
+int gpb_sync(gpb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H */

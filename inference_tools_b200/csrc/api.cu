@@ -1,0 +1,818 @@
+// C-ABI of libgpb200 (declared in include/gpb200.h): context, device state and the host-side drivers
+// that string the kernels together.  No CPU arithmetic on the path: the host only maps the log
+// hyper-parameters (a handful of exp() calls), sequences launches and moves results.
+#include "../../include/gpb200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <utility>
+
+namespace gpb {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+static int64_t g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+int64_t launch_count() { return g_launches; }
+double gemm_flops_issued();  // gemm_dmma.cu
+
+namespace {
+
+struct PhaseTimer {
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    std::vector<cudaEvent_t> pool;
+    cudaStream_t s = nullptr;
+    void reset() {
+        for (auto& m : marks) pool.push_back(m.second);
+        marks.clear();
+    }
+    void mark(const char* name) {  // the interval that ENDS at the next mark is attributed to `name`
+        cudaEvent_t e;
+        if (!pool.empty()) {
+            e = pool.back();
+            pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        cudaEventRecord(e, s);
+        marks.emplace_back(name, e);
+    }
+    ~PhaseTimer() {
+        reset();
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
+template <typename T>
+int ensure(T*& p, size_t& cap, size_t bytes) {
+    if (cap >= bytes && p) return 0;
+    if (p) GPB_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    GPB_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return 0;
+}
+
+}  // namespace
+}  // namespace gpb
+
+using namespace gpb;
+
+struct gpb_ctx {
+    int device = 0;
+    cudaStream_t s = nullptr;
+    int64_t n = 0, npad = 0;
+    int d = 0;
+    double *x = nullptr, *y = nullptr, *noise = nullptr, *ycov = nullptr;
+    bool has_noise = false, has_ycov = false;
+    double xbar[MAX_DIM] = {0};
+    int ncomp = 0, kinds[MAX_COMP] = {0}, theta_off[MAX_COMP] = {0}, mean_kind = 0, n_mean = 0, n_cov = 0;
+    bool model_set = false;
+    double* theta_dev = nullptr;
+    size_t theta_dev_cap = 0;
+    // fitted state (set_hyperparameters)
+    double *Lfit = nullptr, *dinv_fit = nullptr, *alpha = nullptr, *mu = nullptr;
+    size_t Lfit_cap = 0, dinv_fit_cap = 0, alpha_cap = 0, mu_cap = 0;
+    std::vector<double> theta_fit;
+    bool fitted = false;
+    CovParams cp_fit;
+    MeanParams mp_fit;
+    // objective-evaluation workspace
+    double *Kwork = nullptr, *dinv_work = nullptr, *W = nullptr, *Kinv = nullptr, *partials = nullptr,
+           *grad_dev = nullptr, *vec = nullptr, *resid = nullptr, *alpha_work = nullptr, *scal = nullptr, *tmp = nullptr;
+    size_t Kwork_cap = 0, dinv_work_cap = 0, W_cap = 0, Kinv_cap = 0, partials_cap = 0, grad_cap = 0, vec_cap = 0,
+           resid_cap = 0, alpha_work_cap = 0, scal_cap = 0, tmp_cap = 0;
+    int64_t tmp_rows = 0;
+    int* info_dev = nullptr;
+    // predict workspace
+    double *S = nullptr, *dots = nullptr, *G = nullptr, *qbuf = nullptr, *o1 = nullptr, *o2 = nullptr, *o3 = nullptr,
+           *R_dev = nullptr;
+    size_t S_cap = 0, dots_cap = 0, G_cap = 0, qbuf_cap = 0, o1_cap = 0, o2_cap = 0, o3_cap = 0, R_cap = 0;
+    PhaseTimer timer;
+};
+
+namespace {
+
+int use(gpb_ctx* c) {
+    if (!c) {
+        set_error("null context");
+        return -2;
+    }
+    GPB_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+int need_model(gpb_ctx* c) {
+    if (c->n == 0 || !c->model_set) {
+        set_error("gpb_set_data and gpb_set_model must be called first");
+        return -2;
+    }
+    return 0;
+}
+
+int n_cov_params(int kind, int64_t n, int d) {
+    switch (kind) {
+        case COV_SE: return d + 1;
+        case COV_RQ: return d + 2;
+        case COV_WHITE: return 1;
+        default: return (int)n;
+    }
+}
+
+// covariance.py:248-249 (SE), :344-346 (RQ), :167 (White), :678 (Hetero)
+int make_cov_params(gpb_ctx* c, const double* tc, CovParams& cp) {
+    std::memset(&cp, 0, sizeof(cp));
+    cp.ncomp = c->ncomp;
+    cp.d = c->d;
+    cp.jitter = 1e-12;
+    cp.hetero_log_sigma = nullptr;
+    for (int i = 0; i < c->ncomp; ++i) {
+        const int off = c->theta_off[i];
+        cp.kind[i] = c->kinds[i];
+        cp.theta_off[i] = off;
+        if (c->kinds[i] == COV_SE) {
+            const double a = std::exp(tc[off]);
+            cp.amp2[i] = a * a;
+            for (int k = 0; k < c->d; ++k) {
+                const double l = std::exp(tc[off + 1 + k]);
+                cp.inv_l2[i][k] = 1.0 / (l * l);
+            }
+        } else if (c->kinds[i] == COV_RQ) {
+            const double a = std::exp(tc[off]);
+            cp.amp2[i] = a * a;
+            cp.rq_alpha[i] = std::exp(tc[off + 1]);
+            for (int k = 0; k < c->d; ++k) {
+                const double l = std::exp(tc[off + 2 + k]);
+                cp.inv_l2[i][k] = 1.0 / (l * l);
+            }
+        } else if (c->kinds[i] == COV_WHITE) {
+            cp.amp2[i] = std::exp(2.0 * tc[off]);
+        } else {
+            GPB_TRY(ensure(c->theta_dev, c->theta_dev_cap, sizeof(double) * c->npad));
+            GPB_CUDA(cudaMemsetAsync(c->theta_dev, 0, sizeof(double) * c->npad, c->s));
+            GPB_CUDA(cudaMemcpyAsync(c->theta_dev, tc + off, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->s));
+            GPB_CUDA(cudaStreamSynchronize(c->s));  // tc is caller memory
+            cp.hetero_log_sigma = c->theta_dev;
+        }
+    }
+    return 0;
+}
+
+void make_mean_params(gpb_ctx* c, const double* tm, MeanParams& mp) {
+    std::memset(&mp, 0, sizeof(mp));
+    mp.kind = c->mean_kind;
+    mp.d = c->d;
+    mp.c0 = tm[0];
+    for (int k = 0; k < c->d; ++k) {
+        mp.xbar[k] = c->xbar[k];
+        if (c->mean_kind >= MEAN_LINEAR) mp.lin[k] = tm[1 + k];
+        if (c->mean_kind == MEAN_QUADRATIC) mp.quad[k] = tm[1 + c->d + k];
+    }
+}
+
+int ensure_linalg_ws(gpb_ctx* c) {
+    const size_t dinv_bytes = sizeof(double) * (size_t)c->npad * NB;
+    GPB_TRY(ensure(c->dinv_work, c->dinv_work_cap, dinv_bytes));
+    GPB_TRY(ensure(c->dinv_fit, c->dinv_fit_cap, dinv_bytes));
+    const int64_t rows = std::max<int64_t>(c->npad, 148 * 128 * 4);
+    GPB_TRY(ensure(c->tmp, c->tmp_cap, sizeof(double) * (size_t)rows * NB));
+    c->tmp_rows = rows;
+    if (!c->info_dev) GPB_CUDA(cudaMalloc(&c->info_dev, sizeof(int)));
+    GPB_TRY(ensure(c->vec, c->vec_cap, sizeof(double) * 2 * c->npad));
+    GPB_TRY(ensure(c->resid, c->resid_cap, sizeof(double) * c->npad));
+    GPB_TRY(ensure(c->alpha_work, c->alpha_work_cap, sizeof(double) * c->npad));
+    GPB_TRY(ensure(c->scal, c->scal_cap, sizeof(double) * 8));
+    return 0;
+}
+
+LinalgWs ws_of(gpb_ctx* c, double* dinv) { return LinalgWs{dinv, c->tmp, c->tmp_rows, c->info_dev}; }
+
+// assemble K(theta)+sig into `K` (lower tiles), factor in place, solve for alpha.
+//   resid_out: y - mu (optional copy), v_out: L^-1 r left in c->vec[npad..) when !want_alpha
+int assemble_and_factor(gpb_ctx* c, const CovParams& cp, const MeanParams& mp, double* K, double* dinv, double* mu_out,
+                        bool want_alpha, double* alpha_out, int* info_host) {
+    const int npad = (int)c->npad, n = (int)c->n;
+    c->timer.mark("assemble");
+    GPB_TRY(launch_assemble_train(cp, c->x, n, npad, c->has_noise ? c->noise : nullptr,
+                                  c->has_ycov ? c->ycov : nullptr, K, npad, 0, c->s));
+    c->timer.mark("potrf");
+    GPB_TRY(potrf_lower(K, npad, npad, ws_of(c, dinv), c->s));
+    c->timer.mark("solve");
+    GPB_TRY(launch_residual(mp, c->x, c->y, n, npad, c->vec, mu_out, c->s));
+    GPB_CUDA(cudaMemcpyAsync(c->resid, c->vec, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+    GPB_TRY(trsv_lower_fwd(K, npad, npad, dinv, c->vec, c->s));
+    if (want_alpha) {
+        GPB_CUDA(cudaMemcpyAsync(c->vec, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+        GPB_TRY(trsv_lower_bwd(K, npad, npad, dinv, c->vec, c->s));
+        GPB_CUDA(cudaMemcpyAsync(alpha_out, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+    }
+    GPB_CUDA(cudaMemcpyAsync(info_host, c->info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s));
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* gpb_last_error(void) { return g_last_error.c_str(); }
+
+int gpb_device_count(int* count) {
+    GPB_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int64_t gpb_launch_count(void) { return launch_count(); }
+double gpb_gemm_flops(void) { return gemm_flops_issued(); }
+
+int gpb_ctx_create(int device, gpb_ctx** out) {
+    int count = 0;
+    GPB_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) {
+        set_error("gpb_ctx_create: no such CUDA device " + std::to_string(device) + " (visible: " +
+                  std::to_string(count) + "); this library has no CPU fallback");
+        return -2;
+    }
+    GPB_CUDA(cudaSetDevice(device));
+    gpb_ctx* c = new gpb_ctx();
+    c->device = device;
+    GPB_CUDA(cudaStreamCreateWithFlags(&c->s, cudaStreamNonBlocking));
+    c->timer.s = c->s;
+    *out = c;
+    return 0;
+}
+
+void gpb_ctx_destroy(gpb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->s);
+    double* ptrs[] = {c->x, c->y, c->noise, c->ycov, c->theta_dev, c->Lfit, c->dinv_fit, c->alpha, c->mu, c->Kwork,
+                      c->dinv_work, c->W, c->Kinv, c->partials, c->grad_dev, c->vec, c->resid, c->alpha_work, c->scal,
+                      c->tmp, c->S, c->dots, c->G, c->qbuf, c->o1, c->o2, c->o3, c->R_dev};
+    for (double* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->info_dev) cudaFree(c->info_dev);
+    c->timer.reset();
+    cudaStreamDestroy(c->s);
+    delete c;
+}
+
+int gpb_set_data(gpb_ctx* c, const double* x, int64_t n, int d, const double* y, const double* noise_var,
+                 const double* y_cov) {
+    GPB_TRY(use(c));
+    if (n <= 0 || d <= 0 || d > MAX_DIM) {
+        set_error("gpb_set_data: need n > 0 and 1 <= d <= " + std::to_string(MAX_DIM));
+        return -2;
+    }
+    for (double** p : {&c->x, &c->y, &c->noise, &c->ycov}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    c->n = n;
+    c->d = d;
+    c->npad = round_up(n, NB);
+    c->fitted = false;
+    const size_t np = (size_t)c->npad;
+    GPB_CUDA(cudaMalloc(&c->x, sizeof(double) * np * d));
+    GPB_CUDA(cudaMalloc(&c->y, sizeof(double) * np));
+    GPB_CUDA(cudaMemset(c->x, 0, sizeof(double) * np * d));
+    GPB_CUDA(cudaMemset(c->y, 0, sizeof(double) * np));
+    GPB_CUDA(cudaMemcpy(c->x, x, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+    GPB_CUDA(cudaMemcpy(c->y, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+    c->has_noise = noise_var != nullptr;
+    if (noise_var) {
+        GPB_CUDA(cudaMalloc(&c->noise, sizeof(double) * np));
+        GPB_CUDA(cudaMemset(c->noise, 0, sizeof(double) * np));
+        GPB_CUDA(cudaMemcpy(c->noise, noise_var, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    c->has_ycov = y_cov != nullptr;
+    if (y_cov) {
+        GPB_CUDA(cudaMalloc(&c->ycov, sizeof(double) * (size_t)n * n));
+        GPB_CUDA(cudaMemcpy(c->ycov, y_cov, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    }
+    // column means of the training inputs (mean.py:59, 92), numpy pairwise order is not reproduced:
+    // plain left-to-right accumulation in long double, rounded once
+    for (int k = 0; k < d; ++k) {
+        long double acc = 0.0L;
+        for (int64_t i = 0; i < n; ++i) acc += x[i * d + k];
+        c->xbar[k] = (double)(acc / (long double)n);
+    }
+    if (c->model_set) {  // Hetero parameter count follows n
+        int off = 0;
+        for (int i = 0; i < c->ncomp; ++i) {
+            c->theta_off[i] = off;
+            off += n_cov_params(c->kinds[i], c->n, c->d);
+        }
+        c->n_cov = off;
+        c->n_mean = c->mean_kind == MEAN_CONST ? 1 : (c->mean_kind == MEAN_LINEAR ? 1 + d : 1 + 2 * d);
+    }
+    return 0;
+}
+
+int gpb_set_model(gpb_ctx* c, const int* cov_kinds, int ncomp, int mean_kind) {
+    GPB_TRY(use(c));
+    if (ncomp < 1 || ncomp > MAX_COMP) {
+        set_error("gpb_set_model: 1.." + std::to_string(MAX_COMP) + " covariance components supported");
+        return -2;
+    }
+    if (c->n == 0) {
+        set_error("gpb_set_model: call gpb_set_data first");
+        return -2;
+    }
+    int off = 0, n_hetero = 0;
+    for (int i = 0; i < ncomp; ++i) {
+        if (cov_kinds[i] < COV_SE || cov_kinds[i] > COV_HETERO) {
+            set_error("gpb_set_model: unknown covariance kind");
+            return -2;
+        }
+        n_hetero += cov_kinds[i] == COV_HETERO;
+        c->kinds[i] = cov_kinds[i];
+        c->theta_off[i] = off;
+        off += n_cov_params(cov_kinds[i], c->n, c->d);
+    }
+    if (n_hetero > 1) {
+        set_error("gpb_set_model: at most one HeteroscedasticNoise component");
+        return -2;
+    }
+    if (mean_kind < MEAN_CONST || mean_kind > MEAN_QUADRATIC) {
+        set_error("gpb_set_model: unknown mean kind");
+        return -2;
+    }
+    c->ncomp = ncomp;
+    c->n_cov = off;
+    c->mean_kind = mean_kind;
+    c->n_mean = mean_kind == MEAN_CONST ? 1 : (mean_kind == MEAN_LINEAR ? 1 + c->d : 1 + 2 * c->d);
+    c->model_set = true;
+    c->fitted = false;
+    return 0;
+}
+
+int gpb_num_hyperpars(gpb_ctx* c, int* n_mean, int* n_cov) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_model(c));
+    *n_mean = c->n_mean;
+    *n_cov = c->n_cov;
+    return 0;
+}
+
+int gpb_build_covariance(gpb_ctx* c, const double* theta_cov, int add_sig, double* K_out) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_model(c));
+    CovParams cp;
+    GPB_TRY(make_cov_params(c, theta_cov, cp));
+    const size_t np = (size_t)c->npad;
+    GPB_TRY(ensure(c->Kwork, c->Kwork_cap, sizeof(double) * np * np));
+    GPB_TRY(launch_assemble_train(cp, c->x, (int)c->n, (int)c->npad, (add_sig && c->has_noise) ? c->noise : nullptr,
+                                  (add_sig && c->has_ycov) ? c->ycov : nullptr, c->Kwork, c->npad, 1, c->s));
+    GPB_CUDA(cudaMemcpy2DAsync(K_out, sizeof(double) * c->n, c->Kwork, sizeof(double) * np, sizeof(double) * c->n,
+                               c->n, cudaMemcpyDeviceToHost, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
+}
+
+int gpb_covariance_and_gradients(gpb_ctx* c, const double* theta_cov, double* K_out, double* dK_out) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_model(c));
+    CovParams cp;
+    GPB_TRY(make_cov_params(c, theta_cov, cp));
+    const size_t plane = (size_t)c->n * c->n;
+    double *dK = nullptr, *K = nullptr;
+    GPB_CUDA(cudaMalloc(&K, sizeof(double) * plane));
+    GPB_CUDA(cudaMalloc(&dK, sizeof(double) * plane * c->n_cov));
+    int r = launch_assemble_grads(cp, c->x, (int)c->n, K, dK, c->s);
+    if (r == 0) {
+        cudaMemcpyAsync(K_out, K, sizeof(double) * plane, cudaMemcpyDeviceToHost, c->s);
+        cudaMemcpyAsync(dK_out, dK, sizeof(double) * plane * c->n_cov, cudaMemcpyDeviceToHost, c->s);
+    }
+    cudaError_t e = cudaStreamSynchronize(c->s);
+    cudaFree(K);
+    cudaFree(dK);
+    if (r) return r;
+    GPB_CUDA(e);
+    return 0;
+}
+
+int gpb_cross_covariance(gpb_ctx* c, const double* u, int64_t m, const double* v, int64_t n, const double* theta_cov,
+                         double* out) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_model(c));
+    if (m == 0 || n == 0) return 0;
+    CovParams cp;
+    GPB_TRY(make_cov_params(c, theta_cov, cp));
+    double *du = nullptr, *dv = nullptr, *dout = nullptr;
+    GPB_CUDA(cudaMalloc(&du, sizeof(double) * m * c->d));
+    GPB_CUDA(cudaMalloc(&dv, sizeof(double) * n * c->d));
+    GPB_CUDA(cudaMalloc(&dout, sizeof(double) * m * n));
+    cudaMemcpyAsync(du, u, sizeof(double) * m * c->d, cudaMemcpyHostToDevice, c->s);
+    cudaMemcpyAsync(dv, v, sizeof(double) * n * c->d, cudaMemcpyHostToDevice, c->s);
+    int r = launch_cross_cov(cp, du, (int)m, dv, (int)n, dout, n, c->s);
+    if (r == 0) cudaMemcpyAsync(out, dout, sizeof(double) * m * n, cudaMemcpyDeviceToHost, c->s);
+    cudaError_t e = cudaStreamSynchronize(c->s);
+    cudaFree(du);
+    cudaFree(dv);
+    cudaFree(dout);
+    if (r) return r;
+    GPB_CUDA(e);
+    return 0;
+}
+
+int gpb_factor(gpb_ctx* c, const double* theta, int* info) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_model(c));
+    c->timer.reset();
+    const size_t np = (size_t)c->npad;
+    GPB_TRY(ensure_linalg_ws(c));
+    GPB_TRY(ensure(c->Lfit, c->Lfit_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->alpha, c->alpha_cap, sizeof(double) * np));
+    GPB_TRY(ensure(c->mu, c->mu_cap, sizeof(double) * np));
+    c->fitted = false;
+    GPB_TRY(make_cov_params(c, theta + c->n_mean, c->cp_fit));
+    make_mean_params(c, theta, c->mp_fit);
+    int info_h = 0;
+    GPB_TRY(assemble_and_factor(c, c->cp_fit, c->mp_fit, c->Lfit, c->dinv_fit, c->mu, true, c->alpha, &info_h));
+    c->timer.mark("end");
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    *info = info_h;
+    if (info_h == 0) {
+        c->theta_fit.assign(theta, theta + c->n_mean + c->n_cov);
+        c->fitted = true;
+    }
+    return 0;
+}
+
+int gpb_get(gpb_ctx* c, int which, double* out) {
+    GPB_TRY(use(c));
+    if (!c->fitted) {
+        set_error("gpb_get: no fitted state (call gpb_factor)");
+        return -2;
+    }
+    const size_t np = (size_t)c->npad;
+    const int64_t n = c->n;
+    if (which == GPB_GET_ALPHA || which == GPB_GET_MU) {
+        GPB_CUDA(cudaMemcpyAsync(out, which == GPB_GET_ALPHA ? c->alpha : c->mu, sizeof(double) * n,
+                                 cudaMemcpyDeviceToHost, c->s));
+        GPB_CUDA(cudaStreamSynchronize(c->s));
+        return 0;
+    }
+    if (which == GPB_GET_L) {
+        GPB_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n, c->Lfit, sizeof(double) * np, sizeof(double) * n, n,
+                                   cudaMemcpyDeviceToHost, c->s));
+        GPB_CUDA(cudaStreamSynchronize(c->s));
+        for (int64_t i = 0; i < n; ++i)  // numpy.linalg.cholesky returns zeros above the diagonal
+            for (int64_t j = i + 1; j < n; ++j) out[i * n + j] = 0.0;
+        return 0;
+    }
+    if (which == GPB_GET_K_XX) return gpb_build_covariance(c, c->theta_fit.data() + c->n_mean, 1, out);
+    set_error("gpb_get: unknown selector");
+    return -2;
+}
+
+int gpb_lml(gpb_ctx* c, const double* theta, double* lml, int* info) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_model(c));
+    c->timer.reset();
+    const size_t np = (size_t)c->npad;
+    GPB_TRY(ensure_linalg_ws(c));
+    GPB_TRY(ensure(c->Kwork, c->Kwork_cap, sizeof(double) * np * np));
+    CovParams cp;
+    MeanParams mp;
+    GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
+    make_mean_params(c, theta, mp);
+    int info_h = 0;
+    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, false, nullptr, &info_h));
+    // -0.5 v.v - sum log L_ii   (regression.py:538-539)
+    GPB_TRY(launch_logdet_dot(c->Kwork, c->npad, c->vec + c->npad, c->vec + c->npad, (int)c->n, c->scal, c->s));
+    double sc[2];
+    GPB_CUDA(cudaMemcpyAsync(sc, c->scal, sizeof(sc), cudaMemcpyDeviceToHost, c->s));
+    c->timer.mark("end");
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    *info = info_h;
+    *lml = -0.5 * sc[1] - sc[0];
+    return 0;
+}
+
+int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int* info) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_model(c));
+    c->timer.reset();
+    const size_t np = (size_t)c->npad;
+    const int npad = (int)c->npad, n = (int)c->n, nt = c->n_mean + c->n_cov;
+    GPB_TRY(ensure_linalg_ws(c));
+    GPB_TRY(ensure(c->Kwork, c->Kwork_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->W, c->W_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->Kinv, c->Kinv_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->partials, c->partials_cap, trace_partials_size(npad)));
+    GPB_TRY(ensure(c->grad_dev, c->grad_cap, sizeof(double) * (nt + 2)));
+    CovParams cp;
+    MeanParams mp;
+    GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
+    make_mean_params(c, theta, mp);
+    int info_h = 0;
+    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, true, c->alpha_work, &info_h));
+    // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
+    GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
+    c->timer.mark("trtri");
+    GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+    GPB_TRY(trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s));
+    c->timer.mark("lauum");
+    GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+    c->timer.mark("trace");
+    GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2), c->s));
+    GPB_TRY(launch_lml_grad(cp, mp, c->n_mean, c->x, n, npad, c->alpha_work, c->Kinv, npad, c->partials, c->grad_dev,
+                            c->s));
+    double sc[2];
+    GPB_CUDA(cudaMemcpyAsync(sc, c->scal, sizeof(sc), cudaMemcpyDeviceToHost, c->s));
+    GPB_CUDA(cudaMemcpyAsync(grad, c->grad_dev, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->s));
+    c->timer.mark("end");
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    *info = info_h;
+    *lml = -0.5 * sc[1] - sc[0];
+    return 0;
+}
+
+int gpb_loo(gpb_ctx* c, const double*, double*, double*, int*) {
+    GPB_TRY(use(c));
+    set_error("gpb_loo: leave-one-out objective is not implemented yet (SURVEY.md section 8f rank 2)");
+    return -3;
+}
+int gpb_loo_predictions(gpb_ctx* c, double*, double*) {
+    GPB_TRY(use(c));
+    set_error("gpb_loo_predictions: not implemented yet (SURVEY.md section 8f rank 2)");
+    return -3;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ predict family
+namespace {
+
+enum PredMode { PM_PREDICT, PM_GRADIENT, PM_SPATIAL, PM_EI };
+
+bool is_pure_se(const gpb_ctx* c) { return c->ncomp == 1 && c->kinds[0] == COV_SE; }
+
+int64_t chunk_rows(const gpb_ctx* c) {
+    // rows of the stacked cross-covariance per pass: one full wave of 2 CTAs/SM on the 128-wide leaf
+    // solves (148 * 128) when N is large, more when the rows are short
+    const int64_t base = 148 * 128;
+    if (c->npad >= 8192) return base;
+    if (c->npad >= 2048) return base * 2;
+    return base * 4;
+}
+
+// Shared driver: out pointers are DEVICE pointers sized for all m queries.
+//   PM_PREDICT : o_a = mu (m), o_b = sig (m)
+//   PM_GRADIENT: o_a = mean (m x d), o_b = cov (m x d x d)
+//   PM_SPATIAL : o_a = dmu (m x d), o_b = dvar (m x d)
+//   PM_EI      : o_a = value (m), o_b = grad (m x d) or nullptr; ei_mode, y_max
+int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, double* o_a, double* o_b, int ei_mode,
+                   double y_max) {
+    const int npad = (int)c->npad, n = (int)c->n, d = c->d;
+    const bool stacked = mode == PM_GRADIENT || mode == PM_SPATIAL || (mode == PM_EI && ei_mode == GPB_EI_NEG_LOG_GRAD);
+    const int ns = stacked ? d + 1 : 1;
+    const int64_t rc = chunk_rows(c);
+    const int64_t qc = std::max<int64_t>(1, rc / ns);  // queries per chunk
+    const int64_t qmax = std::min<int64_t>(qc, m);
+    const int64_t rows_cap = round_up(qmax * ns, 128);
+    GPB_TRY(ensure(c->S, c->S_cap, sizeof(double) * (size_t)rows_cap * npad));
+    GPB_TRY(ensure(c->dots, c->dots_cap, sizeof(double) * (size_t)rows_cap));
+    GPB_TRY(ensure(c->G, c->G_cap, sizeof(double) * (size_t)qmax * ns * ns));
+    if (mode == PM_EI) {
+        GPB_TRY(ensure(c->o1, c->o1_cap, sizeof(double) * (size_t)qmax));          // mu
+        GPB_TRY(ensure(c->o2, c->o2_cap, sizeof(double) * (size_t)qmax));          // sig
+        if (stacked) GPB_TRY(ensure(c->o3, c->o3_cap, sizeof(double) * (size_t)qmax * d * 2));  // dmu | dvar
+    }
+    double kqq = 0.0;
+    for (int i = 0; i < c->ncomp; ++i)
+        if (c->kinds[i] <= COV_RQ) kqq += c->cp_fit.amp2[i];
+    if (mode == PM_GRADIENT) {  // R = (a / l)^2  (covariance.py:266)
+        GPB_TRY(ensure(c->R_dev, c->R_cap, sizeof(double) * MAX_DIM));
+        double R[MAX_DIM];
+        for (int k = 0; k < d; ++k) R[k] = c->cp_fit.amp2[0] * c->cp_fit.inv_l2[0][k];
+        GPB_CUDA(cudaMemcpyAsync(c->R_dev, R, sizeof(double) * d, cudaMemcpyHostToDevice, c->s));
+        GPB_CUDA(cudaStreamSynchronize(c->s));
+    }
+    const LinalgWs ws = ws_of(c, c->dinv_fit);
+    for (int64_t q0 = 0; q0 < m; q0 += qc) {
+        const int mq = (int)std::min<int64_t>(qc, m - q0);
+        const int rows = mq * ns, rows_pad = (int)round_up(rows, 128);
+        const double* qp = q_dev + q0 * d;
+        c->timer.mark("cross_cov");
+        GPB_TRY(launch_cross_stack(c->cp_fit, qp, mq, ns, c->x, n, npad, c->S, npad, c->s));
+        if (rows_pad > rows)
+            GPB_CUDA(cudaMemsetAsync(c->S + (size_t)rows * npad, 0, sizeof(double) * (size_t)(rows_pad - rows) * npad,
+                                     c->s));
+        c->timer.mark("mean_dot");
+        GPB_TRY(launch_row_dot(c->S, npad, rows, npad, c->alpha, c->dots, c->s));
+        c->timer.mark("trsm");
+        GPB_TRY(trsm_right_lt(c->S, npad, rows_pad, c->Lfit, npad, npad, 0, ws, c->s));
+        c->timer.mark("gram");
+        GPB_TRY(launch_row_gram(c->S, npad, mq, ns, npad, c->G, c->s));
+        c->timer.mark("finalize");
+        switch (mode) {
+            case PM_PREDICT:
+                GPB_TRY(launch_finalize_predict(c->mp_fit, qp, mq, ns, c->dots, c->G, kqq, o_a + q0, o_b + q0, c->s));
+                break;
+            case PM_GRADIENT:
+                GPB_TRY(launch_finalize_gradient(c->dots, c->G, mq, d, c->R_dev, o_a + q0 * d, o_b + q0 * d * d, c->s));
+                break;
+            case PM_SPATIAL:
+                GPB_TRY(launch_finalize_spatial(c->dots, c->G, mq, d, o_a + q0 * d, o_b + q0 * d, c->s));
+                break;
+            case PM_EI:
+                GPB_TRY(launch_finalize_predict(c->mp_fit, qp, mq, ns, c->dots, c->G, kqq, c->o1, c->o2, c->s));
+                if (stacked)
+                    GPB_TRY(launch_finalize_spatial(c->dots, c->G, mq, d, c->o3, c->o3 + (size_t)qmax * d, c->s));
+                GPB_TRY(launch_ei(c->o1, c->o2, stacked ? c->o3 : nullptr, stacked ? c->o3 + (size_t)qmax * d : nullptr,
+                                  mq, d, y_max, ei_mode, o_a + q0, stacked ? o_b + q0 * d : nullptr, c->s));
+                break;
+        }
+    }
+    c->timer.mark("end");
+    return 0;
+}
+
+int need_fit(gpb_ctx* c) {
+    if (!c->fitted) {
+        set_error("no fitted state: call gpb_factor first");
+        return -2;
+    }
+    return 0;
+}
+
+// host-buffer wrapper: uploads q, runs the driver into device outputs, downloads na/nb doubles per query
+int predict_host(gpb_ctx* c, const double* q, int64_t m, PredMode mode, double* a, int64_t na, double* b, int64_t nb,
+                 int ei_mode = 0, double y_max = 0.0) {
+    if (m == 0) return 0;
+    c->timer.reset();
+    c->timer.mark("h2d");
+    GPB_TRY(ensure(c->qbuf, c->qbuf_cap, sizeof(double) * (size_t)m * (c->d + na + nb)));
+    double* qd = c->qbuf;
+    double* ad = qd + (size_t)m * c->d;
+    double* bd = ad + (size_t)m * na;
+    GPB_CUDA(cudaMemcpyAsync(qd, q, sizeof(double) * m * c->d, cudaMemcpyHostToDevice, c->s));
+    GPB_TRY(predict_driver(c, qd, m, mode, ad, nb ? bd : nullptr, ei_mode, y_max));
+    c->timer.marks.back().first = "d2h";
+    GPB_CUDA(cudaMemcpyAsync(a, ad, sizeof(double) * m * na, cudaMemcpyDeviceToHost, c->s));
+    if (nb && b) GPB_CUDA(cudaMemcpyAsync(b, bd, sizeof(double) * m * nb, cudaMemcpyDeviceToHost, c->s));
+    c->timer.mark("end");
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpb_predict(gpb_ctx* c, const double* q, int64_t m, double* mu, double* sig) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_fit(c));
+    return predict_host(c, q, m, PM_PREDICT, mu, 1, sig, 1);
+}
+
+int gpb_predict_dev(gpb_ctx* c, const double* q_dev, int64_t m, double* mu_dev, double* sig_dev) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_fit(c));
+    if (m == 0) return 0;
+    c->timer.reset();
+    GPB_TRY(predict_driver(c, q_dev, m, PM_PREDICT, mu_dev, sig_dev, 0, 0.0));
+    return 0;  // asynchronous on the context stream; gpb_sync() to wait
+}
+
+int gpb_gradient(gpb_ctx* c, const double* q, int64_t m, double* mean, double* cov) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_fit(c));
+    if (!is_pure_se(c)) {
+        set_error("gradient terms are only available for the SquaredExponential covariance (covariance.py:38-44)");
+        return -3;
+    }
+    return predict_host(c, q, m, PM_GRADIENT, mean, c->d, cov, (int64_t)c->d * c->d);
+}
+
+int gpb_spatial_derivatives(gpb_ctx* c, const double* q, int64_t m, double* dmu, double* dvar) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_fit(c));
+    if (!is_pure_se(c)) {
+        set_error("gradient terms are only available for the SquaredExponential covariance (covariance.py:38-44)");
+        return -3;
+    }
+    return predict_host(c, q, m, PM_SPATIAL, dmu, c->d, dvar, c->d);
+}
+
+int gpb_expected_improvement(gpb_ctx* c, const double* q, int64_t m, double y_max, int mode, double* out,
+                             double* grad_or_null, int64_t* argmax_or_null) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_fit(c));
+    if (mode == GPB_EI_NEG_LOG_GRAD && !is_pure_se(c)) {
+        set_error("gradient terms are only available for the SquaredExponential covariance (covariance.py:38-44)");
+        return -3;
+    }
+    const bool g = mode == GPB_EI_NEG_LOG_GRAD;
+    GPB_TRY(predict_host(c, q, m, PM_EI, out, 1, g ? grad_or_null : nullptr, g ? c->d : 0, mode, y_max));
+    if (argmax_or_null && m > 0) {
+        // best candidate: largest EI, i.e. smallest -ln EI
+        int64_t best = 0;
+        for (int64_t i = 1; i < m; ++i)
+            if (mode == GPB_EI_VALUE ? out[i] > out[best] : out[i] < out[best]) best = i;
+        *argmax_or_null = best;
+    }
+    return 0;
+}
+
+int gpb_posterior(gpb_ctx* c, const double* q, int64_t m, double* mu, double* sigma) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_fit(c));
+    if (m == 0) return 0;
+    c->timer.reset();
+    const int npad = (int)c->npad, n = (int)c->n, d = c->d;
+    const int mp = (int)round_up(m, 128);
+    GPB_TRY(ensure(c->S, c->S_cap, sizeof(double) * (size_t)mp * npad));
+    GPB_TRY(ensure(c->dots, c->dots_cap, sizeof(double) * (size_t)mp));
+    GPB_TRY(ensure(c->qbuf, c->qbuf_cap, sizeof(double) * ((size_t)m * (d + 1) + (size_t)mp * mp)));
+    double* qd = c->qbuf;
+    double* mud = qd + (size_t)m * d;
+    double* sg = mud + m;
+    if ((reinterpret_cast<uintptr_t>(sg) & 15) != 0) sg += 1;  // 16-byte alignment for the GEMM epilogue
+    GPB_CUDA(cudaMemcpyAsync(qd, q, sizeof(double) * m * d, cudaMemcpyHostToDevice, c->s));
+    GPB_TRY(launch_cross_stack(c->cp_fit, qd, (int)m, 1, c->x, n, npad, c->S, npad, c->s));
+    if (mp > m) GPB_CUDA(cudaMemsetAsync(c->S + (size_t)m * npad, 0, sizeof(double) * (size_t)(mp - m) * npad, c->s));
+    GPB_TRY(launch_row_dot(c->S, npad, (int)m, npad, c->alpha, c->dots, c->s));
+    GPB_TRY(launch_finalize_predict(c->mp_fit, qd, (int)m, 1, c->dots, nullptr, 0.0, mud, nullptr, c->s));
+    GPB_CUDA(cudaMemcpyAsync(mu, mud, sizeof(double) * m, cudaMemcpyDeviceToHost, c->s));
+    if (sigma) {
+        GPB_TRY(trsm_right_lt(c->S, npad, mp, c->Lfit, npad, npad, 0, ws_of(c, c->dinv_fit), c->s));
+        GPB_CUDA(cudaMemsetAsync(sg, 0, sizeof(double) * (size_t)mp * mp, c->s));
+        GPB_TRY(launch_cross_cov(c->cp_fit, qd, (int)m, qd, (int)m, sg, mp, c->s));
+        GemmArgs g{mp, mp, npad, c->S, npad, c->S, npad, sg, mp, sg, mp, nullptr, 0, -1.0, 1.0, GEMM_FULL};
+        GPB_TRY(gemm_nt(g, c->s));
+        GPB_CUDA(cudaMemcpy2DAsync(sigma, sizeof(double) * m, sg, sizeof(double) * mp, sizeof(double) * m, m,
+                                   cudaMemcpyDeviceToHost, c->s));
+    }
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
+}
+
+int gpb_timers(gpb_ctx* c, char* name_buf, int name_buf_len, double* ms, int max_entries, int* n_entries) {
+    GPB_TRY(use(c));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    std::vector<std::pair<std::string, double>> acc;
+    auto& mk = c->timer.marks;
+    for (size_t i = 0; i + 1 < mk.size(); ++i) {
+        float t = 0.f;
+        GPB_CUDA(cudaEventElapsedTime(&t, mk[i].second, mk[i + 1].second));
+        bool found = false;
+        for (auto& a : acc)
+            if (a.first == mk[i].first) {
+                a.second += t;
+                found = true;
+                break;
+            }
+        if (!found) acc.emplace_back(mk[i].first, (double)t);
+    }
+    std::string names;
+    int k = 0;
+    for (auto& a : acc) {
+        if (k >= max_entries) break;
+        if (k) names += ";";
+        names += a.first;
+        ms[k++] = a.second;
+    }
+    if ((int)names.size() + 1 > name_buf_len) {
+        set_error("gpb_timers: name buffer too small");
+        return -2;
+    }
+    std::memcpy(name_buf, names.c_str(), names.size() + 1);
+    *n_entries = k;
+    return 0;
+}
+
+int gpb_dev_alloc(gpb_ctx* c, int64_t n_doubles, double** out_dev) {
+    GPB_TRY(use(c));
+    GPB_CUDA(cudaMalloc(out_dev, sizeof(double) * (size_t)n_doubles));
+    return 0;
+}
+int gpb_dev_free(gpb_ctx* c, double* p) {
+    GPB_TRY(use(c));
+    GPB_CUDA(cudaFree(p));
+    return 0;
+}
+int gpb_dev_upload(gpb_ctx* c, double* dst, const double* src, int64_t n) {
+    GPB_TRY(use(c));
+    GPB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
+}
+int gpb_dev_download(gpb_ctx* c, double* dst, const double* src, int64_t n) {
+    GPB_TRY(use(c));
+    GPB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
+}
+int gpb_sync(gpb_ctx* c) {
+    GPB_TRY(use(c));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
+}
+
+}  // extern "C"

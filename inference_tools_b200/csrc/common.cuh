@@ -1,0 +1,91 @@
+// Shared declarations for the gpb200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace gpb {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const std::string& msg);  // api.cu; message returned by gpb_last_error()
+
+#define GPB_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::gpb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +       \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                 \
+            return -1;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+#define GPB_TRY(expr)                    \
+    do {                                 \
+        int _r = (expr);                 \
+        if (_r != 0) return _r;          \
+    } while (0)
+
+// ---------------------------------------------------------------- blocking constants
+constexpr int NB = 128;          // diagonal-block / padding granularity of every dense matrix
+constexpr int MAX_DIM = 8;       // spatial dimensions held in constant-size kernel parameter structs
+constexpr int MAX_COMP = 4;      // covariance components in a composite kernel
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------- GEMM (gemm_dmma.cu)
+// D = alpha * A * B^T + beta * C on logical operands A(m,k) [M x K], B(n,k) [N x K]; C/D/D2 are
+// row-major M x N.  Storage of the operands is selectable:
+//   a_kmajor: A stored row-major M x K (k contiguous), else stored row-major K x M (m contiguous)
+//   b_kmajor: B stored row-major N x K (k contiguous), else stored row-major K x N (n contiguous)
+// M % 128 == 0, N % 64 == 0, K % 16 == 0.  Triangular operands are exploited through per-tile
+// k-ranges; the skipped parts must still hold finite values only where they are read (they are
+// not read at all for whole skipped k-tiles; inside a diagonal tile zeros must be stored).
+enum GemmFlags : int {
+    GEMM_FULL = 0,
+    GEMM_LOWER = 1,    // only tiles that intersect the lower triangle (row >= col) are computed
+    GEMM_TRIK_A = 2,   // A(m,k) == 0 for k < m  -> k starts at the tile's first row
+    GEMM_TRIK_B = 4,   // B(n,k) == 0 for k < n  -> k starts at the tile's first column
+    GEMM_TRIL_B = 8,   // B(n,k) == 0 for k > n  -> k ends after the tile's last column
+    GEMM_TRIL_A = 16,  // A(m,k) == 0 for k > m  -> k ends after the tile's last row
+    GEMM_A_MMAJOR = 32,  // A stored K x M
+    GEMM_B_NMAJOR = 64   // B stored K x N
+};
+struct GemmArgs {
+    int M, N, K;
+    const double* A; int64_t lda;
+    const double* B; int64_t ldb;
+    const double* C; int64_t ldc;   // may be nullptr when beta == 0
+    double* D; int64_t ldd;
+    double* D2; int64_t ldd2;       // optional second copy of the output (nullptr = off)
+    double alpha, beta;
+    int flags;
+};
+int gemm_nt(const GemmArgs& a, cudaStream_t s);
+int64_t gemm_launch_count();   // number of GEMM kernel launches so far (bench "gpu_launches")
+void count_launch(int n = 1);  // every other kernel launch is counted through this
+int64_t launch_count();
+
+// ---------------------------------------------------------------- model description (kernels.cu)
+enum CovKind : int { COV_SE = 0, COV_RQ = 1, COV_WHITE = 2, COV_HETERO = 3 };
+enum MeanKind : int { MEAN_CONST = 0, MEAN_LINEAR = 1, MEAN_QUADRATIC = 2 };
+
+// Hyper-parameters already mapped from log space on the host (covariance.py:248-249, 344-346).
+struct CovParams {
+    int ncomp, d;
+    int kind[MAX_COMP];
+    int theta_off[MAX_COMP];             // offset of the component's first parameter inside theta_cov
+    double amp2[MAX_COMP];               // a^2 (SE/RQ) or sigma^2 (WHITE)
+    double rq_alpha[MAX_COMP];           // RQ shape parameter
+    double inv_l2[MAX_COMP][MAX_DIM];    // 1 / l_k^2
+    const double* hetero_log_sigma;      // device pointer (N entries) for COV_HETERO, else nullptr
+    double jitter;                       // 1e-12 (covariance.py:221, 318)
+};
+struct MeanParams {
+    int kind, d;
+    double c0;
+    double lin[MAX_DIM], quad[MAX_DIM], xbar[MAX_DIM];
+};
+
+}  // namespace gpb

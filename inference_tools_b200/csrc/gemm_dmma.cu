@@ -1,0 +1,265 @@
+// FP64 tensor-core GEMM for sm_100a:  D = alpha * A * B^T + beta * C  (row-major, both operands K-contiguous).
+//
+// Blackwell's tcgen05/TMEM path has no FP64 kind; FP64 tensor work is the warp-level
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), measured at 37.1 TFLOP/s on this pool's B200s
+// (profiles/fp64_peak_r1.json) -- the same rate as the DFMA pipe but at 1/8 of the register-file and
+// shared-memory traffic per flop, which is what lets a tile kernel sit on the pipe limit.
+//
+// Tiling: CTA tile 128 x 64, 4 warps (2 x 2), warp tile 64 x 32 = 8 x 4 DMMA tiles (64 accumulator
+// doubles per thread), BK = 16, 3-stage cp.async pipeline, 2 CTAs resident per SM so one CTA's
+// epilogue (C read-modify-write) overlaps the other's main loop.  Shared-memory rows are padded to
+// 20 doubles: the fragment read (row g, column t) then hits bank pairs (4g + t) mod 16 -- conflict free.
+//
+// Every blocked driver in this library (Cholesky trailing update, panel solve through the inverted
+// diagonal block, triangular inverse, K^-1 = Z Z^T, batched predict solve) is expressed in this one
+// NT form; triangular operands are handled by per-tile k-ranges (GEMM_TRIK_*), symmetric outputs by
+// enumerating lower tiles only (GEMM_LOWER).
+#include "common.cuh"
+#include <algorithm>
+
+namespace gpb {
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int LDSK = 20;  // padded smem row length (doubles)
+constexpr int STAGES = 3;
+constexpr int THREADS = 128;
+constexpr int LDSM_A = BM + 4;  // m-major A tile: 16 rows of 132 doubles (132 mod 16 == 4 -> conflict free)
+constexpr int LDSM_B = BN + 4;  // n-major B tile: 16 rows of 68 doubles
+constexpr int A_STAGE = BM * LDSK;  // 2560 >= BK * LDSM_A (2112)
+constexpr int B_STAGE = BN * LDSK;  // 1280 >= BK * LDSM_B (1088)
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);  // 92160
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+template <bool AKM, bool BKM>  // operand stored k-major (k contiguous) or not
+__global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, const int tiles_n) {
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * A_STAGE;
+
+    const int tid = threadIdx.x;
+    int bi, bj;
+    if (p.flags & GEMM_LOWER) {
+        // lower tiles enumerated row by row: tile row bi owns bj = 0 .. 2*bi+1  (BM = 2*BN)
+        const int t = blockIdx.x;
+        int r = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (r * (r + 1) > t) --r;
+        while ((r + 1) * (r + 2) <= t) ++r;
+        bi = r;
+        bj = t - r * (r + 1);
+    } else {
+        bi = blockIdx.x / tiles_n;
+        bj = blockIdx.x - bi * tiles_n;
+    }
+    const int row0 = bi * BM, col0 = bj * BN;
+
+    int k_begin = 0, k_end = p.K;
+    if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, row0);
+    if (p.flags & GEMM_TRIK_B) k_begin = max(k_begin, col0);
+    if (p.flags & GEMM_TRIL_B) k_end = min(k_end, col0 + BN);
+    if (p.flags & GEMM_TRIL_A) k_end = min(k_end, row0 + BM);
+    const int KT = (k_end - k_begin) / BK;
+
+    // per-thread 16-byte chunk coordinates of the global -> shared copies
+    const double* Ag;
+    const double* Bg;
+    double *as_w, *bs_w;
+    if (AKM) {  // 128 rows x 8 chunks: thread owns chunk (tid & 7) of rows (tid >> 3) + 16 i
+        Ag = p.A + (int64_t)(row0 + (tid >> 3)) * p.lda + k_begin + (tid & 7) * 2;
+        as_w = As + (tid >> 3) * LDSK + (tid & 7) * 2;
+    } else {    // 16 k-rows x 64 chunks: thread owns chunk (tid & 63) of k-rows (tid >> 6) + 2 i
+        Ag = p.A + (int64_t)(k_begin + (tid >> 6)) * p.lda + row0 + (tid & 63) * 2;
+        as_w = As + (tid >> 6) * LDSM_A + (tid & 63) * 2;
+    }
+    if (BKM) {
+        Bg = p.B + (int64_t)(col0 + (tid >> 3)) * p.ldb + k_begin + (tid & 7) * 2;
+        bs_w = Bs + (tid >> 3) * LDSK + (tid & 7) * 2;
+    } else {    // 16 k-rows x 32 chunks: thread owns chunk (tid & 31) of k-rows (tid >> 5) + 4 i
+        Bg = p.B + (int64_t)(k_begin + (tid >> 5)) * p.ldb + col0 + (tid & 31) * 2;
+        bs_w = Bs + (tid >> 5) * LDSM_B + (tid & 31) * 2;
+    }
+
+    auto load_stage = [&](int stage, int kt) {
+        double* as = as_w + stage * A_STAGE;
+        if (AKM) {
+            const double* a = Ag + kt * BK;
+#pragma unroll
+            for (int i = 0; i < BM / 16; ++i) cp_async16(as + i * 16 * LDSK, a + (int64_t)i * 16 * p.lda);
+        } else {
+            const double* a = Ag + (int64_t)kt * BK * p.lda;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp_async16(as + i * 2 * LDSM_A, a + (int64_t)i * 2 * p.lda);
+        }
+        double* bs = bs_w + stage * B_STAGE;
+        if (BKM) {
+            const double* b = Bg + kt * BK;
+#pragma unroll
+            for (int i = 0; i < BN / 16; ++i) cp_async16(bs + i * 16 * LDSK, b + (int64_t)i * 16 * p.ldb);
+        } else {
+            const double* b = Bg + (int64_t)kt * BK * p.ldb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async16(bs + i * 4 * LDSM_B, b + (int64_t)i * 4 * p.ldb);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int g = lane >> 2, t = lane & 3;
+    // fragment read origins: A(row g, k t) / B(col g, k t) of the warp tile
+    const double* as_r = AKM ? As + (wm * 64 + g) * LDSK + t : As + t * LDSM_A + wm * 64 + g;
+    const double* bs_r = BKM ? Bs + (wn * 32 + g) * LDSK + t : Bs + t * LDSM_B + wn * 32 + g;
+    constexpr int A_I = AKM ? 8 * LDSK : 8, A_K = AKM ? 4 : 4 * LDSM_A;   // strides: next 8 rows / next k-step
+    constexpr int B_J = BKM ? 8 * LDSK : 8, B_K = BKM ? 4 : 4 * LDSM_B;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nk = kt + STAGES - 1;
+            if (nk < KT) load_stage(nk % STAGES, nk);
+            cp_async_commit();
+        }
+        const int stage = kt % STAGES;
+        const double* as = as_r + stage * A_STAGE;
+        const double* bs = bs_r + stage * B_STAGE;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = as[i * A_I + ks * A_K];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = bs[j * B_J + ks * B_K];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue straight from the accumulator fragments: each lane owns 2 adjacent columns (16 B), a
+    // quad covers 64 contiguous bytes of a row -> two fully used 32 B sectors per row
+    const double alpha = p.alpha, beta = p.beta;
+    const int r_base = row0 + wm * 64 + g;
+    const int c_base = col0 + wn * 32 + 2 * t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = r_base + 8 * i;
+        double2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j].x = alpha * acc[i][j][0];
+            v[j].y = alpha * acc[i][j][1];
+        }
+        if (beta != 0.0) {
+            double2 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = *reinterpret_cast<const double2*>(p.C + r * p.ldc + c_base + 8 * j);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j].x = fma(beta, c[j].x, v[j].x);
+                v[j].y = fma(beta, c[j].y, v[j].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p.D + r * p.ldd + c_base + 8 * j) = v[j];
+        if (p.D2 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p.D2 + r * p.ldd2 + c_base + 8 * j) = v[j];
+        }
+    }
+}
+
+}  // namespace
+
+static int64_t g_gemm_launches = 0;
+static double g_gemm_flops = 0.0;
+
+int gemm_nt(const GemmArgs& a, cudaStream_t s) {
+    if (a.M <= 0 || a.N <= 0) return 0;
+    if (a.M % BM || a.N % BN || a.K % BK || a.K < 0) {
+        set_error("gemm_nt: M % 128, N % 64, K % 16 must be 0 (got " + std::to_string(a.M) + "," +
+                  std::to_string(a.N) + "," + std::to_string(a.K) + ")");
+        return -2;
+    }
+    using kern_t = void (*)(const GemmArgs, const int);
+    const bool akm = !(a.flags & GEMM_A_MMAJOR), bkm = !(a.flags & GEMM_B_NMAJOR);
+    kern_t kern = akm ? (bkm ? dgemm_kernel<true, true> : dgemm_kernel<true, false>)
+                      : (bkm ? dgemm_kernel<false, true> : dgemm_kernel<false, false>);
+    static bool configured_dev[64][4] = {};
+    int dev = 0;
+    GPB_CUDA(cudaGetDevice(&dev));
+    bool* configured = configured_dev[dev & 63];
+    const int ki = (akm ? 0 : 2) + (bkm ? 0 : 1);
+    if (!configured[ki]) {
+        GPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured[ki] = true;
+    }
+    const int tm = a.M / BM, tn = a.N / BN;
+    int64_t tiles;
+    if (a.flags & GEMM_LOWER) {
+        // rows beyond N/BM*... : tile row bi has min(2*(bi+1), tn) tiles; require square-ish use: N >= M
+        if (a.N < a.M) {
+            set_error("gemm_nt: GEMM_LOWER needs N >= M");
+            return -2;
+        }
+        tiles = (int64_t)tm * (tm + 1);
+    } else {
+        tiles = (int64_t)tm * tn;
+    }
+    kern<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(a, tn);
+    GPB_CUDA(cudaGetLastError());
+    ++g_gemm_launches;
+    count_launch();
+    // algorithmic flops of this launch (2 * 128 * 64 * k-extent per computed tile)
+    if (!(a.flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) {
+        g_gemm_flops += (double)tiles * 2.0 * BM * BN * a.K;
+    } else {
+        double kext = 0.0;
+        for (int bi = 0; bi < tm; ++bi) {
+            const int ntile = (a.flags & GEMM_LOWER) ? 2 * (bi + 1) : tn;
+            for (int bj = 0; bj < ntile; ++bj) {
+                int kb = 0, ke = a.K;
+                if (a.flags & GEMM_TRIK_A) kb = std::max(kb, bi * BM);
+                if (a.flags & GEMM_TRIK_B) kb = std::max(kb, bj * BN);
+                if (a.flags & GEMM_TRIL_B) ke = std::min(ke, bj * BN + BN);
+                if (a.flags & GEMM_TRIL_A) ke = std::min(ke, bi * BM + BM);
+                kext += std::max(0, ke - kb);
+            }
+        }
+        g_gemm_flops += kext * 2.0 * BM * BN;
+    }
+    return 0;
+}
+
+int64_t gemm_launch_count() { return g_gemm_launches; }
+double gemm_flops_issued() { return g_gemm_flops; }
+
+}  // namespace gpb

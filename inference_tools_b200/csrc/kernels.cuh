@@ -1,0 +1,77 @@
+// Launch wrappers of the non-GEMM kernels (kernels.cu, potrf.cu, solve.cu, lml.cu).
+#pragma once
+#include "common.cuh"
+
+namespace gpb {
+
+// ---- kernels.cu : covariance assembly, cross-covariance, row reductions, acquisition
+// K(theta)+diag terms on the padded training grid, lower 128x128 tiles (mirror=1 also fills the upper
+// triangle).  Padded rows/cols (>= n) hold the identity.
+int launch_assemble_train(const CovParams& cp, const double* x, int n, int npad, const double* noise_var,
+                          const double* y_cov, double* K, int64_t ld, int mirror, cudaStream_t s);
+// dK/dtheta_p planes for the covariance_and_gradients API (small N; dense output, np x n x n)
+int launch_assemble_grads(const CovParams& cp, const double* x, int n, double* K, double* dK, cudaStream_t s);
+// generic cross covariance cov(u, v) (covariance.py:240-245, 335-341): out is m x n row-major
+int launch_cross_cov(const CovParams& cp, const double* u, int m, const double* v, int n, double* out, int64_t ld,
+                     cudaStream_t s);
+// stacked cross-covariance rows for a chunk of queries: row q*nstack+0 = k(q, x_j); rows a=1..d (SE only)
+// = ((x_ja - q_a)/l_a^2) k(q, x_j)  (covariance.py:257-266, regression.py:376, 414).  Columns >= n are 0.
+int launch_cross_stack(const CovParams& cp, const double* q, int mq, int nstack, const double* x, int n, int npad,
+                       double* S, int64_t ld, cudaStream_t s);
+// out[r] = sum_j S[r][j] * vec[j]  (one warp per row, fixed-order reduction)
+int launch_row_dot(const double* S, int64_t ld, int rows, int ncols, const double* vec, double* out, cudaStream_t s);
+// G[q][a][b] = sum_j X[q*ns+a][j] X[q*ns+b][j]
+int launch_row_gram(const double* X, int64_t ld, int mq, int nstack, int ncols, double* G, cudaStream_t s);
+// predictive mean/sigma (regression.py:212-216): mu = dot + mean(q); sig = sqrt|kqq - G|
+int launch_finalize_predict(const MeanParams& mp, const double* q, int mq, int nstack, const double* dots,
+                            const double* G, double kqq, double* mu, double* sig, cudaStream_t s);
+// gradient() outputs (regression.py:379-380): mean[q][a] = dots[q*ns+1+a]; cov[q][a][b] = R[b] - G[q][a+1][b+1]
+int launch_finalize_gradient(const double* dots, const double* G, int mq, int d, const double* R_dev, double* mean,
+                             double* cov, cudaStream_t s);
+// spatial_derivatives() outputs (regression.py:413-414): dmu = dots rows a>=1; dvar[q][a] = -2 G[q][0][a+1]
+int launch_finalize_spatial(const double* dots, const double* G, int mq, int d, double* dmu, double* dvar,
+                            cudaStream_t s);
+// ExpectedImprovement (acquisition.py:76-125). mode 0: EI, 1: -ln EI, 2: -ln EI and its gradient
+int launch_ei(const double* mu, const double* sig, const double* dmu, const double* dvar, int m, int d, double y_max,
+              int mode, double* out, double* grad, cudaStream_t s);
+// resid = y - mean(x) (regression.py:243, 538); mu_out optional
+int launch_residual(const MeanParams& mp, const double* x, const double* y, int n, int npad, double* resid,
+                    double* mu_out, cudaStream_t s);
+// small utility kernels
+int launch_transpose_block(const double* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, double scale,
+                           cudaStream_t s);
+int launch_copy2d(const double* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, cudaStream_t s);
+
+// ---- potrf.cu : blocked recursive Cholesky / triangular inverse / triangular solve drivers
+struct LinalgWs {
+    double* dinv;      // npad/NB blocks of NB x NB: inverses of the diagonal blocks of L
+    double* tmp;       // scratch: rows_max x NB panel for the out-of-place leaf solves
+    int64_t tmp_rows;  // capacity of tmp in rows
+    int* info;         // device: 0 or 1-based index of the first non-positive pivot
+};
+int potrf_lower(double* A, int64_t ld, int n, const LinalgWs& ws, cudaStream_t s);
+// X <- X * L^-T  (X: m x n row-major, L: n x n lower with inverted diagonal blocks in ws.dinv + blk0)
+int trsm_right_lt(double* X, int64_t ldx, int m, const double* L, int64_t ldl, int n, int blk0, const LinalgWs& ws,
+                  cudaStream_t s);
+// W = L^-1 (lower, row-major; the strict upper triangle of W must be zero on entry); scratch n/2 x n/2
+int trtri_lower(const double* L, int64_t ldl, double* W, int64_t ldw, int n, int blk0, const LinalgWs& ws,
+                double* scratch, int64_t lds, cudaStream_t s);
+// Kinv(lower tiles) = W^T W
+int lauum_lower(const double* W, int64_t ldw, double* Kinv, int64_t ldk, int n, cudaStream_t s);
+
+// ---- solve.cu : vector solves and reductions
+// v = L^-1 r (fwd) ; a = L^-T v (bwd).  vec holds 2*npad doubles: [0,npad) = right-hand side (destroyed),
+// [npad, 2*npad) = solution.
+int trsv_lower_fwd(const double* L, int64_t ld, int npad, const double* dinv, double* vec, cudaStream_t s);
+int trsv_lower_bwd(const double* L, int64_t ld, int npad, const double* dinv, double* vec, cudaStream_t s);
+// out[0] = sum_i log L_ii (i < n); out[1] = a.b (i < n)
+int launch_logdet_dot(const double* L, int64_t ld, const double* a, const double* b, int n, double* out2,
+                      cudaStream_t s);
+
+// ---- lml.cu : fused gradient traces (regression.py:563-566)
+// grad layout: [mean params | cov params]; partial buffer sized by trace_partials_size()
+size_t trace_partials_size(int npad);
+int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad, const double* alpha, const double* Kinv, int64_t ld,
+                    double* partials, double* grad_dev, cudaStream_t s);
+
+}  // namespace gpb

@@ -1,0 +1,200 @@
+// Fused trace / quadratic terms of the log-marginal-likelihood gradient (regression.py:563-566):
+//     dLML/dtheta_mean,i = sum_n alpha_n dmu_n/dtheta_i
+//     dLML/dtheta_cov,p  = 1/2 sum_ij (alpha_i alpha_j - Kinv_ij) dK_p,ij
+// The reference materialises every dK_p as a dense N x N array (covariance.py:273-276, 356-364) and
+// makes one pass per parameter.  Here dK_p,ij is recomputed from the coordinates inside ONE pass over
+// the lower tiles of Kinv per smooth component (HBM-read bound: 4 N^2 bytes), with per-tile partial sums
+// reduced in a fixed order (bit-reproducible).  Noise kernels only need diag(alpha alpha^T - Kinv).
+#include "kernels.cuh"
+
+namespace gpb {
+namespace {
+
+constexpr int TILE = 128;
+constexpr int NACC = MAX_DIM + 2;  // [ln a, (ln alpha_rq), ln l_1..l_d]
+
+__device__ __forceinline__ void lower_tile(int t, int& bi, int& bj) {
+    int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while (r * (r + 1) / 2 > t) --r;
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    bi = r;
+    bj = t - r * (r + 1) / 2;
+}
+
+// one smooth component `c`; partials[tile][NACC]
+__global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, int c, const double* __restrict__ x,
+                                                           int n, const double* __restrict__ alpha,
+                                                           const double* __restrict__ Kinv, int64_t ld,
+                                                           double* __restrict__ partials) {
+    __shared__ double xs[TILE * MAX_DIM];
+    __shared__ double as[TILE];
+    __shared__ double red[8][NACC];
+    int bi, bj;
+    lower_tile(blockIdx.x, bi, bj);
+    const int row0 = bi * TILE, col0 = bj * TILE;
+    const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
+    const int d = cp.d;
+    for (int idx = tid; idx < TILE * d; idx += 256) xs[idx] = x[(int64_t)row0 * d + idx];
+    if (tid < TILE) as[tid] = alpha[row0 + tid];
+    const int gj = col0 + col;
+    double xj[MAX_DIM], il2[MAX_DIM];
+#pragma unroll
+    for (int k = 0; k < MAX_DIM; ++k) {
+        xj[k] = (k < d) ? x[(int64_t)gj * d + k] : 0.0;
+        il2[k] = (k < d) ? cp.inv_l2[c][k] : 0.0;
+    }
+    const double aj = alpha[gj];
+    const double amp2 = cp.amp2[c], q = cp.rq_alpha[c];
+    const bool is_rq = cp.kind[c] == COV_RQ;
+    double acc[NACC];
+#pragma unroll
+    for (int p = 0; p < NACC; ++p) acc[p] = 0.0;
+    __syncthreads();
+    for (int r = 0; r < TILE / 2; ++r) {
+        const int i = half * (TILE / 2) + r;
+        const int gi = row0 + i;
+        if (gi < gj || gi >= n || gj >= n) continue;
+        const double w = (gi == gj) ? 1.0 : 2.0;  // symmetry: strict lower counted twice
+        const double Q = w * (as[i] * aj - Kinv[(int64_t)gi * ld + gj]);
+        double s[MAX_DIM];  // 0.5 dx^2 / l^2 per dimension
+        double z = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAX_DIM; ++k) {
+            const double df = (k < d) ? xs[i * d + k] - xj[k] : 0.0;
+            s[k] = (0.5 * df * df) * il2[k];
+            z += s[k];
+        }
+        if (!is_rq) {
+            // covariance.py:271-275: grads = [2K, (dx_k^2 / l_k^2) K]
+            const double kv = amp2 * (exp(-z) + (gi == gj ? cp.jitter : 0.0));
+            const double qk = Q * kv;
+            acc[0] += qk;  // 0.5 * Q * 2K
+#pragma unroll
+            for (int k = 0; k < MAX_DIM; ++k) acc[2 + k] = fma(qk, s[k], acc[2 + k]);  // 0.5 * Q * 2 s_k K
+        } else {
+            // covariance.py:356-364: F = 1 + Z/q; grads = [2K, -K (q ln F - Z/F), (2K/F) s_k]
+            const double F = 1.0 + z / q, lnF = log(F);
+            const double kv = amp2 * (exp(-q * lnF) + (gi == gj ? cp.jitter : 0.0));
+            const double qk = Q * kv;
+            acc[0] += qk;
+            acc[1] = fma(-0.5 * qk, lnF * q - z / F, acc[1]);
+            const double qkf = qk / F;
+#pragma unroll
+            for (int k = 0; k < MAX_DIM; ++k) acc[2 + k] = fma(qkf, s[k], acc[2 + k]);
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int p = 0; p < NACC; ++p) {
+        double v = acc[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][p] = v;
+    }
+    __syncthreads();
+    if (tid < NACC) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][tid];
+        partials[(int64_t)blockIdx.x * NACC + tid] = v;
+    }
+}
+
+// grad[off + map(p)] = sum over tiles of partials[tile][p]; one CTA per accumulator slot
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int ntiles, int d,
+                                                              int is_rq, int off, double* __restrict__ grad) {
+    __shared__ double sm[256];
+    const int p = blockIdx.x;  // accumulator slot
+    if (p == 1 && !is_rq) return;
+    if (p >= 2 + d) return;
+    double v = 0.0;
+    for (int t = threadIdx.x; t < ntiles; t += 256) v += partials[(int64_t)t * NACC + p];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int idx = is_rq ? p : (p == 0 ? 0 : p - 1);
+        grad[off + idx] = sm[0];
+    }
+}
+
+// single CTA: mean-parameter gradients, White / Hetero gradients from diag(alpha alpha^T - Kinv)
+__global__ void __launch_bounds__(1024) diag_terms_kernel(const CovParams cp, const MeanParams mp, int n_theta_mean, const double* __restrict__ x, int n,
+                                                          const double* __restrict__ alpha,
+                                                          const double* __restrict__ Kinv, int64_t ld,
+                                                          double* __restrict__ grad) {
+    __shared__ double sm[1024];
+    const int tid = threadIdx.x;
+    auto block_sum = [&](double v) -> double {
+        sm[tid] = v;
+        __syncthreads();
+        for (int o = 512; o > 0; o >>= 1) {
+            if (tid < o) sm[tid] += sm[tid + o];
+            __syncthreads();
+        }
+        const double r = sm[0];
+        __syncthreads();
+        return r;
+    };
+    // mean gradients (mean.py:50-51, 80-83, 122-126)
+    const int d = mp.d;
+    const int n_mean = (mp.kind == MEAN_CONST) ? 1 : (mp.kind == MEAN_LINEAR ? 1 + d : 1 + 2 * d);
+    for (int p = 0; p < n_mean; ++p) {
+        double v = 0.0;
+        for (int i = tid; i < n; i += 1024) {
+            double g = 1.0;
+            if (p >= 1) {
+                const int k = (p - 1) % d;
+                const double dx = x[(int64_t)i * d + k] - mp.xbar[k];
+                g = (p <= d) ? dx : dx * dx;
+            }
+            v = fma(alpha[i], g, v);
+        }
+        v = block_sum(v);
+        if (tid == 0) grad[p] = v;
+    }
+    // noise components
+    for (int c = 0; c < cp.ncomp; ++c) {
+        if (cp.kind[c] == COV_WHITE) {
+            double v = 0.0;
+            for (int i = tid; i < n; i += 1024) v += alpha[i] * alpha[i] - Kinv[(int64_t)i * ld + i];
+            v = block_sum(v);
+            if (tid == 0) grad[n_theta_mean + cp.theta_off[c]] = cp.amp2[c] * v;  // 0.5 * sum Q_ii * 2 sigma^2
+        } else if (cp.kind[c] == COV_HETERO) {
+            for (int i = tid; i < n; i += 1024) {
+                const double s2 = exp(2.0 * cp.hetero_log_sigma[i]);
+                grad[n_theta_mean + cp.theta_off[c] + i] = s2 * (alpha[i] * alpha[i] - Kinv[(int64_t)i * ld + i]);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t trace_partials_size(int npad) {
+    const int64_t nb = npad / TILE;
+    return (size_t)(nb * (nb + 1) / 2) * NACC * sizeof(double);
+}
+
+int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad, const double* alpha, const double* Kinv,
+                    int64_t ld, double* partials, double* grad_dev, cudaStream_t s) {
+    const int nb = npad / TILE;
+    const int ntiles = nb * (nb + 1) / 2;
+    for (int c = 0; c < cp.ncomp; ++c) {
+        if (cp.kind[c] > COV_RQ) continue;
+        trace_smooth_kernel<<<ntiles, 256, 0, s>>>(cp, c, x, n, alpha, Kinv, ld, partials);
+        GPB_CUDA(cudaGetLastError());
+        reduce_partials_kernel<<<NACC, 256, 0, s>>>(partials, ntiles, cp.d, cp.kind[c] == COV_RQ,
+                                                    n_theta_mean + cp.theta_off[c], grad_dev);
+        GPB_CUDA(cudaGetLastError());
+        count_launch(2);
+    }
+    diag_terms_kernel<<<1, 1024, 0, s>>>(cp, mp, n_theta_mean, x, n, alpha, Kinv, ld, grad_dev);
+    GPB_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace gpb
