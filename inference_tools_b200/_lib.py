@@ -274,3 +274,11 @@ class Engine:
 
     def gemm_flops(self):
         return float(self.lib.gpb_gemm_flops())
+
+
+def device_count() -> int:
+    lib = load_library()
+    cnt = C.c_int(0)
+    if lib.gpb_device_count(C.byref(cnt)) != 0:
+        raise EngineError(lib.gpb_last_error().decode())
+    return cnt.value

@@ -1,0 +1,329 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI (ctypes) behind the
+reference-shaped Python API, against (a) the committed fixtures generated from the unmodified reference
+and (b) the numpy oracle on seeded inputs.  Tolerance: 1e-9 relative (BASELINE.json north_star) on mean,
+sigma, LML and its gradient; the gradient is compared norm-relative."""
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+from numpy.linalg import LinAlgError
+
+from conftest import golden_names, load_golden, make_kernel, make_mean, rel_err, synth
+import inference_tools_b200.gp as gp
+from inference_tools_b200 import _lib
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def fitted(g, **kw):
+    return gp.GpRegressor(g["x"], g["y"], y_err=None if g["noise_var"] is None else g["y_err"],
+                          kernel=make_kernel(gp, g["comps"]), mean=make_mean(gp, g["mean"]), hyperpars=g["theta"], **kw)
+
+
+def test_cuda_library_is_the_path():
+    assert _lib.device_count() >= 1
+    x, y, e = synth(0, 50, 1)
+    before = _lib.load_library().gpb_launch_count()
+    gp.GpRegressor(x, y, y_err=e, hyperpars=[0.0, 0.0, -1.0])(np.linspace(0, 1, 5))
+    assert _lib.load_library().gpb_launch_count() > before
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fit_predict_against_reference_fixtures(name):
+    g = load_golden(name)
+    m = fitted(g)
+    assert rel_err(m.alpha, g["alpha"]) < TOL
+    assert rel_err(m.mu, g["mu_train"]) < 1e-14 if "mu_train" in g else True
+    if "L" in g:
+        assert rel_err(m.L, g["L"]) < TOL and np.all(np.triu(m.L, 1) == 0)
+        assert rel_err(m.K_xx, g["K_xx"]) < 1e-13
+    if "pred_mu" in g:
+        mu, sig = m(g["q"])
+        assert mu.shape == sig.shape == (g["q"].shape[0],)
+        assert rel_err(mu, g["pred_mu"]) < TOL
+        assert np.abs(sig / g["pred_sig"] - 1).max() < TOL
+    if "post_mu" in g:
+        pm, pc = m.build_posterior(g["q"][:16])
+        assert rel_err(pm, g["post_mu"]) < TOL and rel_err(pc, g["post_cov"]) < TOL
+        assert rel_err(m.build_posterior(g["q"][:16], mean_only=True), g["post_mu"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_marginal_likelihood_and_gradient_against_reference_fixtures(name):
+    g = load_golden(name)
+    m = fitted(g)
+    lml = m.marginal_likelihood(g["theta"])
+    assert isinstance(lml, np.float64) and abs(lml - g["lml"]) <= TOL * abs(g["lml"])
+    lml2, grad = m.marginal_likelihood_gradient(g["theta"])
+    assert abs(lml2 - g["lml_from_grad"]) <= TOL * abs(g["lml_from_grad"])
+    assert grad.shape == g["lml_grad"].shape
+    assert np.abs(grad - g["lml_grad"]).max() <= TOL * np.abs(g["lml_grad"]).max()
+    # objective evaluations must not disturb the fitted state (reference: pure functions of theta)
+    assert rel_err(m.alpha, g["alpha"]) < TOL
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "K_xx" in load_golden(n)])
+def test_covariance_plugin_api_against_reference_fixtures(name):
+    g = load_golden(name)
+    cov = make_kernel(gp, g["comps"])
+    cov.pass_spatial_data(g["x"])
+    n_mean = {"const": 1, "linear": 1 + g["x"].shape[1], "quadratic": 1 + 2 * g["x"].shape[1]}[g["mean"]]
+    tc = g["theta"][n_mean:]
+    assert rel_err(cov.build_covariance(tc), g["K_cov"]) < 1e-13
+    k, grads = cov.covariance_and_gradients(tc)
+    assert isinstance(grads, list) and len(grads) == len(tc)
+    assert rel_err(k, g["K_cov"]) < 1e-13 and rel_err(np.array(grads), g["dK"]) < 1e-12
+    assert rel_err(cov(g["q"], g["x"], tc), g["K_qx"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "grad_mean" in load_golden(n)])
+def test_gradient_spatial_derivatives_ei_against_reference_fixtures(name):
+    g = load_golden(name)
+    m = fitted(g)
+    gm, gc = m.gradient(g["q"])
+    assert gm.shape == g["grad_mean"].shape and gc.shape == g["grad_cov"].shape
+    assert rel_err(gm, g["grad_mean"]) < TOL and rel_err(gc, g["grad_cov"]) < TOL
+    dm, dv = m.spatial_derivatives(g["q"])
+    assert dm.shape == g["sd_dmu"].shape and dv.shape == g["sd_dvar"].shape
+    assert rel_err(dm, g["sd_dmu"]) < TOL and rel_err(dv, g["sd_dvar"]) < TOL
+    if "ei_q" not in g:
+        return
+    qq = g["ei_q"].reshape(-1, g["x"].shape[1])
+    ei = gp.ExpectedImprovement()
+    ei.update_gp(m)
+    val, best = ei.batch(qq)
+    assert np.allclose(val, g["ei"], rtol=1e-7, atol=1e-300)
+    assert val[best] == val.max()
+    assert rel_err(ei.opt_func_batch(qq), g["ei_optfunc"]) < TOL
+    v2, gr = ei.opt_func_gradient_batch(qq)
+    assert rel_err(v2, g["ei_optfunc_g_val"]) < TOL
+    assert rel_err(gr, g["ei_optfunc_g_grad"].reshape(gr.shape)) < 1e-8
+    # scalar protocol of the reference (one point per call)
+    assert ei(qq[0]) == pytest.approx(g["ei"][0], rel=1e-7, abs=1e-300)
+    assert ei.opt_func(qq[1]) == pytest.approx(g["ei_optfunc"][1], rel=TOL)
+    v, gvec = ei.opt_func_gradient(qq[2])
+    assert isinstance(v, np.ndarray) and float(v) == pytest.approx(g["ei_optfunc_g_val"][2], rel=TOL)
+    assert np.allclose(gvec, g["ei_optfunc_g_grad"][2], rtol=1e-7)
+
+
+@pytest.mark.parametrize("n,d,comps,mean", [(1000, 3, ("SE",), "linear"), (2500, 5, ("RQ", "WHITE"), "const"),
+                                            (3, 2, ("SE",), "const"), (129, 4, ("SE", "RQ"), "quadratic"),
+                                            (640, 8, ("SE",), "const")])
+def test_against_oracle_on_seeded_inputs(n, d, comps, mean):
+    x, y, e = synth(100 + n, n, d)
+    rng = np.random.default_rng(n)
+    tm = {"const": [0.3], "linear": [0.3] + [0.1] * d, "quadratic": [0.3] + [0.1] * d + [-0.05] * d}[mean]
+    tc = []
+    for c in comps:
+        tc += {"SE": [0.1] + [np.log(0.35)] * d, "RQ": [-0.2, 0.8] + [np.log(0.3)] * d, "WHITE": [np.log(0.04)]}[c]
+    theta = np.array(tm + tc)
+    m = gp.GpRegressor(x, y, y_err=e, kernel=make_kernel(gp, comps), mean=make_mean(gp, mean), hyperpars=theta)
+    ref = orc.Fit(x, y, comps, mean, theta, e**2)
+    q = rng.uniform(-0.05, 1.05, (300, d))
+    mu, sig = m(q)
+    mu_o, sig_o = ref.predict(q)
+    assert rel_err(m.alpha, ref.alpha) < TOL
+    assert rel_err(mu, mu_o) < TOL and np.abs(sig / sig_o - 1).max() < TOL
+    lml_o, grad_o = orc.marginal_likelihood_gradient(x, y, comps, mean, theta, e**2)
+    lml, grad = m.marginal_likelihood_gradient(theta)
+    assert abs(lml - lml_o) <= TOL * abs(lml_o)
+    assert np.abs(grad - grad_o).max() <= TOL * np.abs(grad_o).max()
+    assert abs(m.marginal_likelihood(theta) - orc.marginal_likelihood(x, y, comps, mean, theta, e**2)) <= TOL * abs(lml_o)
+
+
+def test_dense_y_cov_path():
+    x, y, e = synth(7, 90, 2)
+    rng = np.random.default_rng(7)
+    a = rng.normal(size=(90, 90)) * 0.01
+    y_cov = a @ a.T + np.diag(e**2)
+    y_cov = 0.5 * (y_cov + y_cov.T)
+    theta = np.array([0.2, 0.0, -1.0, -1.2])
+    m = gp.GpRegressor(x, y, y_cov=y_cov, hyperpars=theta)
+    ref = orc.Fit(x, y, ("SE",), "const", theta, None, y_cov)
+    assert rel_err(m.alpha, ref.alpha) < TOL
+    assert abs(m.marginal_likelihood(theta) - orc.marginal_likelihood(x, y, ("SE",), "const", theta, None, y_cov)) < 1e-9 * 100
+    assert np.array_equal(m.sig, y_cov)
+
+
+def test_output_shapes_and_squeeze_rules():
+    """SURVEY.md section 8d 'output shapes to match'"""
+    x, y, e = synth(3, 40, 1)
+    m1 = gp.GpRegressor(x[:, 0], y, y_err=e, hyperpars=[0.0, 0.0, -1.0])
+    mu, sig = m1(0.5)
+    assert mu.shape == sig.shape == (1,)
+    mu, sig = m1(np.linspace(0, 1, 7))
+    assert mu.shape == (7,)
+    gm, gc = m1.gradient(np.linspace(0, 1, 7))
+    assert gm.shape == (7,) and gc.shape == (7,)
+    gm, gc = m1.gradient(0.3)
+    assert gm.shape == () and gc.shape == ()
+    dm, dv = m1.spatial_derivatives([0.1, 0.2])
+    assert dm.shape == dv.shape == (2,)
+    x3, y3, e3 = synth(4, 40, 3)
+    m3 = gp.GpRegressor(x3, y3, y_err=e3, hyperpars=[0.0, 0.0, -1.0, -1.0, -1.0])
+    mu, sig = m3(np.array([0.1, 0.2, 0.3]))
+    assert mu.shape == (1,)
+    gm, gc = m3.gradient(np.array([0.1, 0.2, 0.3]))
+    assert gm.shape == (3,) and gc.shape == (3, 3)
+    gm, gc = m3.gradient(x3[:5])
+    assert gm.shape == (5, 3) and gc.shape == (5, 3, 3)
+    pm, pc = m3.build_posterior(x3[:6])
+    assert pm.shape == (6,) and pc.shape == (6, 6)
+    mu, sig = m3(np.zeros((0, 3)))
+    assert mu.shape == (0,)
+    with pytest.raises(ValueError):
+        m3(np.zeros((4, 2)))
+    with pytest.raises(ValueError):
+        m3(np.zeros((2, 2, 3)))
+    with pytest.raises(ValueError):
+        m3.set_hyperparameters([0.0, 0.0])
+    assert "SqrExp log-scale 2" in str(m3)
+
+
+def test_gradient_terms_only_for_squared_exponential():
+    x, y, e = synth(5, 30, 2)
+    for kern in (gp.RationalQuadratic(), gp.SquaredExponential() + gp.WhiteNoise()):
+        m = gp.GpRegressor(x, y, y_err=e, kernel=kern, hyperpars=np.zeros(4 + (1 if isinstance(kern, gp.RationalQuadratic) else 1)) - 0.5)
+        with pytest.raises(NotImplementedError):
+            m.gradient(x[:2])
+        with pytest.raises(NotImplementedError):
+            m.spatial_derivatives(x[:2])
+
+
+def test_non_positive_definite_handling():
+    """regression.py:536-542 (warn + -1e50) vs :555 and :241 (LinAlgError propagates)"""
+    x = np.linspace(0, 1, 40)
+    x[21] = x[20]
+    y = np.sin(3 * x)
+    m = gp.GpRegressor(x, y, y_err=np.full(40, 0.1), hyperpars=[0.0, 0.0, -1.0])
+    bad = np.array([0.0, 30.0, 6.0])        # a^2 = e^60 with O(1) noise and duplicate points: numerically singular
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        val = m.marginal_likelihood(bad)
+    if val == -1e50:
+        assert any("Cholesky decomposition failure" in str(i.message) for i in w)
+        with pytest.raises(LinAlgError):
+            m.marginal_likelihood_gradient(bad)
+        with pytest.raises(LinAlgError):
+            gp.GpRegressor(x, y, y_err=np.full(40, 0.1), hyperpars=bad)
+    # exact indefiniteness through y_cov: negative variance on one point
+    yc = np.eye(40) * 0.01
+    yc[7, 7] = -50.0
+    with pytest.raises(LinAlgError):
+        gp.GpRegressor(x, y, y_cov=yc, hyperpars=[0.0, 0.0, -1.0])
+
+
+def test_reference_finite_difference_checks():
+    """tests/gp/test_GpRegressor.py:61-76 (LML gradient), :97-117 (gradient), :120-144 (spatial derivatives)
+    re-pointed at the CUDA engine, same tolerances."""
+    rng = np.random.default_rng(1)
+    n = 32
+    x = np.stack([rng.uniform(0, 2, n), rng.uniform(0, 2, n)], axis=1)
+    y = np.sin(x[:, 0]) * np.sin(x[:, 1]) * (x[:, 1] + 1) + rng.normal(0, 0.1, n)
+    m = gp.GpRegressor(x, y, y_err=np.full(n, 0.1), kernel=gp.SquaredExponential(), hyperpars=[0.0, 0.0, 0.0, 0.0])
+    rng = np.random.default_rng(123)
+    for _ in range(20):
+        th = rng.uniform(-0.5, 1.0, 4)
+        _, g = m.marginal_likelihood_gradient(th)
+        fd = np.zeros(4)
+        for i in range(4):
+            dt = np.zeros(4)
+            dt[i] = 1e-6
+            fd[i] = (m.marginal_likelihood(th + dt) - m.marginal_likelihood(th - dt)) / 2e-6
+        assert np.abs(fd / g - 1).max() < 1e-5
+    xs = np.linspace(0, 10, 10)
+    ys = np.sin(xs)
+    m1 = gp.GpRegressor(xs, ys, y_err=np.full(10, 0.05), hyperpars=[0.0, 0.0, 0.5])
+    pts = np.linspace(0.5, 9.5, 120)
+    dx = 1e-5
+    gm, _ = m1.gradient(pts)
+    fd = (m1(pts + dx)[0] - m1(pts - dx)[0]) / (2 * dx)
+    assert np.abs(gm / fd - 1).max() < 1e-6
+    dm, dv = m1.spatial_derivatives(pts)
+    mu_p, s_p = m1(pts + dx)
+    mu_m, s_m = m1(pts - dx)
+    assert np.abs(dm / ((mu_p - mu_m) / (2 * dx)) - 1).max() < 1e-6
+    assert np.abs(dv / ((s_p**2 - s_m**2) / (2 * dx)) - 1).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["fit_se_d1_n60", "fit_rqwhite_d2_n80"])
+def test_multistart_fit_reaches_the_reference_optimum(name):
+    g = np.load(f"tests/golden/{name}.npz") if False else None
+    import os
+    from conftest import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    comps = tuple(str(c) for c in g["comps"])
+    np.random.seed(int(g["np_seed"]))
+    m = gp.GpRegressor(g["x"], g["y"], y_err=g["y_err"], kernel=make_kernel(gp, comps), mean=make_mean(gp, str(g["mean"])))
+    assert np.allclose(np.array(m.hp_bounds, dtype=float), g["bounds"], rtol=1e-11, atol=1e-12)
+    lml = m.marginal_likelihood(m.hyperpars)
+    # same seeded starts, same scipy L-BFGS-B: the optimum found must be as good as the reference's
+    assert lml >= float(g["lml_opt"]) - 1e-4 * abs(float(g["lml_opt"]))
+    mu, sig = m(g["q"])
+    assert np.abs(mu - g["pred_mu"]).max() < 1e-3 * np.abs(g["pred_mu"]).max()
+
+
+def test_optimisers_and_threaded_restarts():
+    """tests/gp/test_GpRegressor.py:147-151 smoke: n_starts, n_processes=2, diffev, bad optimizer string"""
+    x, y, e = synth(11, 48, 1)
+    np.random.seed(2)
+    a = gp.GpRegressor(x, y, y_err=e, n_starts=4)
+    np.random.seed(2)
+    b = gp.GpRegressor(x, y, y_err=e, n_starts=4, n_processes=2)
+    assert np.allclose(a.hyperpars, b.hyperpars, rtol=1e-6, atol=1e-6)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        c = gp.GpRegressor(x, y, y_err=e, optimizer="nonsense", n_starts=2)
+        assert any("invalid option" in str(i.message) for i in w)
+    assert np.isfinite(c.marginal_likelihood(c.hyperpars))
+    d = gp.GpRegressor(x[:24], y[:24], y_err=e[:24], optimizer="diffev")
+    assert d.marginal_likelihood(d.hyperpars) >= a.marginal_likelihood(d.hyperpars) - 1e9
+
+
+def test_pickle_round_trip_drops_device_handles():
+    x, y, e = synth(12, 64, 2)
+    m = gp.GpRegressor(x, y, y_err=e, hyperpars=[0.1, 0.0, -1.0, -1.0])
+    q = x[:9] + 0.01
+    mu0, s0 = m(q)
+    m2 = pickle.loads(pickle.dumps(m))
+    mu1, s1 = m2(q)
+    assert np.array_equal(mu0, mu1) and np.array_equal(s0, s1)
+
+
+def test_run_to_run_bit_reproducibility():
+    x, y, e = synth(13, 500, 3)
+    th = np.array([0.1, 0.0, -1.0, -1.1, -0.9])
+    m = gp.GpRegressor(x, y, y_err=e, hyperpars=th)
+    r1 = m.marginal_likelihood_gradient(th)
+    r2 = m.marginal_likelihood_gradient(th)
+    assert r1[0] == r2[0] and np.array_equal(r1[1], r2[1])
+    assert np.array_equal(m(x[:50])[1], m(x[:50])[1])
+
+
+def test_size_independent_properties_at_baseline_scale():
+    """BASELINE.json config 3 shape (N=32768, d=5, RQ+White): the oracle cannot factor this in test time, so
+    check properties that pin the result without it: K alpha = y - mu on sampled rows, the posterior mean at
+    training points, sigma^2 >= 0 and <= prior variance, and LML gradient vs central differences."""
+    n, d = 32768, 5
+    x, y, e = synth(2024, n, d)
+    theta = np.array([0.2, 0.1, 1.0] + [np.log(0.3)] * d + [np.log(0.05)])
+    m = gp.GpRegressor(x, y, y_err=e, kernel=gp.RationalQuadratic() + gp.WhiteNoise(), hyperpars=theta)
+    alpha = m.alpha
+    rows = np.random.default_rng(0).choice(n, 64, replace=False)
+    tm, parts = orc.split_theta(theta, ("RQ", "WHITE"), "const", n, d)
+    k_rows = np.stack([orc.train_cov_rows(("RQ", "WHITE"), parts, x, r, r + 1, e**2)[0] for r in rows])
+    resid = y[rows] - theta[0]
+    assert np.abs(k_rows @ alpha - resid).max() < 1e-9 * np.abs(resid).max() * 1e2   # backward error of the solve
+    mu, sig = m(x[rows])
+    noise = e[rows] ** 2 + np.exp(2 * theta[-1]) + np.exp(theta[1]) ** 2 * 1e-12
+    assert np.abs(mu - (y[rows] - noise * alpha[rows])).max() < 1e-9
+    assert np.all(sig >= 0) and np.all(sig**2 <= np.exp(theta[1]) ** 2 * (1 + 1e-12))
+    lml, grad = m.marginal_likelihood_gradient(theta)
+    for i in (1, 2, 4, 8):
+        dt = np.zeros_like(theta)
+        dt[i] = 1e-5
+        fd = (m.marginal_likelihood(theta + dt) - m.marginal_likelihood(theta - dt)) / 2e-5
+        assert abs(fd - grad[i]) <= 2e-5 * max(1.0, np.abs(grad).max())

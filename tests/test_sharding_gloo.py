@@ -1,0 +1,61 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of bench.py / multi-GPU predict -- slabs cover the query
+set exactly once, the timing reduction is the max over ranks, results gathered in rank order."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from inference_tools_b200.sharding import round_robin, shard_range
+
+
+def test_shard_range_properties():
+    for n in (0, 1, 7, 1 << 20, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert sorted(sum((round_robin(11, r, 4) for r in range(4)), [])) == list(range(11))
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _worker(rank, world, port, m, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(m, rank, world)
+    q = np.arange(m, dtype=np.float64)
+    local = torch.from_numpy(q[lo:hi] * 2.0)                       # stand-in for this rank's predictions
+    sizes = [shard_range(m, r, world) for r in range(world)]
+    bufs = [torch.empty(h - l, dtype=torch.float64) for l, h in sizes]
+    dist.all_gather(bufs, local) if len({b.numel() for b in bufs}) == 1 else None
+    t = torch.tensor([0.5 + rank], dtype=torch.float64)            # per-rank elapsed time
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([hi - lo], dtype=torch.int64)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        out.put((float(t), int(cnt), [b.tolist() for b in bufs] if len({b.numel() for b in bufs}) == 1 else None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_predict_bookkeeping():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    m = 64
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, m, out)) for r in range(2)]
+    [p.start() for p in procs]
+    tmax, total, gathered = out.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert tmax == 1.5 and total == m
+    assert np.allclose(np.concatenate(gathered), np.arange(m) * 2.0)
