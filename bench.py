@@ -1,0 +1,290 @@
+"""Benchmark of the GpRegressor hot path on B200 (contract: see the round prompt / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload = BASELINE.json config 3, the shape the headline metric is quoted on: GpRegressor with
+RationalQuadratic + WhiteNoise in 5-D, N = 32768 training points, fixed well-conditioned theta.  One step =
+one marginal_likelihood_gradient(theta) (assemble, Cholesky, explicit inverse, traces) + one
+set_hyperparameters(theta) (assemble, Cholesky, alpha) + predict mean/sigma at 131072 query points per GPU
+(2^20 over 8 GPUs: weak scaling, query points are the sharded unit, no data-path collective).
+`value` = query points processed by all ranks / max-over-ranks device time of the step (fit and gradient
+time included), inputs resident in HBM; `e2e` = the same through the public GpRegressor API with pinned
+host buffers.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAIN = int(os.environ.get("GPB_BENCH_N", 32768))
+DIM = 5
+M_PER_GPU = int(os.environ.get("GPB_BENCH_M", 131072))
+COMPS = ("RQ", "WHITE")
+THETA = np.array([0.2, 0.1, 1.0] + [np.log(0.3)] * DIM + [np.log(0.05)])
+METRIC = "GpRegressor fit+gradient+predict throughput at N=32768,d=5 (query points/s over the whole step; seconds in step_s)"
+UNIT = "query points/s"
+SAMPLE_N = int(os.environ.get("GPB_BENCH_CPU_N", 8192))
+SAMPLE_M = 32
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "cfg3: GpRegressor RationalQuadratic+WhiteNoise 5D, N=32768; step = marginal_likelihood_gradient + "
+                    "set_hyperparameters + predict mean/sigma at 131072 points per GPU",
+        "N": N_TRAIN, "d": DIM, "points_per_gpu": M_PER_GPU, "points_total": M_PER_GPU * n_gpus,
+        "theta": "a=e^0.1, alpha=e, l=0.3, white=0.05, y_err=0.05 (SURVEY.md 8d)",
+        "l2": "inputs larger than L2: K/L are 8.6 GB each, query slab 5.2 MB re-read against 8.6 GB of L",
+        "sharding": f"query points, {n_gpus} rank(s), fit replicated per rank, no collective on the data path",
+    }
+
+
+def load_fp64_peak():
+    """FP64 tensor (DMMA) peak: MEASURED_PEAKS.json carries only HBM and bf16; the FP64 denominator is this
+    repo's own measurement on the same pool (tools/fp64_probe.cu -> profiles/fp64_peak_r1.json)."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r1.json")))
+        return float(p["probe"]["dmma_tflops_sustained"]), "measured: tools/fp64_probe DMMA issue rate (profiles/fp64_peak_r1.json); MEASURED_PEAKS.json has no FP64 entry"
+    except Exception:
+        return 37.2, "nominal 148 SM x 128 flop/clk x 1.965 GHz (profiles/fp64_peak_r1.json missing)"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            smax = int(f[1])
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(n_gpus):
+    from oracle import cpu_reference as cr
+    t = cr.timed_step(SAMPLE_N, DIM, COMPS, "const", THETA, SAMPLE_M)
+    total_pts = M_PER_GPU * n_gpus
+    full_s, fit_s, pred_s = cr.extrapolate(t, SAMPLE_N, N_TRAIN, total_pts)
+    return {
+        "value": total_pts / full_s, "unit": UNIT, "cores": cr.blas_threads(), "kind": "port",
+        "sample": f"reference algorithm (oracle port: numpy/scipy LAPACK+BLAS, the reference's own calls) timed at N={SAMPLE_N}, "
+                  f"{SAMPLE_M} query points; components extrapolated to N={N_TRAIN}, M={total_pts}: assembly/traces x(N/Ns)^2, "
+                  f"LAPACK x(N/Ns)^3, predict per point x(N/Ns)^2 x M. The unmodified reference cannot allocate this config.",
+        "sample_seconds": {k: round(v, 4) for k, v in t.items() if not k.startswith("_")},
+        "extrapolated_step_s": full_s, "extrapolated_fit_grad_s": fit_s, "extrapolated_predict_s": pred_s,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = min(args.warmup, 1)
+    steps = min(args.steps, 3)
+    from oracle import cpu_reference as cr
+    for _ in range(warm):
+        cr.timed_step(SAMPLE_N, DIM, COMPS, "const", THETA, SAMPLE_M)
+    t0 = time.perf_counter()
+    vals = [cpu_reference(args.gpus) for _ in range(steps)]
+    wall = time.perf_counter() - t0
+    best = max(vals, key=lambda v: v["value"])
+    value = float(np.mean([v["value"] for v in vals]))
+    best = dict(best, value=value)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * args.gpus * M_PER_GPU / value, "sample_wall_s_per_step": wall / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": best, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from inference_tools_b200 import _lib
+    from inference_tools_b200.gp import GpRegressor, RationalQuadratic, WhiteNoise
+    from inference_tools_b200.sharding import shard_range
+    from oracle.cpu_reference import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic data (identical on every rank), query slab of this rank
+    x, y, y_err = synth(2024, N_TRAIN, DIM)
+    m_total = M_PER_GPU * world
+    lo, hi = shard_range(m_total, rank, world)
+    q_all_rng = np.random.default_rng(99)
+    q_host = torch.empty((hi - lo, DIM), dtype=torch.float64, pin_memory=True)
+    q_np = q_host.numpy()
+    q_np[:] = q_all_rng.uniform(0, 1, (m_total, DIM))[lo:hi]
+
+    gp = GpRegressor(x, y, y_err=y_err, kernel=RationalQuadratic() + WhiteNoise(), hyperpars=THETA, device=local)
+    eng = gp.engine
+    m_loc = hi - lo
+    q_dev = eng.dev_alloc(m_loc * DIM)
+    mu_dev = eng.dev_alloc(m_loc)
+    sig_dev = eng.dev_alloc(m_loc)
+    eng.dev_upload(q_dev, q_np)
+
+    phase_acc = {}
+
+    def add_phases(prefix, tm):
+        for k, v in tm.items():
+            phase_acc[prefix + k] = phase_acc.get(prefix + k, 0.0) + v
+
+    def step_resident(record=False):
+        """device-resident step; returns device milliseconds from the library's CUDA events"""
+        ms = 0.0
+        lml, grad, info = eng.lml_grad(THETA)
+        tm = eng.timers(); ms += sum(tm.values())
+        if record: add_phases("grad.", tm)
+        info2 = eng.factor(THETA)
+        tm = eng.timers(); ms += sum(tm.values())
+        if record: add_phases("fit.", tm)
+        eng.predict_dev(q_dev, m_loc, mu_dev, sig_dev)
+        eng.sync()
+        tm = eng.timers(); ms += sum(tm.values())
+        if record: add_phases("predict.", tm)
+        assert info == 0 and info2 == 0
+        return ms, lml, grad
+
+    def step_e2e():
+        lml, grad = gp.marginal_likelihood_gradient(THETA)
+        gp.set_hyperparameters(THETA)
+        mu, sig = gp(q_np)
+        return float(lml), mu, sig
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0, flops0 = eng.launch_count(), eng.gemm_flops()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        ms, lml, grad = step_resident(record=True)
+        dev_ms += ms
+    barrier()
+    wall_s = time.perf_counter() - t0
+    launches = eng.launch_count() - launches0
+    flops = eng.gemm_flops() - flops0
+    clocks = sampler.stop() if sampler else None
+    dev_s = max_over_ranks(dev_ms * 1e-3)
+    wall_s = max_over_ranks(wall_s)
+    step_s = dev_s / args.steps
+
+    # ---- e2e through the public API with pinned host buffers
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lml_e, mu_h, sig_h = step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+
+    # parity guard inside the bench: resident and e2e paths agree bit for bit on this rank's slab
+    mu_r = eng.dev_download(mu_dev, m_loc)
+    assert np.array_equal(mu_r, mu_h), "device-resident and host-buffer paths disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_fp64_peak()
+    ph = {k: v / args.steps for k, v in phase_acc.items()}
+    potrf_ms = 0.5 * (ph.get("grad.potrf", 0) + ph.get("fit.potrf", 0))
+    chol_tf = (N_TRAIN**3 / 3) / (potrf_ms * 1e-3) / 1e12 if potrf_ms else None
+    npad = (N_TRAIN + 127) // 128 * 128
+    # dominant kernel = dgemm_kernel (DMMA GEMM): algorithmic flops issued / time of the GEMM-only phases
+    gemm_phase_ms = sum(ph.get(k, 0) for k in ("grad.potrf", "fit.potrf", "grad.trtri", "grad.lauum", "predict.trsm"))
+    gemm_tf = (flops / args.steps) / (gemm_phase_ms * 1e-3) / 1e12 if gemm_phase_ms else None
+    pred_tf = (m_loc * float(npad) ** 2) / (ph.get("predict.trsm", 1e30) * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r1.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": m_total / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_s * 1e3, "step_s": step_s, "wall_ms_per_step": wall_s / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world), "clocks": clocks,
+        "e2e": {"value": m_total / e2e_s, "unit": UNIT, "step_s": e2e_s,
+                "h2d_bytes_per_step": int(m_loc * DIM * 8 + 3 * THETA.size * 8), "d2h_bytes_per_step": int(2 * m_loc * 8 + (THETA.size + 1) * 8)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "dgemm_kernel (mma.sync m8n8k4 f64 -> DMMA.8x8x4)", "bound": "tensor", "achieved": gemm_tf, "peak": peak,
+                     "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": traffic, "peak_source": peak_src,
+                     "how": "algorithmic GEMM flops issued in the step / CUDA-event time of the GEMM-only phases (potrf x2, trtri, lauum, predict trsm) on the library stream"},
+        "cholesky": {"seconds": potrf_ms * 1e-3, "tflops": chol_tf, "frac_of_fp64_peak": chol_tf / peak if chol_tf else None, "flops": "N^3/3"},
+        "predict": {"tflops": pred_tf, "frac_of_fp64_peak": pred_tf / peak, "flops": "M N^2"},
+        "phases_ms": {k: round(v, 3) for k, v in sorted(ph.items())},
+        "lml": float(lml),
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_reference(1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

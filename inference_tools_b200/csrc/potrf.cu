@@ -16,99 +16,113 @@
 namespace gpb {
 namespace {
 
-constexpr int LDD = NB + 1;
-constexpr int DIAG_SMEM = (NB * LDD + 3 * NB) * (int)sizeof(double);
-
 // Factor one 128x128 diagonal block in place (lower triangle) and write inv(L_block) (full block,
 // zero upper triangle) to dinv.  info: 1-based global index of the first non-positive pivot.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ dinv,
-                                                         int* __restrict__ info, int row_offset) {
-    extern __shared__ double sm[];
-    double* S = sm;
-    double* col = sm + NB * LDD;   // two column snapshots (double buffered)
-    double* dg = col + 2 * NB;
+//
+// Register-resident right-looking sweep: 256 threads as a 16 x 16 grid, thread (ty,tx) owns the 64
+// elements (ty + 16a, tx + 16b) of the block AND of the running inverse in registers.  Step j publishes
+// column j of the factor and row j of the partially solved identity through 2 KB of shared memory (one
+// __syncthreads per step, double buffered); every thread then applies the rank-1 update to its own
+// registers:  A[i][k] -= l_ij l_kj (potrf)  and  B[i][c] -= l_ij W[j][c] (forward substitution of L W = I).
+// The whole kernel needs 4 KB of shared memory, so it can be scheduled next to resident GEMM CTAs.
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld,
+                                                            double* __restrict__ dinv, int* __restrict__ info,
+                                                            int row_offset) {
+    __shared__ double cbuf[2][NB];  // column j of A (unscaled)
+    __shared__ double rbuf[2][NB];  // row j of B (unscaled)
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        S[r * LDD + c] = A[(int64_t)r * ld + c];
-    }
-    __syncthreads();
     const int tx = tid & 15, ty = tid >> 4;
+    double r[8][8], w[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b <= a) {
+                r[a][b] = A[(int64_t)(ty + 16 * a) * ld + tx + 16 * b];
+                w[a][b] = (a == b && tx == ty) ? 1.0 : 0.0;
+            } else {
+                r[a][b] = 0.0;
+                w[a][b] = 0.0;
+            }
+        }
     bool failed = false;
-    for (int j = 0; j < NB; ++j) {
-        const double ajj = S[j * LDD + j];
-        if (!(ajj > 0.0)) {  // also catches NaN; uniform across the CTA
-            failed = true;
-            if (tid == 0) atomicCAS(info, 0, row_offset + j + 1);
-            break;
-        }
-        const double dj = sqrt(ajj);
-        if (tid < NB) {
-            if (tid > j) {
-                const double v = S[tid * LDD + j] / dj;
-                S[tid * LDD + j] = v;
-                col[tid] = v;
-            } else if (tid == j) {
-                dg[j] = dj;
+#pragma unroll
+    for (int bj = 0; bj < 8; ++bj) {
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * bj + jj;
+            const int buf = jj & 1;
+            if (tx == jj) {
+#pragma unroll
+                for (int a = bj; a < 8; ++a) cbuf[buf][ty + 16 * a] = r[a][bj];
+            }
+            if (ty == jj) {
+#pragma unroll
+                for (int b = 0; b <= bj; ++b) rbuf[buf][tx + 16 * b] = w[bj][b];
+            }
+            __syncthreads();
+            const double ajj = cbuf[buf][j];
+            if (!(ajj > 0.0)) {  // also catches NaN; uniform across the CTA
+                failed = true;
+                if (tid == 0) atomicCAS(info, 0, row_offset + j + 1);
+                break;
+            }
+            const double dj = sqrt(ajj);
+            const double rinv = 1.0 / dj;
+            double ci[8], ck[8], wj[8];
+#pragma unroll
+            for (int a = bj; a < 8; ++a) ci[a] = cbuf[buf][ty + 16 * a] * rinv;  // l_ij for my rows
+#pragma unroll
+            for (int b = bj; b < 8; ++b) ck[b] = cbuf[buf][tx + 16 * b] * rinv;  // l_kj for my columns
+#pragma unroll
+            for (int b = 0; b <= bj; ++b) wj[b] = rbuf[buf][tx + 16 * b] * rinv;  // W[j][c] for my columns
+#pragma unroll
+            for (int a = bj; a < 8; ++a) {
+                const bool row_below = (a > bj) || (ty > jj);  // i > j
+                if (row_below) {
+#pragma unroll
+                    for (int b = bj; b <= a; ++b) {
+                        const bool col_right = (b > bj) || (tx > jj);  // k > j
+                        const bool lower = (a > b) || (tx <= ty);      // k <= i
+                        if (col_right && lower) r[a][b] = fma(-ci[a], ck[b], r[a][b]);
+                    }
+#pragma unroll
+                    for (int b = 0; b <= bj; ++b) {
+                        const bool col_left = (b < bj) || (tx <= jj);  // c <= j
+                        if (col_left) w[a][b] = fma(-ci[a], wj[b], w[a][b]);
+                    }
+                }
+            }
+            // the owners keep the finished column j of L and row j of W
+            if (tx == jj) {
+#pragma unroll
+                for (int a = bj; a < 8; ++a) {
+                    if ((a > bj) || (ty > jj)) r[a][bj] = ci[a];
+                    else if (ty == jj) r[a][bj] = dj;
+                }
+            }
+            if (ty == jj) {
+#pragma unroll
+                for (int b = 0; b <= bj; ++b) w[bj][b] = wj[b];
             }
         }
-        __syncthreads();
-        const int a0 = (j >= ty) ? (j - ty) / 16 + 1 : 0;
-        const int b0 = (j >= tx) ? (j - tx) / 16 + 1 : 0;
-        for (int a = a0; a < NB / 16; ++a) {
-            const int i = ty + 16 * a;
-            const double ci = col[i];
-            for (int b = b0; tx + 16 * b <= i; ++b) {
-                const int k = tx + 16 * b;
-                S[i * LDD + k] = fma(-ci, col[k], S[i * LDD + k]);
-            }
-        }
-        __syncthreads();
+        if (failed) break;
     }
     if (failed) {
-        // leave a defined (NaN) factor behind so downstream kernels stay finite-state; info carries the error
         for (int idx = tid; idx < NB * NB; idx += 256) dinv[idx] = 0.0;
         return;
     }
-    // write L back (lower triangle only)
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        if (c < r) A[(int64_t)r * ld + c] = S[r * LDD + c];
-        else if (c == r) A[(int64_t)r * ld + c] = dg[r];
-    }
-    // in-place inverse of the lower-triangular factor (unblocked dtrti2 order: last column first)
-    if (tid < NB) S[tid * LDD + tid] = dg[tid];
-    __syncthreads();
-    const int i = tid >> 1, h = tid & 1;
-    for (int j = NB - 1; j >= 0; --j) {
-        double* cj = col + (j & 1) * NB;
-        if (tid < NB && tid > j) cj[tid] = S[tid * LDD + j];
-        const double wjj = 1.0 / S[j * LDD + j];
-        __syncthreads();
-        double sum = 0.0;
-        if (i > j) {
-            for (int k = j + 1 + h; k <= i; k += 2) sum = fma(S[i * LDD + k], cj[k], sum);
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int i = ty + 16 * a, k = tx + 16 * b;
+            if (b <= a && k <= i) A[(int64_t)i * ld + k] = r[a][b];
+            dinv[i * NB + k] = (b <= a && k <= i) ? w[a][b] : 0.0;
         }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        if (h == 0) {
-            if (i > j) S[i * LDD + j] = -wjj * sum;
-            else if (i == j) S[j * LDD + j] = wjj;
-        }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        dinv[idx] = (c <= r) ? S[r * LDD + c] : 0.0;
-    }
 }
 
 int launch_diag(double* A, int64_t ld, int blk, const LinalgWs& ws, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        GPB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-        configured = true;
-    }
-    potrf_diag_kernel<<<1, 256, DIAG_SMEM, s>>>(A, ld, ws.dinv + (int64_t)blk * NB * NB, ws.info, blk * NB);
+    potrf_diag_kernel<<<1, 256, 0, s>>>(A, ld, ws.dinv + (int64_t)blk * NB * NB, ws.info, blk * NB);
     GPB_CUDA(cudaGetLastError());
     count_launch();
     return 0;
