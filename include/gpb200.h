@@ -96,6 +96,15 @@ int gpb_posterior(gpb_ctx* ctx, const double* q, int64_t m, double* mu, double* 
 int gpb_expected_improvement(gpb_ctx* ctx, const double* q, int64_t m, double y_max, int mode, double* out,
                              double* grad_or_null, int64_t* argmax_or_null);
 
+/* Distributed (one process per GPU) block-column-cyclic Cholesky + log marginal likelihood for N beyond one GPU
+ * (BASELINE.json config 5).  Replaces regression.py:534-539 (build_covariance + cholesky + solve_triangular) when
+ * the matrix is sharded; the only collective on the data path is the NCCL panel broadcast.  Rank 0 creates the
+ * 128-byte NCCL unique id and shares it (torch.distributed / any channel); every rank then calls gpb_dist_init. */
+int gpb_dist_unique_id(char* out128);
+int gpb_dist_init(gpb_ctx* ctx, int rank, int world, const char* id128);
+int gpb_dist_lml(gpb_ctx* ctx, const double* theta, int block, double* lml, int* info, double* seconds_out3);
+int gpb_dist_finalize(gpb_ctx* ctx);
+
 /* CUDA-event phase timings (milliseconds) of the most recent call on this context:
  * names is a ';'-separated list written into name_buf, ms[i] the matching durations. */
 int gpb_timers(gpb_ctx* ctx, char* name_buf, int name_buf_len, double* ms, int max_entries, int* n_entries);

@@ -45,6 +45,10 @@ SIGNATURES = {
     "gpb_spatial_derivatives": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_posterior": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_expected_improvement": (C.c_int, [_ctx_p, _dp, C.c_int64, C.c_double, C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
+    "gpb_dist_unique_id": (C.c_int, [C.c_char_p]),
+    "gpb_dist_init": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_char_p]),
+    "gpb_dist_lml": (C.c_int, [_ctx_p, _dp, C.c_int, _dp, _ip, _dp]),
+    "gpb_dist_finalize": (C.c_int, [_ctx_p]),
     "gpb_timers": (C.c_int, [_ctx_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
     "gpb_dev_alloc": (C.c_int, [_ctx_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "gpb_dev_free": (C.c_int, [_ctx_p, C.c_void_p]),
@@ -261,6 +265,21 @@ class Engine:
     def sync(self):
         self._check(self.lib.gpb_sync(self._ctx))
 
+    # ---------------------------------------------------------------- distributed Cholesky (one process per GPU)
+    def dist_init(self, rank: int, world: int, unique_id: bytes | None):
+        uid = C.create_string_buffer(unique_id if unique_id else b"\0" * 128, 128)
+        self._check(self.lib.gpb_dist_init(self._ctx, rank, world, uid))
+
+    def dist_lml(self, theta, block: int = 1024):
+        th = _f64(theta)
+        val, info = C.c_double(0), C.c_int(0)
+        secs = (C.c_double * 3)()
+        self._check(self.lib.gpb_dist_lml(self._ctx, _ptr(th), block, C.byref(val), C.byref(info), secs))
+        return val.value, info.value, {"assemble_s": secs[0], "factor_s": secs[1], "total_s": secs[2]}
+
+    def dist_finalize(self):
+        self._check(self.lib.gpb_dist_finalize(self._ctx))
+
     def timers(self):
         names = C.create_string_buffer(1024)
         ms = (C.c_double * 64)()
@@ -282,3 +301,12 @@ def device_count() -> int:
     if lib.gpb_device_count(C.byref(cnt)) != 0:
         raise EngineError(lib.gpb_last_error().decode())
     return cnt.value
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on rank 0 and share it with the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.gpb_dist_unique_id(buf) != 0:
+        raise EngineError(lib.gpb_last_error().decode())
+    return buf.raw

@@ -1,13 +1,7 @@
 // C-ABI of libgpb200 (declared in include/gpb200.h): context, device state and the host-side drivers
 // that string the kernels together.  No CPU arithmetic on the path: the host only maps the log
 // hyper-parameters (a handful of exp() calls), sequences launches and moves results.
-#include "../../include/gpb200.h"
-#include "kernels.cuh"
-
-#include <algorithm>
-#include <cmath>
-#include <cstring>
-#include <utility>
+#include "ctx.cuh"
 
 namespace gpb {
 static thread_local std::string g_last_error;
@@ -17,81 +11,9 @@ void count_launch(int n) { g_launches += n; }
 int64_t launch_count() { return g_launches; }
 double gemm_flops_issued();  // gemm_dmma.cu
 
-namespace {
-
-struct PhaseTimer {
-    std::vector<std::pair<std::string, cudaEvent_t>> marks;
-    std::vector<cudaEvent_t> pool;
-    cudaStream_t s = nullptr;
-    void reset() {
-        for (auto& m : marks) pool.push_back(m.second);
-        marks.clear();
-    }
-    void mark(const char* name) {  // the interval that ENDS at the next mark is attributed to `name`
-        cudaEvent_t e;
-        if (!pool.empty()) {
-            e = pool.back();
-            pool.pop_back();
-        } else {
-            cudaEventCreate(&e);
-        }
-        cudaEventRecord(e, s);
-        marks.emplace_back(name, e);
-    }
-    ~PhaseTimer() {
-        reset();
-        for (auto e : pool) cudaEventDestroy(e);
-    }
-};
-
-template <typename T>
-int ensure(T*& p, size_t& cap, size_t bytes) {
-    if (cap >= bytes && p) return 0;
-    if (p) GPB_CUDA(cudaFree(p));
-    p = nullptr;
-    cap = 0;
-    GPB_CUDA(cudaMalloc(&p, bytes));
-    cap = bytes;
-    return 0;
-}
-
-}  // namespace
 }  // namespace gpb
 
 using namespace gpb;
-
-struct gpb_ctx {
-    int device = 0;
-    cudaStream_t s = nullptr;
-    int64_t n = 0, npad = 0;
-    int d = 0;
-    double *x = nullptr, *y = nullptr, *noise = nullptr, *ycov = nullptr;
-    bool has_noise = false, has_ycov = false;
-    double xbar[MAX_DIM] = {0};
-    int ncomp = 0, kinds[MAX_COMP] = {0}, theta_off[MAX_COMP] = {0}, mean_kind = 0, n_mean = 0, n_cov = 0;
-    bool model_set = false;
-    double* theta_dev = nullptr;
-    size_t theta_dev_cap = 0;
-    // fitted state (set_hyperparameters)
-    double *Lfit = nullptr, *dinv_fit = nullptr, *alpha = nullptr, *mu = nullptr;
-    size_t Lfit_cap = 0, dinv_fit_cap = 0, alpha_cap = 0, mu_cap = 0;
-    std::vector<double> theta_fit;
-    bool fitted = false;
-    CovParams cp_fit;
-    MeanParams mp_fit;
-    // objective-evaluation workspace
-    double *Kwork = nullptr, *dinv_work = nullptr, *W = nullptr, *Kinv = nullptr, *partials = nullptr,
-           *grad_dev = nullptr, *vec = nullptr, *resid = nullptr, *alpha_work = nullptr, *scal = nullptr, *tmp = nullptr;
-    size_t Kwork_cap = 0, dinv_work_cap = 0, W_cap = 0, Kinv_cap = 0, partials_cap = 0, grad_cap = 0, vec_cap = 0,
-           resid_cap = 0, alpha_work_cap = 0, scal_cap = 0, tmp_cap = 0;
-    int64_t tmp_rows = 0;
-    int* info_dev = nullptr;
-    // predict workspace
-    double *S = nullptr, *dots = nullptr, *G = nullptr, *qbuf = nullptr, *o1 = nullptr, *o2 = nullptr, *o3 = nullptr,
-           *R_dev = nullptr;
-    size_t S_cap = 0, dots_cap = 0, G_cap = 0, qbuf_cap = 0, o1_cap = 0, o2_cap = 0, o3_cap = 0, R_cap = 0;
-    PhaseTimer timer;
-};
 
 namespace {
 
@@ -187,6 +109,15 @@ int ensure_linalg_ws(gpb_ctx* c) {
     return 0;
 }
 
+}  // namespace
+namespace gpb {
+int ctx_use(gpb_ctx* c) { return use(c); }
+int ctx_need_model(gpb_ctx* c) { return need_model(c); }
+int ctx_make_cov_params(gpb_ctx* c, const double* t, CovParams& cp) { return make_cov_params(c, t, cp); }
+void ctx_make_mean_params(gpb_ctx* c, const double* t, MeanParams& mp) { make_mean_params(c, t, mp); }
+}  // namespace gpb
+namespace {
+
 LinalgWs ws_of(gpb_ctx* c, double* dinv) { return LinalgWs{dinv, c->tmp, c->tmp_rows, c->info_dev}; }
 
 // assemble K(theta)+sig into `K` (lower tiles), factor in place, solve for alpha.
@@ -253,6 +184,7 @@ void gpb_ctx_destroy(gpb_ctx* c) {
                       c->tmp, c->S, c->dots, c->G, c->qbuf, c->o1, c->o2, c->o3, c->R_dev};
     for (double* p : ptrs)
         if (p) cudaFree(p);
+    dist_destroy(c);
     if (c->info_dev) cudaFree(c->info_dev);
     c->timer.reset();
     cudaStreamDestroy(c->s);

@@ -89,6 +89,37 @@ __global__ void __launch_bounds__(256) assemble_train_kernel(const CovParams cp,
     }
 }
 
+// Rectangular block rows [row0, ..) x cols [col0, ..) of K(theta)+diag terms into a panel buffer
+// (distributed Cholesky: every rank assembles only the block columns it owns).  grid = (ncols/128, nrows/128)
+__global__ void __launch_bounds__(256) assemble_block_kernel(const CovParams cp, const double* __restrict__ x, int n,
+                                                             const double* __restrict__ noise_var, int row0, int col0,
+                                                             double* __restrict__ out, int64_t ld) {
+    __shared__ double xs[TILE * MAX_DIM];
+    const int r0 = row0 + blockIdx.y * TILE, c0 = col0 + blockIdx.x * TILE;
+    const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
+    const int d = cp.d;
+    for (int idx = tid; idx < TILE * d; idx += 256) xs[idx] = x[(int64_t)r0 * d + idx];
+    const int gj = c0 + col;
+    double xj[MAX_DIM];
+#pragma unroll
+    for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d) ? x[(int64_t)gj * d + k] : 0.0;
+    __syncthreads();
+    for (int r = 0; r < TILE / 2; ++r) {
+        const int i = half * (TILE / 2) + r;
+        const int gi = r0 + i;
+        double d2[MAX_DIM];
+#pragma unroll
+        for (int k = 0; k < MAX_DIM; ++k) {
+            const double df = (k < d) ? xs[i * d + k] - xj[k] : 0.0;
+            d2[k] = df * df;
+        }
+        double v = cov_from_d2(cp, d2);
+        if (gi == gj) v += diag_terms(cp, gi, noise_var);
+        if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
+        out[(int64_t)(gi - row0) * ld + (gj - col0)] = v;
+    }
+}
+
 // K (without sig) and every dK/dtheta plane, dense n x n each (covariance.py:268-276, 350-365,
 // 171-175, 682-686).  API-parity path for small N; one thread per element.
 __global__ void assemble_grads_kernel(const CovParams cp, const double* __restrict__ x, int n, double* __restrict__ K,
@@ -375,6 +406,13 @@ int launch_assemble_train(const CovParams& cp, const double* x, int n, int npad,
                           const double* y_cov, double* K, int64_t ld, int mirror, cudaStream_t s) {
     const int nb = npad / TILE;
     assemble_train_kernel<<<nb * (nb + 1) / 2, 256, 0, s>>>(cp, x, n, noise_var, y_cov, K, ld, mirror);
+    GPB_LAUNCH_CHECK();
+}
+
+int launch_assemble_block(const CovParams& cp, const double* x, int n, const double* noise_var, int row0, int nrows,
+                          int col0, int ncols, double* out, int64_t ld, cudaStream_t s) {
+    dim3 grid(ncols / TILE, nrows / TILE);
+    assemble_block_kernel<<<grid, 256, 0, s>>>(cp, x, n, noise_var, row0, col0, out, ld);
     GPB_LAUNCH_CHECK();
 }
 

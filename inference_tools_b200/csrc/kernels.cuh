@@ -9,6 +9,9 @@ namespace gpb {
 // triangle).  Padded rows/cols (>= n) hold the identity.
 int launch_assemble_train(const CovParams& cp, const double* x, int n, int npad, const double* noise_var,
                           const double* y_cov, double* K, int64_t ld, int mirror, cudaStream_t s);
+// rectangular block of the same matrix into a panel buffer (rows/cols multiples of 128, within npad)
+int launch_assemble_block(const CovParams& cp, const double* x, int n, const double* noise_var, int row0, int nrows,
+                          int col0, int ncols, double* out, int64_t ld, cudaStream_t s);
 // dK/dtheta_p planes for the covariance_and_gradients API (small N; dense output, np x n x n)
 int launch_assemble_grads(const CovParams& cp, const double* x, int n, double* K, double* dK, cudaStream_t s);
 // generic cross covariance cov(u, v) (covariance.py:240-245, 335-341): out is m x n row-major

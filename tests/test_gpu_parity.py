@@ -327,3 +327,21 @@ def test_size_independent_properties_at_baseline_scale():
         dt[i] = 1e-5
         fd = (m.marginal_likelihood(theta + dt) - m.marginal_likelihood(theta - dt)) / 2e-5
         assert abs(fd - grad[i]) <= 2e-5 * max(1.0, np.abs(grad).max())
+
+
+@pytest.mark.parametrize("n,block", [(700, 128), (1500, 256), (2048, 512)])
+def test_block_cyclic_sweep_single_rank_matches_dense_path(n, block):
+    """The distributed Cholesky driver (dist.cu) with world = 1: same LML as the dense single-GPU path and as the
+    oracle; the multi-rank run is exercised by tools/dist_cholesky.py under torchrun (profiles/)."""
+    x, y, e = synth(77 + n, n, 2)
+    theta = np.array([0.2, 0.1, np.log(0.3), np.log(0.25)])
+    eng = _lib.Engine()
+    eng.set_data(x, y, e**2)
+    eng.set_model([_lib.COV_SE], _lib.MEAN_CONST)
+    eng.dist_init(0, 1, None)
+    lml_d, info, _ = eng.dist_lml(theta, block)
+    lml_s, info_s = eng.lml(theta)
+    ref = orc.marginal_likelihood(x, y, ("SE",), "const", theta, e**2)
+    assert info == 0 and info_s == 0
+    assert abs(lml_d - ref) <= TOL * abs(ref) and abs(lml_s - ref) <= TOL * abs(ref)
+    eng.close()

@@ -1,0 +1,68 @@
+"""Distributed block-column-cyclic Cholesky / LML (BASELINE.json config 5), one process per GPU.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
+        tools/dist_cholesky.py --size 131072 --block 1024 [--check]
+
+SquaredExponential 2-D, fixed theta.  torch.distributed (NCCL/gloo) is only the rendezvous: it carries the NCCL
+unique id to the ranks and the max-over-ranks timing; the panel broadcasts run inside libgpb200 (dist.cu).
+--check compares with the single-GPU gpb_lml on rank 0 (only for N that fits one GPU)."""
+import argparse, json, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from inference_tools_b200 import _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size", type=int, default=131072)
+ap.add_argument("--dim", type=int, default=2)
+ap.add_argument("--block", type=int, default=1024)
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--check", action="store_true")
+ap.add_argument("--out", default="")
+a = ap.parse_args()
+
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+uid = [_lib.nccl_unique_id() if (rank == 0 and world > 1) else None]
+if world > 1:
+    dist.broadcast_object_list(uid, src=0)
+
+rng = np.random.default_rng(5)
+x = rng.uniform(0, 1, (a.size, a.dim))
+y = np.sin(3 * x).sum(axis=1) + rng.normal(0, 0.05, a.size)
+theta = np.array([0.2, 0.1] + [np.log(0.3)] * a.dim)
+eng = _lib.Engine(local)
+eng.set_data(x, y, np.full(a.size, 0.05**2))
+eng.set_model([_lib.COV_SE], _lib.MEAN_CONST)
+eng.dist_init(rank, world, uid[0])
+res = []
+for r in range(a.reps + 1):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lml, info, t = eng.dist_lml(theta, a.block)
+    tt = torch.tensor([t["assemble_s"], t["factor_s"], t["total_s"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    res.append((lml, info, tt.tolist()))
+if rank == 0:
+    best = min(res[1:], key=lambda v: v[2][1])
+    npad = (a.size + 127) // 128 * 128
+    out = {"n": a.size, "d": a.dim, "block": a.block, "world": world, "lml": best[0], "info": best[1], "assemble_s": best[2][0],
+           "factor_s": best[2][1], "total_s": best[2][2], "cholesky_tflops_aggregate": npad**3 / 3 / best[2][1] / 1e12,
+           "cholesky_tflops_per_gpu": npad**3 / 3 / best[2][1] / 1e12 / world, "lml_all_reps": [v[0] for v in res]}
+    if a.check:
+        ref, info = eng.lml(theta)
+        out["single_gpu_lml"] = ref
+        out["rel_diff"] = abs(best[0] - ref) / abs(ref)
+    print(json.dumps(out))
+    if a.out:
+        os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+        json.dump(out, open(a.out, "w"), indent=1)
+eng.dist_finalize()
+if world > 1:
+    dist.destroy_process_group()
