@@ -464,15 +464,64 @@ int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int
     return 0;
 }
 
-int gpb_loo(gpb_ctx* c, const double*, double*, double*, int*) {
+int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* info) {
     GPB_TRY(use(c));
-    set_error("gpb_loo: leave-one-out objective is not implemented yet (SURVEY.md section 8f rank 2)");
-    return -3;
+    GPB_TRY(need_model(c));
+    c->timer.reset();
+    const size_t np = (size_t)c->npad;
+    const int npad = (int)c->npad, n = (int)c->n, nt = c->n_mean + c->n_cov;
+    GPB_TRY(ensure_linalg_ws(c));
+    GPB_TRY(ensure(c->Kwork, c->Kwork_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->W, c->W_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->Kinv, c->Kinv_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->grad_dev, c->grad_cap, sizeof(double) * (nt + 2)));
+    GPB_TRY(ensure(c->partials, c->partials_cap, std::max(trace_partials_size(npad), sizeof(double) * 5 * np)));
+    CovParams cp;
+    MeanParams mp;
+    GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
+    make_mean_params(c, theta, mp);
+    int info_h = 0;
+    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, true, c->alpha_work, &info_h));
+    c->timer.mark("trtri");
+    GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+    GPB_TRY(trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s));
+    c->timer.mark("lauum");
+    GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+    c->timer.mark("loo");
+    // the factor (Kwork) and W are dead from here on: reuse them as the dK plane and the product buffer
+    GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2), c->s));
+    GPB_TRY(launch_loo(cp, mp, c->n_mean, c->x, n, npad, c->alpha_work, c->Kinv, npad, c->partials, c->Kwork, c->W,
+                       c->scal, grad ? c->grad_dev : nullptr, c->s));
+    double val = 0.0;
+    GPB_CUDA(cudaMemcpyAsync(&val, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->s));
+    if (grad) GPB_CUDA(cudaMemcpyAsync(grad, c->grad_dev, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->s));
+    c->timer.mark("end");
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    *info = info_h;
+    *loo = val;
+    return 0;
 }
-int gpb_loo_predictions(gpb_ctx* c, double*, double*) {
+
+int gpb_loo_predictions(gpb_ctx* c, double* mu, double* sigma) {
     GPB_TRY(use(c));
-    set_error("gpb_loo_predictions: not implemented yet (SURVEY.md section 8f rank 2)");
-    return -3;
+    if (!c->fitted) {
+        set_error("gpb_loo_predictions: no fitted state (call gpb_factor)");
+        return -2;
+    }
+    const size_t np = (size_t)c->npad;
+    const int npad = (int)c->npad, n = (int)c->n;
+    GPB_TRY(ensure(c->W, c->W_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->Kinv, c->Kinv_cap, sizeof(double) * np * np));
+    GPB_TRY(ensure(c->partials, c->partials_cap, std::max(trace_partials_size(npad), sizeof(double) * 5 * np)));
+    GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+    GPB_TRY(trtri_lower(c->Lfit, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_fit), c->Kinv, npad, c->s));
+    GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+    double* out = c->partials;
+    GPB_TRY(launch_loo_predictions(c->Kinv, npad, c->alpha, c->y, n, out, out + np, c->s));
+    GPB_CUDA(cudaMemcpyAsync(mu, out, sizeof(double) * n, cudaMemcpyDeviceToHost, c->s));
+    GPB_CUDA(cudaMemcpyAsync(sigma, out + np, sizeof(double) * n, cudaMemcpyDeviceToHost, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
 }
 
 }  // extern "C"

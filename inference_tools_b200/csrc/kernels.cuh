@@ -77,4 +77,12 @@ size_t trace_partials_size(int npad);
 int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad, const double* alpha, const double* Kinv, int64_t ld,
                     double* partials, double* grad_dev, cudaStream_t s);
 
+// ---- loo.cu : leave-one-out objective (regression.py:451-526)
+int launch_symmetrize(double* A, int64_t ld, int n, cudaStream_t s);
+int launch_loo_predictions(const double* Kinv, int64_t ld, const double* alpha, const double* y, int n, double* mu,
+                           double* sigma, cudaStream_t s);
+int launch_loo(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad,
+               const double* alpha, double* Kinv, int64_t ld, double* ws, double* Dk, double* T, double* val_dev,
+               double* grad_dev, cudaStream_t s);
+
 }  // namespace gpb

@@ -345,3 +345,42 @@ def test_block_cyclic_sweep_single_rank_matches_dense_path(n, block):
     assert info == 0 and info_s == 0
     assert abs(lml_d - ref) <= TOL * abs(ref) and abs(lml_s - ref) <= TOL * abs(ref)
     eng.close()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "loo" in load_golden(n)])
+def test_loo_against_reference_fixtures(name):
+    g = load_golden(name)
+    m = fitted(g)
+    assert abs(m.loo_likelihood(g["theta"]) - g["loo"]) <= TOL * abs(g["loo"])
+    val, grad = m.loo_likelihood_gradient(g["theta"])
+    assert abs(val - g["loo_from_grad"]) <= TOL * abs(g["loo_from_grad"])
+    assert np.abs(grad - g["loo_grad"]).max() <= 1e-8 * np.abs(g["loo_grad"]).max()
+    mu, sig = m.loo_predictions()
+    assert rel_err(mu, g["loo_mu"]) < TOL and rel_err(sig, g["loo_sig"]) < TOL
+
+
+@pytest.mark.parametrize("n,d,comps,mean", [(300, 3, ("RQ", "WHITE"), "linear"), (150, 1, ("SE", "HETERO"), "const"),
+                                            (520, 2, ("SE",), "quadratic")])
+def test_loo_against_oracle(n, d, comps, mean):
+    x, y, e = synth(500 + n, n, d)
+    rng = np.random.default_rng(n)
+    tm = {"const": [0.3], "linear": [0.3] + [0.1] * d, "quadratic": [0.3] + [0.1] * d + [-0.05] * d}[mean]
+    tc = []
+    for c in comps:
+        tc += {"SE": [0.1] + [np.log(0.35)] * d, "RQ": [-0.2, 0.8] + [np.log(0.3)] * d, "WHITE": [np.log(0.04)],
+               "HETERO": list(np.log(0.05) + 0.2 * rng.standard_normal(n))}[c]
+    theta = np.array(tm + tc)
+    m = gp.GpRegressor(x, y, y_err=e, kernel=make_kernel(gp, comps), mean=make_mean(gp, mean), hyperpars=theta)
+    val_o, grad_o = orc.loo_likelihood_gradient(x, y, comps, mean, theta, e**2)
+    val, grad = m.loo_likelihood_gradient(theta)
+    assert abs(val - val_o) <= TOL * abs(val_o)
+    assert np.abs(grad - grad_o).max() <= 1e-8 * np.abs(grad_o).max()
+    assert abs(m.loo_likelihood(theta) - orc.loo_likelihood(x, y, comps, mean, theta, e**2)) <= TOL * abs(val_o)
+
+
+def test_cross_validation_model_selection_runs():
+    x, y, e = synth(21, 60, 1)
+    np.random.seed(4)
+    m = gp.GpRegressor(x, y, y_err=e, cross_val=True, n_starts=3)
+    assert np.isfinite(m.loo_likelihood(m.hyperpars))
+    assert m.model_selector == m.loo_likelihood
