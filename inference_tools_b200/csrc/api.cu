@@ -10,6 +10,7 @@ static int64_t g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 int64_t launch_count() { return g_launches; }
 double gemm_flops_issued();  // gemm_dmma.cu
+void credit_gemm_flops(double f);
 
 }  // namespace gpb
 
@@ -120,6 +121,61 @@ namespace {
 
 LinalgWs ws_of(gpb_ctx* c, double* dinv) { return LinalgWs{dinv, c->tmp, c->tmp_rows, c->info_dev}; }
 
+std::string pkey(const char* tag, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> dims) {
+    std::string k(tag);
+    for (const void* p : ptrs) k += ":" + std::to_string(reinterpret_cast<uintptr_t>(p));
+    for (int64_t v : dims) k += "/" + std::to_string(v);
+    return k;
+}
+
+// Run a launch sequence whose arguments are only device pointers and shapes.  First use: plain launches (also
+// performs the one-time kernel attribute setup).  Second use: the same sequence is captured into a CUDA graph;
+// from then on every call is one cudaGraphLaunch -- the recursion issues hundreds of short kernels whose host
+// launch cost otherwise dominates for N <= 8192.  GPB200_NO_GRAPHS=1 disables the cache.
+template <class F>
+int run_graphed(gpb_ctx* c, const std::string& key, F&& body) {
+    if (!c->use_graphs) return body();
+    auto& e = c->graphs[key];
+    if (e.exec) {
+        GPB_CUDA(cudaGraphLaunch(e.exec, c->s));
+        count_launch((int)e.launches);
+        credit_gemm_flops(e.flops);
+        return 0;
+    }
+    if (e.uses++ == 0) return body();
+    const int64_t l0 = launch_count();
+    const double f0 = gemm_flops_issued();
+    GPB_CUDA(cudaStreamBeginCapture(c->s, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->s, &g);
+    if (rc != 0 || ce != cudaSuccess || g == nullptr) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        c->use_graphs = false;  // fall back to plain launches for the rest of this context's life
+        if (rc != 0) return rc;
+        return body();
+    }
+    e.launches = launch_count() - l0;
+    e.flops = gemm_flops_issued() - f0;
+    const cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) {
+        e.exec = nullptr;
+        cudaGetLastError();
+        c->use_graphs = false;
+        return body();
+    }
+    GPB_CUDA(cudaGraphLaunch(e.exec, c->s));
+    return 0;
+}
+
+void clear_graphs(gpb_ctx* c) {
+    for (auto& kv : c->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c->graphs.clear();
+}
+
 // assemble K(theta)+sig into `K` (lower tiles), factor in place, solve for alpha.
 //   resid_out: y - mu (optional copy), v_out: L^-1 r left in c->vec[npad..) when !want_alpha
 int assemble_and_factor(gpb_ctx* c, const CovParams& cp, const MeanParams& mp, double* K, double* dinv, double* mu_out,
@@ -129,16 +185,20 @@ int assemble_and_factor(gpb_ctx* c, const CovParams& cp, const MeanParams& mp, d
     GPB_TRY(launch_assemble_train(cp, c->x, n, npad, c->has_noise ? c->noise : nullptr,
                                   c->has_ycov ? c->ycov : nullptr, K, npad, 0, c->s));
     c->timer.mark("potrf");
-    GPB_TRY(potrf_lower(K, npad, npad, ws_of(c, dinv), c->s));
+    GPB_TRY(run_graphed(c, pkey("potrf", {K, dinv, c->tmp, c->info_dev}, {npad}),
+                        [&]() { return potrf_lower(K, npad, npad, ws_of(c, dinv), c->s); }));
     c->timer.mark("solve");
     GPB_TRY(launch_residual(mp, c->x, c->y, n, npad, c->vec, mu_out, c->s));
-    GPB_CUDA(cudaMemcpyAsync(c->resid, c->vec, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
-    GPB_TRY(trsv_lower_fwd(K, npad, npad, dinv, c->vec, c->s));
-    if (want_alpha) {
-        GPB_CUDA(cudaMemcpyAsync(c->vec, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
-        GPB_TRY(trsv_lower_bwd(K, npad, npad, dinv, c->vec, c->s));
-        GPB_CUDA(cudaMemcpyAsync(alpha_out, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
-    }
+    GPB_TRY(run_graphed(c, pkey("solve", {K, dinv, c->vec, c->resid, alpha_out}, {npad, want_alpha}), [&]() -> int {
+        GPB_CUDA(cudaMemcpyAsync(c->resid, c->vec, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+        GPB_TRY(trsv_lower_fwd(K, npad, npad, dinv, c->vec, c->s));
+        if (want_alpha) {
+            GPB_CUDA(cudaMemcpyAsync(c->vec, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+            GPB_TRY(trsv_lower_bwd(K, npad, npad, dinv, c->vec, c->s));
+            GPB_CUDA(cudaMemcpyAsync(alpha_out, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+        }
+        return 0;
+    }));
     GPB_CUDA(cudaMemcpyAsync(info_host, c->info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s));
     return 0;
 }
@@ -171,6 +231,7 @@ int gpb_ctx_create(int device, gpb_ctx** out) {
     c->device = device;
     GPB_CUDA(cudaStreamCreateWithFlags(&c->s, cudaStreamNonBlocking));
     c->timer.s = c->s;
+    c->use_graphs = getenv("GPB200_NO_GRAPHS") == nullptr;
     *out = c;
     return 0;
 }
@@ -185,6 +246,7 @@ void gpb_ctx_destroy(gpb_ctx* c) {
     for (double* p : ptrs)
         if (p) cudaFree(p);
     dist_destroy(c);
+    clear_graphs(c);
     if (c->info_dev) cudaFree(c->info_dev);
     c->timer.reset();
     cudaStreamDestroy(c->s);
@@ -202,6 +264,7 @@ int gpb_set_data(gpb_ctx* c, const double* x, int64_t n, int d, const double* y,
         if (*p) cudaFree(*p);
         *p = nullptr;
     }
+    clear_graphs(c);
     c->n = n;
     c->d = d;
     c->npad = round_up(n, NB);
@@ -446,8 +509,10 @@ int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int
     // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
     GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
     c->timer.mark("trtri");
-    GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
-    GPB_TRY(trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s));
+    GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
+        GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+        return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
+    }));
     c->timer.mark("lauum");
     GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
     c->timer.mark("trace");
@@ -483,8 +548,10 @@ int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* inf
     int info_h = 0;
     GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, true, c->alpha_work, &info_h));
     c->timer.mark("trtri");
-    GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
-    GPB_TRY(trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s));
+    GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
+        GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+        return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
+    }));
     c->timer.mark("lauum");
     GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
     c->timer.mark("loo");
@@ -587,7 +654,8 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
         c->timer.mark("mean_dot");
         GPB_TRY(launch_row_dot(c->S, npad, rows, npad, c->alpha, c->dots, c->s));
         c->timer.mark("trsm");
-        GPB_TRY(trsm_right_lt(c->S, npad, rows_pad, c->Lfit, npad, npad, 0, ws, c->s));
+        GPB_TRY(run_graphed(c, pkey("ptrsm", {c->S, c->Lfit, c->dinv_fit, c->tmp}, {npad, rows_pad}),
+                            [&]() { return trsm_right_lt(c->S, npad, rows_pad, c->Lfit, npad, npad, 0, ws, c->s); }));
         c->timer.mark("gram");
         GPB_TRY(launch_row_gram(c->S, npad, mq, ns, npad, c->G, c->s));
         c->timer.mark("finalize");

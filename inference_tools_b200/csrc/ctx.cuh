@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <utility>
 
 namespace gpb {
@@ -82,6 +83,15 @@ struct gpb_ctx {
            *R_dev = nullptr;
     size_t S_cap = 0, dots_cap = 0, G_cap = 0, qbuf_cap = 0, o1_cap = 0, o2_cap = 0, o3_cap = 0, R_cap = 0;
     gpb::PhaseTimer timer;
+    // CUDA-graph cache of the pointer/shape-only launch sequences (potrf, solves, inverse, predict solve)
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int uses = 0;
+        int64_t launches = 0;
+        double flops = 0.0;
+    };
+    std::map<std::string, GraphEntry> graphs;
+    bool use_graphs = true;
     gpb_dist* dist = nullptr;
 };
 

@@ -16,19 +16,29 @@
 // enumerating lower tiles only (GEMM_LOWER).
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace gpb {
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int BK = 16;
 constexpr int LDSK = 20;  // padded smem row length (doubles)
 constexpr int STAGES = 3;
 constexpr int THREADS = 128;
-constexpr int LDSM_A = BM + 4;  // m-major A tile: 16 rows of 132 doubles (132 mod 16 == 4 -> conflict free)
-constexpr int LDSM_B = BN + 4;  // n-major B tile: 16 rows of 68 doubles
-constexpr int A_STAGE = BM * LDSK;  // 2560 >= BK * LDSM_A (2112)
-constexpr int B_STAGE = BN * LDSK;  // 1280 >= BK * LDSM_B (1088)
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);  // 92160
+// Two tile configurations (4 warps as 2 x 2, warp tile = 8*WMT x 8*WNT):
+//   big   WMT=8, WNT=4: CTA 128 x 64, 2 CTAs/SM  -- throughput configuration
+//   small WMT=4, WNT=2: CTA  64 x 32, 4+ CTAs/SM -- latency configuration for launches that cannot fill the
+//                       machine with big tiles (the leaves and low levels of the recursive drivers)
+template <int WMT, int WNT>
+struct Cfg {
+    static constexpr int BM = 16 * WMT, BN = 16 * WNT;
+    static constexpr int LDSM_A = BM + 4;  // m-major A tile rows: (BM + 4) mod 16 == 4 -> conflict free
+    static constexpr int LDSM_B = BN + 4;
+    static constexpr int A_STAGE = BM * LDSK;  // >= BK * LDSM_A
+    static constexpr int B_STAGE = BN * LDSK;  // >= BK * LDSM_B
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);  // 92160 / 46080
+    static constexpr int MIN_CTAS = WMT == 8 ? 2 : 4;
+};
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -45,8 +55,11 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-template <bool AKM, bool BKM>  // operand stored k-major (k contiguous) or not
-__global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, const int tiles_n) {
+template <bool AKM, bool BKM, int WMT, int WNT>  // operand stored k-major (k contiguous) or not; warp tile
+__global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel(const GemmArgs p, const int tiles_n) {
+    using C = Cfg<WMT, WNT>;
+    constexpr int BM = C::BM, BN = C::BN, LDSM_A = C::LDSM_A, LDSM_B = C::LDSM_B, A_STAGE = C::A_STAGE,
+                  B_STAGE = C::B_STAGE;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
@@ -81,16 +94,18 @@ __global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, con
     if (AKM) {  // 128 rows x 8 chunks: thread owns chunk (tid & 7) of rows (tid >> 3) + 16 i
         Ag = p.A + (int64_t)(row0 + (tid >> 3)) * p.lda + k_begin + (tid & 7) * 2;
         as_w = As + (tid >> 3) * LDSK + (tid & 7) * 2;
-    } else {    // 16 k-rows x 64 chunks: thread owns chunk (tid & 63) of k-rows (tid >> 6) + 2 i
-        Ag = p.A + (int64_t)(k_begin + (tid >> 6)) * p.lda + row0 + (tid & 63) * 2;
-        as_w = As + (tid >> 6) * LDSM_A + (tid & 63) * 2;
+    } else {    // 16 k-rows x BM/2 chunks: thread owns chunk (tid % CPR) of k-rows tid / CPR + (128 / CPR) i
+        constexpr int CPR = BM / 2;
+        Ag = p.A + (int64_t)(k_begin + tid / CPR) * p.lda + row0 + (tid % CPR) * 2;
+        as_w = As + (tid / CPR) * LDSM_A + (tid % CPR) * 2;
     }
     if (BKM) {
         Bg = p.B + (int64_t)(col0 + (tid >> 3)) * p.ldb + k_begin + (tid & 7) * 2;
         bs_w = Bs + (tid >> 3) * LDSK + (tid & 7) * 2;
-    } else {    // 16 k-rows x 32 chunks: thread owns chunk (tid & 31) of k-rows (tid >> 5) + 4 i
-        Bg = p.B + (int64_t)(k_begin + (tid >> 5)) * p.ldb + col0 + (tid & 31) * 2;
-        bs_w = Bs + (tid >> 5) * LDSM_B + (tid & 31) * 2;
+    } else {    // 16 k-rows x BN/2 chunks
+        constexpr int CPR = BN / 2;
+        Bg = p.B + (int64_t)(k_begin + tid / CPR) * p.ldb + col0 + (tid % CPR) * 2;
+        bs_w = Bs + (tid / CPR) * LDSM_B + (tid % CPR) * 2;
     }
 
     auto load_stage = [&](int stage, int kt) {
@@ -100,9 +115,10 @@ __global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, con
 #pragma unroll
             for (int i = 0; i < BM / 16; ++i) cp_async16(as + i * 16 * LDSK, a + (int64_t)i * 16 * p.lda);
         } else {
+            constexpr int RPP = THREADS / (BM / 2);  // k-rows per pass
             const double* a = Ag + (int64_t)kt * BK * p.lda;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cp_async16(as + i * 2 * LDSM_A, a + (int64_t)i * 2 * p.lda);
+            for (int i = 0; i < BK / RPP; ++i) cp_async16(as + i * RPP * LDSM_A, a + (int64_t)i * RPP * p.lda);
         }
         double* bs = bs_w + stage * B_STAGE;
         if (BKM) {
@@ -110,17 +126,18 @@ __global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, con
 #pragma unroll
             for (int i = 0; i < BN / 16; ++i) cp_async16(bs + i * 16 * LDSK, b + (int64_t)i * 16 * p.ldb);
         } else {
+            constexpr int RPP = THREADS / (BN / 2);
             const double* b = Bg + (int64_t)kt * BK * p.ldb;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cp_async16(bs + i * 4 * LDSM_B, b + (int64_t)i * 4 * p.ldb);
+            for (int i = 0; i < BK / RPP; ++i) cp_async16(bs + i * RPP * LDSM_B, b + (int64_t)i * RPP * p.ldb);
         }
     };
 
-    double acc[8][4][2];
+    double acc[WMT][WNT][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < WMT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < WNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -132,8 +149,8 @@ __global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, con
     const int wm = warp >> 1, wn = warp & 1;
     const int g = lane >> 2, t = lane & 3;
     // fragment read origins: A(row g, k t) / B(col g, k t) of the warp tile
-    const double* as_r = AKM ? As + (wm * 64 + g) * LDSK + t : As + t * LDSM_A + wm * 64 + g;
-    const double* bs_r = BKM ? Bs + (wn * 32 + g) * LDSK + t : Bs + t * LDSM_B + wn * 32 + g;
+    const double* as_r = AKM ? As + (wm * 8 * WMT + g) * LDSK + t : As + t * LDSM_A + wm * 8 * WMT + g;
+    const double* bs_r = BKM ? Bs + (wn * 8 * WNT + g) * LDSK + t : Bs + t * LDSM_B + wn * 8 * WNT + g;
     constexpr int A_I = AKM ? 8 * LDSK : 8, A_K = AKM ? 4 : 4 * LDSM_A;   // strides: next 8 rows / next k-step
     constexpr int B_J = BKM ? 8 * LDSK : 8, B_K = BKM ? 4 : 4 * LDSM_B;
 
@@ -150,15 +167,15 @@ __global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, con
         const double* bs = bs_r + stage * B_STAGE;
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ++ks) {
-            double a[8], b[4];
+            double a[WMT], b[WNT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = as[i * A_I + ks * A_K];
+            for (int i = 0; i < WMT; ++i) a[i] = as[i * A_I + ks * A_K];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = bs[j * B_J + ks * B_K];
+            for (int j = 0; j < WNT; ++j) b[j] = bs[j * B_J + ks * B_K];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < WMT; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < WNT; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();
@@ -166,32 +183,32 @@ __global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, con
     // epilogue straight from the accumulator fragments: each lane owns 2 adjacent columns (16 B), a
     // quad covers 64 contiguous bytes of a row -> two fully used 32 B sectors per row
     const double alpha = p.alpha, beta = p.beta;
-    const int r_base = row0 + wm * 64 + g;
-    const int c_base = col0 + wn * 32 + 2 * t;
+    const int r_base = row0 + wm * 8 * WMT + g;
+    const int c_base = col0 + wn * 8 * WNT + 2 * t;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < WMT; ++i) {
         const int64_t r = r_base + 8 * i;
-        double2 v[4];
+        double2 v[WNT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < WNT; ++j) {
             v[j].x = alpha * acc[i][j][0];
             v[j].y = alpha * acc[i][j][1];
         }
         if (beta != 0.0) {
-            double2 c[4];
+            double2 c[WNT];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) c[j] = *reinterpret_cast<const double2*>(p.C + r * p.ldc + c_base + 8 * j);
+            for (int j = 0; j < WNT; ++j) c[j] = *reinterpret_cast<const double2*>(p.C + r * p.ldc + c_base + 8 * j);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < WNT; ++j) {
                 v[j].x = fma(beta, c[j].x, v[j].x);
                 v[j].y = fma(beta, c[j].y, v[j].y);
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p.D + r * p.ldd + c_base + 8 * j) = v[j];
+        for (int j = 0; j < WNT; ++j) *reinterpret_cast<double2*>(p.D + r * p.ldd + c_base + 8 * j) = v[j];
         if (p.D2 != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p.D2 + r * p.ldd2 + c_base + 8 * j) = v[j];
+            for (int j = 0; j < WNT; ++j) *reinterpret_cast<double2*>(p.D2 + r * p.ldd2 + c_base + 8 * j) = v[j];
         }
     }
 }
@@ -201,44 +218,31 @@ __global__ void __launch_bounds__(THREADS, 2) dgemm_kernel(const GemmArgs p, con
 static int64_t g_gemm_launches = 0;
 static double g_gemm_flops = 0.0;
 
-int gemm_nt(const GemmArgs& a, cudaStream_t s) {
-    if (a.M <= 0 || a.N <= 0) return 0;
-    if (a.M % BM || a.N % BN || a.K % BK || a.K < 0) {
-        set_error("gemm_nt: M % 128, N % 64, K % 16 must be 0 (got " + std::to_string(a.M) + "," +
-                  std::to_string(a.N) + "," + std::to_string(a.K) + ")");
-        return -2;
-    }
+template <int WMT, int WNT>
+int launch_cfg(const GemmArgs& a, cudaStream_t s) {
+    using C = Cfg<WMT, WNT>;
+    constexpr int BM = C::BM, BN = C::BN;
     using kern_t = void (*)(const GemmArgs, const int);
     const bool akm = !(a.flags & GEMM_A_MMAJOR), bkm = !(a.flags & GEMM_B_NMAJOR);
-    kern_t kern = akm ? (bkm ? dgemm_kernel<true, true> : dgemm_kernel<true, false>)
-                      : (bkm ? dgemm_kernel<false, true> : dgemm_kernel<false, false>);
+    kern_t kern = akm ? (bkm ? dgemm_kernel<true, true, WMT, WNT> : dgemm_kernel<true, false, WMT, WNT>)
+                      : (bkm ? dgemm_kernel<false, true, WMT, WNT> : dgemm_kernel<false, false, WMT, WNT>);
     static bool configured_dev[64][4] = {};
     int dev = 0;
     GPB_CUDA(cudaGetDevice(&dev));
     bool* configured = configured_dev[dev & 63];
     const int ki = (akm ? 0 : 2) + (bkm ? 0 : 1);
     if (!configured[ki]) {
-        GPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         GPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured[ki] = true;
     }
     const int tm = a.M / BM, tn = a.N / BN;
-    int64_t tiles;
-    if (a.flags & GEMM_LOWER) {
-        // rows beyond N/BM*... : tile row bi has min(2*(bi+1), tn) tiles; require square-ish use: N >= M
-        if (a.N < a.M) {
-            set_error("gemm_nt: GEMM_LOWER needs N >= M");
-            return -2;
-        }
-        tiles = (int64_t)tm * (tm + 1);
-    } else {
-        tiles = (int64_t)tm * tn;
-    }
-    kern<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(a, tn);
+    const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) : (int64_t)tm * tn;
+    kern<<<(unsigned)tiles, THREADS, C::SMEM_BYTES, s>>>(a, tn);
     GPB_CUDA(cudaGetLastError());
     ++g_gemm_launches;
     count_launch();
-    // algorithmic flops of this launch (2 * 128 * 64 * k-extent per computed tile)
+    // algorithmic flops of this launch (2 * BM * BN * k-extent per computed tile)
     if (!(a.flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) {
         g_gemm_flops += (double)tiles * 2.0 * BM * BN * a.K;
     } else {
@@ -259,7 +263,27 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     return 0;
 }
 
+int gemm_nt(const GemmArgs& a, cudaStream_t s) {
+    if (a.M <= 0 || a.N <= 0) return 0;
+    if (a.M % 128 || a.N % 64 || a.K % BK || a.K < 0) {
+        set_error("gemm_nt: M % 128, N % 64, K % 16 must be 0 (got " + std::to_string(a.M) + "," +
+                  std::to_string(a.N) + "," + std::to_string(a.K) + ")");
+        return -2;
+    }
+    if ((a.flags & GEMM_LOWER) && a.N < a.M) {
+        set_error("gemm_nt: GEMM_LOWER needs N >= M");
+        return -2;
+    }
+    // big tiles unless they cannot fill one wave of 2 CTAs per SM (148 SMs)
+    const int64_t tm = a.M / 128, tn = a.N / 64;
+    const int64_t big_tiles = (a.flags & GEMM_LOWER) ? tm * (tm + 1) : tm * tn;
+    static const int force = getenv("GPB200_GEMM_TILE") ? atoi(getenv("GPB200_GEMM_TILE")) : 0;  // 1 = big, 2 = small
+    const bool small = force ? force == 2 : big_tiles < 296;
+    return small ? launch_cfg<4, 2>(a, s) : launch_cfg<8, 4>(a, s);
+}
+
 int64_t gemm_launch_count() { return g_gemm_launches; }
 double gemm_flops_issued() { return g_gemm_flops; }
+void credit_gemm_flops(double f) { g_gemm_flops += f; }
 
 }  // namespace gpb

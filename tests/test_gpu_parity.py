@@ -384,3 +384,28 @@ def test_cross_validation_model_selection_runs():
     m = gp.GpRegressor(x, y, y_err=e, cross_val=True, n_starts=3)
     assert np.isfinite(m.loo_likelihood(m.hyperpars))
     assert m.model_selector == m.loo_likelihood
+
+
+@pytest.mark.parametrize("acq", ["ei", "ucb", "maxvar"])
+def test_gp_optimiser_loop(acq):
+    """tests/gp/test_GpOptimiser.py:21-68 smoke re-pointed: propose/add cycles stay inside the bounds; the batched
+    sweep proposal agrees with the reference-style per-point search on the acquisition value."""
+    def f(x):
+        return np.sin(0.5 * x) * 3 / (2 + 0.1 * x**2)
+
+    rng = np.random.default_rng(3)
+    x = np.array([-8.0, -2.0, 3.0, 8.0])
+    y = f(x)
+    acquisition = {"ei": gp.ExpectedImprovement, "ucb": gp.UpperConfidenceBound, "maxvar": gp.MaxVariance}[acq]
+    np.random.seed(1)
+    opt = gp.GpOptimiser(x, y, bounds=[(-10.0, 10.0)], y_err=np.full(4, 1e-3), acquisition=acquisition, hyperpars=[0.0, 0.5, 1.0])
+    for _ in range(2):
+        new_x = opt.propose_evaluation()
+        assert -10.0 <= new_x <= 10.0
+        opt.add_evaluation(new_x, f(new_x), 1e-3)
+    assert len(opt.iteration_history) == 2 and opt.gp.y.size == 6
+    prop, val = opt.sweep(n_candidates=20000, n_restarts=8, rng=rng)
+    ref, ref_val = opt.multistart_bfgs()
+    assert val <= ref_val + 1e-6 * abs(ref_val) + 1e-9
+    with pytest.raises(ValueError):
+        opt.add_evaluation(0.0, 0.0)

@@ -1,0 +1,52 @@
+"""BASELINE.json config 2: GpRegressor SquaredExponential 3-D, N = 8192, multistart L-BFGS-B on
+marginal_likelihood_gradient.  Reports the whole fit and the per-evaluation cost; --threads T runs the restarts
+on T worker threads (one engine context each, round-robin over the visible GPUs).  CPU reference = oracle port
+of marginal_likelihood_gradient at the same N (one evaluation, --cpu)."""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import inference_tools_b200.gp as gp
+from inference_tools_b200 import _lib
+from oracle.cpu_reference import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size", type=int, default=8192)
+ap.add_argument("--dim", type=int, default=3)
+ap.add_argument("--starts", type=int, default=None)
+ap.add_argument("--threads", type=int, default=1)
+ap.add_argument("--cpu", action="store_true")
+a = ap.parse_args()
+x, y, e = synth(7, a.size, a.dim)
+
+calls = {"n": 0}
+orig = _lib.Engine.lml_grad
+def counted(self, theta):
+    calls["n"] += 1
+    return orig(self, theta)
+_lib.Engine.lml_grad = counted
+
+np.random.seed(7)
+t0 = time.perf_counter()
+m = gp.GpRegressor(x, y, y_err=e, kernel=gp.SquaredExponential, n_starts=a.starts, n_processes=a.threads)
+fit_s = time.perf_counter() - t0
+th = np.asarray(m.hyperpars)
+t0 = time.perf_counter()
+for _ in range(5):
+    m.marginal_likelihood_gradient(th)
+eval_s = (time.perf_counter() - t0) / 5
+out = {"config": f"cfg2: SE {a.dim}D N={a.size} multistart LML-gradient fit", "fit_s": fit_s, "lml_grad_evaluations": calls["n"] - 0,
+       "seconds_per_evaluation": eval_s, "threads": a.threads, "gpus": _lib.device_count(), "theta": th.tolist(),
+       "lml": float(m.marginal_likelihood(th)), "phases_ms": m.engine.timers()}
+if a.cpu:
+    from oracle import gp_oracle as orc
+    t0 = time.perf_counter()
+    lml_o, g_o = orc.marginal_likelihood_gradient(x, y, ("SE",), "const", th, e**2)
+    out["cpu_seconds_per_evaluation"] = time.perf_counter() - t0
+    out["cpu_cores"] = os.cpu_count()
+    lml, g = m.marginal_likelihood_gradient(th)
+    out["parity_lml_rel"] = abs(lml - lml_o) / abs(lml_o)
+    out["parity_grad_normrel"] = float(np.abs(g - g_o).max() / np.abs(g_o).max())
+    out["cpu_fit_s_extrapolated"] = out["cpu_seconds_per_evaluation"] * calls["n"]
+print(json.dumps(out))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open(f"gpurun_out/cfg2_N{a.size}_t{a.threads}.json", "w"), indent=1)
