@@ -24,20 +24,22 @@ namespace {
 constexpr int BK = 16;
 constexpr int LDSK = 20;  // padded smem row length (doubles)
 constexpr int STAGES = 3;
-constexpr int THREADS = 128;
-// Two tile configurations (4 warps as 2 x 2, warp tile = 8*WMT x 8*WNT):
-//   big   WMT=8, WNT=4: CTA 128 x 64, 2 CTAs/SM  -- throughput configuration
-//   small WMT=4, WNT=2: CTA  64 x 32, 4+ CTAs/SM -- latency configuration for launches that cannot fill the
-//                       machine with big tiles (the leaves and low levels of the recursive drivers)
-template <int WMT, int WNT>
+// Tile configurations (warp tile = 8*WMT x 8*WNT DMMA tiles, WMW x WNW warps per CTA):
+//   wide  <8,4,2,2>: CTA 128 x 64, 4 warps of 64 x 32, 2 CTAs/SM -- throughput configuration (default)
+//   8warp <4,4,4,2>: CTA 128 x 64, 8 warps of 32 x 32, 2 CTAs/SM = 4 warps per scheduler (1 TF/s slower: more
+//                    shared-memory fragment reads per flop; kept for experiments, GPB200_GEMM_TILE=1)
+//   small <4,2,2,2>: CTA  64 x 32, 4 warps, 4+ CTAs/SM -- latency configuration for launches that cannot fill the
+//                    machine with big tiles (the leaves and low levels of the recursive drivers)
+template <int WMT, int WNT, int WMW, int WNW>  // DMMA tiles per warp (M, N), warps per CTA (M, N)
 struct Cfg {
-    static constexpr int BM = 16 * WMT, BN = 16 * WNT;
+    static constexpr int THREADS = 32 * WMW * WNW;
+    static constexpr int BM = 8 * WMT * WMW, BN = 8 * WNT * WNW;
     static constexpr int LDSM_A = BM + 4;  // m-major A tile rows: (BM + 4) mod 16 == 4 -> conflict free
     static constexpr int LDSM_B = BN + 4;
     static constexpr int A_STAGE = BM * LDSK;  // >= BK * LDSM_A
     static constexpr int B_STAGE = BN * LDSK;  // >= BK * LDSM_B
     static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);  // 92160 / 46080
-    static constexpr int MIN_CTAS = WMT == 8 ? 2 : 4;
+    static constexpr int MIN_CTAS = BM == 128 ? 2 : 4;
 };
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
@@ -55,11 +57,13 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-template <bool AKM, bool BKM, int WMT, int WNT>  // operand stored k-major (k contiguous) or not; warp tile
-__global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel(const GemmArgs p, const int tiles_n) {
-    using C = Cfg<WMT, WNT>;
+template <bool AKM, bool BKM, int WMT, int WNT, int WMW, int WNW>  // operand k-major or not; tile configuration
+__global__ void __launch_bounds__(Cfg<WMT, WNT, WMW, WNW>::THREADS, Cfg<WMT, WNT, WMW, WNW>::MIN_CTAS)
+    dgemm_kernel(const GemmArgs p, const int tiles_n) {
+    using C = Cfg<WMT, WNT, WMW, WNW>;
     constexpr int BM = C::BM, BN = C::BN, LDSM_A = C::LDSM_A, LDSM_B = C::LDSM_B, A_STAGE = C::A_STAGE,
-                  B_STAGE = C::B_STAGE;
+                  B_STAGE = C::B_STAGE, THREADS = C::THREADS;
+    constexpr int RPK = THREADS / 8;  // rows per pass of the k-major loaders (8 16-byte chunks per 16-double row)
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
@@ -75,8 +79,15 @@ __global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel
         bi = r;
         bj = t - r * (r + 1);
     } else {
-        bi = blockIdx.x / tiles_n;
-        bj = blockIdx.x - bi * tiles_n;
+        // supertile rasterisation: bands of RASTER_H tile rows, column-major inside a band, so the ~300 CTAs
+        // resident at any time cover a near-square patch (16 x ~18 tiles) and share both operands through L2
+        constexpr int RASTER_H = 16;
+        const int tiles_m = gridDim.x / tiles_n;
+        const int band = blockIdx.x / (RASTER_H * tiles_n);
+        const int band_rows = min(RASTER_H, tiles_m - band * RASTER_H);
+        const int in_band = blockIdx.x - band * RASTER_H * tiles_n;
+        bj = in_band / band_rows;
+        bi = band * RASTER_H + (in_band - bj * band_rows);
     }
     const int row0 = bi * BM, col0 = bj * BN;
 
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel
     const double* Ag;
     const double* Bg;
     double *as_w, *bs_w;
-    if (AKM) {  // 128 rows x 8 chunks: thread owns chunk (tid & 7) of rows (tid >> 3) + 16 i
+    if (AKM) {  // BM rows x 8 chunks: thread owns chunk (tid & 7) of rows (tid >> 3) + RPK i
         Ag = p.A + (int64_t)(row0 + (tid >> 3)) * p.lda + k_begin + (tid & 7) * 2;
         as_w = As + (tid >> 3) * LDSK + (tid & 7) * 2;
     } else {    // 16 k-rows x BM/2 chunks: thread owns chunk (tid % CPR) of k-rows tid / CPR + (128 / CPR) i
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel
         if (AKM) {
             const double* a = Ag + kt * BK;
 #pragma unroll
-            for (int i = 0; i < BM / 16; ++i) cp_async16(as + i * 16 * LDSK, a + (int64_t)i * 16 * p.lda);
+            for (int i = 0; i < BM / RPK; ++i) cp_async16(as + i * RPK * LDSK, a + (int64_t)i * RPK * p.lda);
         } else {
             constexpr int RPP = THREADS / (BM / 2);  // k-rows per pass
             const double* a = Ag + (int64_t)kt * BK * p.lda;
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel
         if (BKM) {
             const double* b = Bg + kt * BK;
 #pragma unroll
-            for (int i = 0; i < BN / 16; ++i) cp_async16(bs + i * 16 * LDSK, b + (int64_t)i * 16 * p.ldb);
+            for (int i = 0; i < BN / RPK; ++i) cp_async16(bs + i * RPK * LDSK, b + (int64_t)i * RPK * p.ldb);
         } else {
             constexpr int RPP = THREADS / (BN / 2);
             const double* b = Bg + (int64_t)kt * BK * p.ldb;
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel
     }
 
     const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp / WNW, wn = warp % WNW;
     const int g = lane >> 2, t = lane & 3;
     // fragment read origins: A(row g, k t) / B(col g, k t) of the warp tile
     const double* as_r = AKM ? As + (wm * 8 * WMT + g) * LDSK + t : As + t * LDSM_A + wm * 8 * WMT + g;
@@ -218,14 +229,15 @@ __global__ void __launch_bounds__(THREADS, Cfg<WMT, WNT>::MIN_CTAS) dgemm_kernel
 static int64_t g_gemm_launches = 0;
 static double g_gemm_flops = 0.0;
 
-template <int WMT, int WNT>
+template <int WMT, int WNT, int WMW, int WNW>
 int launch_cfg(const GemmArgs& a, cudaStream_t s) {
-    using C = Cfg<WMT, WNT>;
+    using C = Cfg<WMT, WNT, WMW, WNW>;
+    constexpr int THREADS = C::THREADS;
     constexpr int BM = C::BM, BN = C::BN;
     using kern_t = void (*)(const GemmArgs, const int);
     const bool akm = !(a.flags & GEMM_A_MMAJOR), bkm = !(a.flags & GEMM_B_NMAJOR);
-    kern_t kern = akm ? (bkm ? dgemm_kernel<true, true, WMT, WNT> : dgemm_kernel<true, false, WMT, WNT>)
-                      : (bkm ? dgemm_kernel<false, true, WMT, WNT> : dgemm_kernel<false, false, WMT, WNT>);
+    kern_t kern = akm ? (bkm ? dgemm_kernel<true, true, WMT, WNT, WMW, WNW> : dgemm_kernel<true, false, WMT, WNT, WMW, WNW>)
+                      : (bkm ? dgemm_kernel<false, true, WMT, WNT, WMW, WNW> : dgemm_kernel<false, false, WMT, WNT, WMW, WNW>);
     static bool configured_dev[64][4] = {};
     int dev = 0;
     GPB_CUDA(cudaGetDevice(&dev));
@@ -277,9 +289,12 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     // big tiles unless they cannot fill one wave of 2 CTAs per SM (148 SMs)
     const int64_t tm = a.M / 128, tn = a.N / 64;
     const int64_t big_tiles = (a.flags & GEMM_LOWER) ? tm * (tm + 1) : tm * tn;
-    static const int force = getenv("GPB200_GEMM_TILE") ? atoi(getenv("GPB200_GEMM_TILE")) : 0;  // 1 = big, 2 = small
-    const bool small = force ? force == 2 : big_tiles < 296;
-    return small ? launch_cfg<4, 2>(a, s) : launch_cfg<8, 4>(a, s);
+    // measured on B200 at 8192^3: <8,4,2,2> 34.7 TF/s, <4,4,4,2> (8 warps of 32 x 32) 33.7 TF/s -> the 4-warp tile wins
+    static const int force = getenv("GPB200_GEMM_TILE") ? atoi(getenv("GPB200_GEMM_TILE")) : 0;  // 1 = 8-warp, 2 small, 3 wide
+    const int pick = force ? force : (big_tiles < 296 ? 2 : 3);
+    if (pick == 2) return launch_cfg<4, 2, 2, 2>(a, s);
+    if (pick == 1) return launch_cfg<4, 4, 4, 2>(a, s);
+    return launch_cfg<8, 4, 2, 2>(a, s);
 }
 
 int64_t gemm_launch_count() { return g_gemm_launches; }
