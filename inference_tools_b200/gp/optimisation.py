@@ -66,14 +66,10 @@ class GpOptimiser:
         self.convergence_metric_history = []
         self.iteration_history = []
 
-    def _fresh(self, obj):
-        # kernel / mean may be given as classes (instantiated per fit) or instances (re-used, as the reference does)
-        return obj
-
     def _build_gp(self, hyperpars=None):
         return GpRegressor(
-            x=self.x, y=self.y, y_err=self.y_err, hyperpars=hyperpars, kernel=self._fresh(self.kernel),
-            mean=self._fresh(self.mean), cross_val=self.cross_val, optimizer=self._fit_optimizer,
+            x=self.x, y=self.y, y_err=self.y_err, hyperpars=hyperpars, kernel=self.kernel,
+            mean=self.mean, cross_val=self.cross_val, optimizer=self._fit_optimizer,
             n_processes=self.n_processes, device=self.device,
         )
 

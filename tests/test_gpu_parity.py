@@ -251,7 +251,6 @@ def test_reference_finite_difference_checks():
 
 @pytest.mark.parametrize("name", ["fit_se_d1_n60", "fit_rqwhite_d2_n80"])
 def test_multistart_fit_reaches_the_reference_optimum(name):
-    g = np.load(f"tests/golden/{name}.npz") if False else None
     import os
     from conftest import GOLDEN_DIR
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))

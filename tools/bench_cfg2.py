@@ -40,10 +40,11 @@ out = {"config": f"cfg2: SE {a.dim}D N={a.size} multistart LML-gradient fit", "f
 if a.cpu:
     from oracle import gp_oracle as orc
     t0 = time.perf_counter()
-    lml_o, g_o = orc.marginal_likelihood_gradient(x, y, ("SE",), "const", th, e**2)
+    th_p = th + 0.3            # parity away from the optimum (the gradient vanishes at th)
+    lml_o, g_o = orc.marginal_likelihood_gradient(x, y, ("SE",), "const", th_p, e**2)
     out["cpu_seconds_per_evaluation"] = time.perf_counter() - t0
     out["cpu_cores"] = os.cpu_count()
-    lml, g = m.marginal_likelihood_gradient(th)
+    lml, g = m.marginal_likelihood_gradient(th_p)
     out["parity_lml_rel"] = abs(lml - lml_o) / abs(lml_o)
     out["parity_grad_normrel"] = float(np.abs(g - g_o).max() / np.abs(g_o).max())
     out["cpu_fit_s_extrapolated"] = out["cpu_seconds_per_evaluation"] * calls["n"]
