@@ -408,3 +408,89 @@ def test_gp_optimiser_loop(acq):
     assert val <= ref_val + 1e-6 * abs(ref_val) + 1e-9
     with pytest.raises(ValueError):
         opt.add_evaluation(0.0, 0.0)
+
+
+def test_query_chunking_is_invisible():
+    """More query rows than one pass of the stacked solve holds (api.cu chunk_rows): results must not depend on how
+    the queries are split, for predict and for the (d+1)-row stacked gradient path."""
+    x, y, e = synth(31, 300, 3)
+    theta = np.array([0.2, 0.1, -1.0, -1.1, -0.9])
+    m = gp.GpRegressor(x, y, y_err=e, hyperpars=theta)
+    rng = np.random.default_rng(31)
+    q = rng.uniform(0, 1, (100_003, 3))
+    mu, sig = m(q)
+    mu_a, sig_a = m(q[:40_000])
+    mu_b, sig_b = m(q[40_000:])
+    assert np.array_equal(mu, np.concatenate([mu_a, mu_b])) and np.array_equal(sig, np.concatenate([sig_a, sig_b]))
+    ref = orc.Fit(x, y, ("SE",), "const", theta, e**2)
+    idx = rng.choice(q.shape[0], 200, replace=False)
+    mu_o, sig_o = ref.predict(q[idx])
+    assert rel_err(mu[idx], mu_o) < TOL and np.abs(sig[idx] / sig_o - 1).max() < TOL
+    qs = q[:30_011]
+    dm, dv = m.spatial_derivatives(qs)
+    dm2, dv2 = m.spatial_derivatives(qs[29_000:])
+    assert np.array_equal(dm[29_000:], dm2) and np.array_equal(dv[29_000:], dv2)
+    dm_o, dv_o = ref.spatial_derivatives(qs[:50])
+    assert rel_err(dm[:50], dm_o) < TOL and rel_err(dv[:50], dv_o) < TOL
+
+
+def test_tiny_and_limit_shapes():
+    # N = 2 and N = 3 (almost everything is padding), M = 1; N = 1 is rejected like the reference does (y.squeeze())
+    with pytest.raises(ValueError):
+        gp.GpRegressor(np.array([0.5]), np.array([1.0]), hyperpars=[0.0, 0.0, 0.0])
+    for n in (2, 3):
+        x = np.linspace(0.2, 0.8, n)
+        y = np.sin(3 * x)
+        theta = np.array([0.1, 0.0, -1.0])
+        m = gp.GpRegressor(x, y, y_err=np.full(n, 0.1), hyperpars=theta)
+        ref = orc.Fit(x, y, ("SE",), "const", theta, np.full(n, 0.01))
+        mu, sig = m(np.array([0.5]))
+        mu_o, sig_o = ref.predict(np.array([0.5]))
+        assert rel_err(mu, mu_o) < TOL and rel_err(sig, sig_o) < TOL
+        lml, grad = m.marginal_likelihood_gradient(theta)
+        lml_o, grad_o = orc.marginal_likelihood_gradient(x, y, ("SE",), "const", theta, np.full(n, 0.01))
+        assert abs(lml - lml_o) <= TOL * abs(lml_o) and np.abs(grad - grad_o).max() <= TOL * np.abs(grad_o).max()
+    # d = MAX_DIM works, d = MAX_DIM + 1 is refused before anything runs
+    x8, y8, e8 = synth(8, 200, 8)
+    th8 = np.array([0.2, 0.3] + [0.2] * 8)
+    m8 = gp.GpRegressor(x8, y8, y_err=e8, hyperpars=th8)
+    ref8 = orc.Fit(x8, y8, ("SE",), "const", th8, e8**2)
+    assert rel_err(m8(x8[:20] + 0.01)[0], ref8.predict(x8[:20] + 0.01)[0]) < TOL
+    with pytest.raises(ValueError):
+        gp.GpRegressor(np.zeros((5, 9)), np.zeros(5))
+
+
+def test_no_error_data_and_refit_with_new_hyperparameters():
+    """y_err=None: only the a^2 1e-12 jitter on the diagonal (regression.py:322, covariance.py:254-255)."""
+    rng = np.random.default_rng(9)
+    x = np.sort(rng.uniform(0, 1, 25))
+    y = np.sin(6 * x)
+    th1, th2 = np.array([0.0, 0.3, np.log(0.03)]), np.array([0.1, -0.2, np.log(0.02)])
+    m = gp.GpRegressor(x, y, hyperpars=th1)
+    q = np.linspace(0.05, 0.95, 40)
+    for th in (th1, th2, th1):
+        m.set_hyperparameters(th)
+        ref = orc.Fit(x, y, ("SE",), "const", th, None)
+        mu, sig = m(q)
+        mu_o, sig_o = ref.predict(q)
+        assert rel_err(m.alpha, ref.alpha) < 1e-7           # cond(K) ~ 1e9 here: alpha itself is ill-conditioned
+        assert rel_err(mu, mu_o) < 1e-8 and np.abs(sig - sig_o).max() < 1e-8
+    assert np.array_equal(m.sig, np.zeros((25, 25)))
+
+
+def test_heteroscedastic_noise_in_more_than_one_dimension():
+    """The reference's HeteroscedasticNoise.__call__ uses u.size (covariance.py:672) and cannot predict for d > 1;
+    the engine treats the component as what it is (zero cross-covariance): check against the oracle."""
+    x, y, e = synth(41, 60, 2)
+    rng = np.random.default_rng(41)
+    theta = np.array([0.2, 0.1, -1.0, -1.2] + list(np.log(0.05) + 0.2 * rng.standard_normal(60)))
+    m = gp.GpRegressor(x, y, y_err=e, kernel=gp.SquaredExponential() + gp.HeteroscedasticNoise(), hyperpars=theta)
+    ref = orc.Fit(x, y, ("SE", "HETERO"), "const", theta, e**2)
+    q = rng.uniform(0, 1, (30, 2))
+    mu, sig = m(q)
+    mu_o, sig_o = ref.predict(q)
+    assert rel_err(mu, mu_o) < TOL and np.abs(sig / sig_o - 1).max() < TOL
+    lml, grad = m.marginal_likelihood_gradient(theta)
+    lml_o, grad_o = orc.marginal_likelihood_gradient(x, y, ("SE", "HETERO"), "const", theta, e**2)
+    assert abs(lml - lml_o) <= TOL * abs(lml_o) and np.abs(grad - grad_o).max() <= TOL * np.abs(grad_o).max()
+    assert len(m.hyperpar_labels) == 64 and m.hyperpar_labels[4] == "K2: log_sigma_1"
