@@ -21,17 +21,16 @@
 namespace gpb {
 namespace {
 
-constexpr int BK = 16;
-constexpr int LDSK = 20;  // padded smem row length (doubles)
-constexpr int STAGES = 3;
+constexpr int KALIGN = 16;  // K and every k-range boundary are multiples of this
 // Tile configurations (warp tile = 8*WMT x 8*WNT DMMA tiles, WMW x WNW warps per CTA):
 //   wide  <8,4,2,2>: CTA 128 x 64, 4 warps of 64 x 32, 2 CTAs/SM -- throughput configuration (default)
-//   8warp <4,4,4,2>: CTA 128 x 64, 8 warps of 32 x 32, 2 CTAs/SM = 4 warps per scheduler (1 TF/s slower: more
-//                    shared-memory fragment reads per flop; kept for experiments, GPB200_GEMM_TILE=1)
 //   small <4,2,2,2>: CTA  64 x 32, 4 warps, 4+ CTAs/SM -- latency configuration for launches that cannot fill the
 //                    machine with big tiles (the leaves and low levels of the recursive drivers)
-template <int WMT, int WNT, int WMW, int WNW>  // DMMA tiles per warp (M, N), warps per CTA (M, N)
+template <int WMT, int WNT, int WMW, int WNW, int BK_ = 16, int STAGES_ = 3>  // DMMA tiles per warp, warps per CTA, k-tile, stages
 struct Cfg {
+    static constexpr int BK = BK_, STAGES = STAGES_;
+    static constexpr int LDSK = BK + 4;  // padded k-major smem row (20 or 36 doubles: mod 16 == 4 -> conflict free)
+    static constexpr int WMT_ = WMT, WNT_ = WNT, WNW_ = WNW;
     static constexpr int THREADS = 32 * WMW * WNW;
     static constexpr int BM = 8 * WMT * WMW, BN = 8 * WNT * WNW;
     static constexpr int LDSM_A = BM + 4;  // m-major A tile rows: (BM + 4) mod 16 == 4 -> conflict free
@@ -57,13 +56,13 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-template <bool AKM, bool BKM, int WMT, int WNT, int WMW, int WNW>  // operand k-major or not; tile configuration
-__global__ void __launch_bounds__(Cfg<WMT, WNT, WMW, WNW>::THREADS, Cfg<WMT, WNT, WMW, WNW>::MIN_CTAS)
-    dgemm_kernel(const GemmArgs p, const int tiles_n) {
-    using C = Cfg<WMT, WNT, WMW, WNW>;
+template <bool AKM, bool BKM, class C>  // operand k-major or not; tile configuration
+__global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) dgemm_kernel(const GemmArgs p, const int tiles_n) {
     constexpr int BM = C::BM, BN = C::BN, LDSM_A = C::LDSM_A, LDSM_B = C::LDSM_B, A_STAGE = C::A_STAGE,
-                  B_STAGE = C::B_STAGE, THREADS = C::THREADS;
-    constexpr int RPK = THREADS / 8;  // rows per pass of the k-major loaders (8 16-byte chunks per 16-double row)
+                  B_STAGE = C::B_STAGE, THREADS = C::THREADS, BK = C::BK, LDSK = C::LDSK, STAGES = C::STAGES,
+                  WMT = C::WMT_, WNT = C::WNT_, WNW = C::WNW_;
+    constexpr int CH = BK / 2;         // 16-byte chunks per k-major row
+    constexpr int RPK = THREADS / CH;  // rows per pass of the k-major loaders
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
@@ -102,17 +101,17 @@ __global__ void __launch_bounds__(Cfg<WMT, WNT, WMW, WNW>::THREADS, Cfg<WMT, WNT
     const double* Ag;
     const double* Bg;
     double *as_w, *bs_w;
-    if (AKM) {  // BM rows x 8 chunks: thread owns chunk (tid & 7) of rows (tid >> 3) + RPK i
-        Ag = p.A + (int64_t)(row0 + (tid >> 3)) * p.lda + k_begin + (tid & 7) * 2;
-        as_w = As + (tid >> 3) * LDSK + (tid & 7) * 2;
+    if (AKM) {  // BM rows x CH chunks: thread owns chunk (tid % CH) of rows tid / CH + RPK i
+        Ag = p.A + (int64_t)(row0 + tid / CH) * p.lda + k_begin + (tid % CH) * 2;
+        as_w = As + (tid / CH) * LDSK + (tid % CH) * 2;
     } else {    // 16 k-rows x BM/2 chunks: thread owns chunk (tid % CPR) of k-rows tid / CPR + (128 / CPR) i
         constexpr int CPR = BM / 2;
         Ag = p.A + (int64_t)(k_begin + tid / CPR) * p.lda + row0 + (tid % CPR) * 2;
         as_w = As + (tid / CPR) * LDSM_A + (tid % CPR) * 2;
     }
     if (BKM) {
-        Bg = p.B + (int64_t)(col0 + (tid >> 3)) * p.ldb + k_begin + (tid & 7) * 2;
-        bs_w = Bs + (tid >> 3) * LDSK + (tid & 7) * 2;
+        Bg = p.B + (int64_t)(col0 + tid / CH) * p.ldb + k_begin + (tid % CH) * 2;
+        bs_w = Bs + (tid / CH) * LDSK + (tid % CH) * 2;
     } else {    // 16 k-rows x BN/2 chunks
         constexpr int CPR = BN / 2;
         Bg = p.B + (int64_t)(k_begin + tid / CPR) * p.ldb + col0 + (tid % CPR) * 2;
@@ -229,15 +228,14 @@ __global__ void __launch_bounds__(Cfg<WMT, WNT, WMW, WNW>::THREADS, Cfg<WMT, WNT
 static int64_t g_gemm_launches = 0;
 static double g_gemm_flops = 0.0;
 
-template <int WMT, int WNT, int WMW, int WNW>
+template <class C>
 int launch_cfg(const GemmArgs& a, cudaStream_t s) {
-    using C = Cfg<WMT, WNT, WMW, WNW>;
     constexpr int THREADS = C::THREADS;
     constexpr int BM = C::BM, BN = C::BN;
     using kern_t = void (*)(const GemmArgs, const int);
     const bool akm = !(a.flags & GEMM_A_MMAJOR), bkm = !(a.flags & GEMM_B_NMAJOR);
-    kern_t kern = akm ? (bkm ? dgemm_kernel<true, true, WMT, WNT, WMW, WNW> : dgemm_kernel<true, false, WMT, WNT, WMW, WNW>)
-                      : (bkm ? dgemm_kernel<false, true, WMT, WNT, WMW, WNW> : dgemm_kernel<false, false, WMT, WNT, WMW, WNW>);
+    kern_t kern = akm ? (bkm ? dgemm_kernel<true, true, C> : dgemm_kernel<true, false, C>)
+                      : (bkm ? dgemm_kernel<false, true, C> : dgemm_kernel<false, false, C>);
     static bool configured_dev[64][4] = {};
     int dev = 0;
     GPB_CUDA(cudaGetDevice(&dev));
@@ -277,7 +275,7 @@ int launch_cfg(const GemmArgs& a, cudaStream_t s) {
 
 int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     if (a.M <= 0 || a.N <= 0) return 0;
-    if (a.M % 128 || a.N % 64 || a.K % BK || a.K < 0) {
+    if (a.M % 128 || a.N % 64 || a.K % KALIGN || a.K < 0) {
         set_error("gemm_nt: M % 128, N % 64, K % 16 must be 0 (got " + std::to_string(a.M) + "," +
                   std::to_string(a.N) + "," + std::to_string(a.K) + ")");
         return -2;
@@ -289,12 +287,12 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     // big tiles unless they cannot fill one wave of 2 CTAs per SM (148 SMs)
     const int64_t tm = a.M / 128, tn = a.N / 64;
     const int64_t big_tiles = (a.flags & GEMM_LOWER) ? tm * (tm + 1) : tm * tn;
-    // measured on B200 at 8192^3: <8,4,2,2> 34.7 TF/s, <4,4,4,2> (8 warps of 32 x 32) 33.7 TF/s -> the 4-warp tile wins
-    static const int force = getenv("GPB200_GEMM_TILE") ? atoi(getenv("GPB200_GEMM_TILE")) : 0;  // 1 = 8-warp, 2 small, 3 wide
+    // Configurations tried on B200 at 8192^3 (profiles/gemm_ncu_full_r1.md): <8,4,2,2> BK=16 x 3 stages 34.7 TF/s (kept);
+    // 8 warps of 32 x 32 <4,4,4,2> 33.7; BK=32 x 2 stages <8,4,2,2,32,2> 34.1; supertile rasterisation: no change.
+    static const int force = getenv("GPB200_GEMM_TILE") ? atoi(getenv("GPB200_GEMM_TILE")) : 0;  // 2 = small, 3 = wide
     const int pick = force ? force : (big_tiles < 296 ? 2 : 3);
-    if (pick == 2) return launch_cfg<4, 2, 2, 2>(a, s);
-    if (pick == 1) return launch_cfg<4, 4, 4, 2>(a, s);
-    return launch_cfg<8, 4, 2, 2>(a, s);
+    if (pick == 2) return launch_cfg<Cfg<4, 2, 2, 2>>(a, s);
+    return launch_cfg<Cfg<8, 4, 2, 2>>(a, s);
 }
 
 int64_t gemm_launch_count() { return g_gemm_launches; }
