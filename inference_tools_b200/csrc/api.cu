@@ -178,8 +178,10 @@ void clear_graphs(gpb_ctx* c) {
 
 // assemble K(theta)+sig into `K` (lower tiles), factor in place, solve for alpha.
 //   resid_out: y - mu (optional copy), v_out: L^-1 r left in c->vec[npad..) when !want_alpha
+enum SolveMode { SOLVE_NONE = 0, SOLVE_FWD = 1, SOLVE_BOTH = 2 };
 int assemble_and_factor(gpb_ctx* c, const CovParams& cp, const MeanParams& mp, double* K, double* dinv, double* mu_out,
-                        bool want_alpha, double* alpha_out, int* info_host) {
+                        int solve, double* alpha_out, int* info_host) {
+    const bool want_alpha = solve == SOLVE_BOTH;
     const int npad = (int)c->npad, n = (int)c->n;
     c->timer.mark("assemble");
     GPB_TRY(launch_assemble_train(cp, c->x, n, npad, c->has_noise ? c->noise : nullptr,
@@ -189,6 +191,11 @@ int assemble_and_factor(gpb_ctx* c, const CovParams& cp, const MeanParams& mp, d
                         [&]() { return potrf_lower(K, npad, npad, ws_of(c, dinv), c->s); }));
     c->timer.mark("solve");
     GPB_TRY(launch_residual(mp, c->x, c->y, n, npad, c->vec, mu_out, c->s));
+    if (solve == SOLVE_NONE) {  // the caller solves through the explicit inverse (marginal_likelihood_gradient path)
+        GPB_CUDA(cudaMemcpyAsync(c->resid, c->vec, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+        GPB_CUDA(cudaMemcpyAsync(info_host, c->info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s));
+        return 0;
+    }
     GPB_TRY(run_graphed(c, pkey("solve", {K, dinv, c->vec, c->resid, alpha_out}, {npad, want_alpha}), [&]() -> int {
         GPB_CUDA(cudaMemcpyAsync(c->resid, c->vec, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
         GPB_TRY(trsv_lower_fwd(K, npad, npad, dinv, c->vec, c->s));
@@ -426,7 +433,7 @@ int gpb_factor(gpb_ctx* c, const double* theta, int* info) {
     GPB_TRY(make_cov_params(c, theta + c->n_mean, c->cp_fit));
     make_mean_params(c, theta, c->mp_fit);
     int info_h = 0;
-    GPB_TRY(assemble_and_factor(c, c->cp_fit, c->mp_fit, c->Lfit, c->dinv_fit, c->mu, true, c->alpha, &info_h));
+    GPB_TRY(assemble_and_factor(c, c->cp_fit, c->mp_fit, c->Lfit, c->dinv_fit, c->mu, SOLVE_BOTH, c->alpha, &info_h));
     c->timer.mark("end");
     GPB_CUDA(cudaStreamSynchronize(c->s));
     *info = info_h;
@@ -476,7 +483,7 @@ int gpb_lml(gpb_ctx* c, const double* theta, double* lml, int* info) {
     GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
     make_mean_params(c, theta, mp);
     int info_h = 0;
-    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, false, nullptr, &info_h));
+    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_FWD, nullptr, &info_h));
     // -0.5 v.v - sum log L_ii   (regression.py:538-539)
     GPB_TRY(launch_logdet_dot(c->Kwork, c->npad, c->vec + c->npad, c->vec + c->npad, (int)c->n, c->scal, c->s));
     double sc[2];
@@ -498,21 +505,26 @@ int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int
     GPB_TRY(ensure(c->Kwork, c->Kwork_cap, sizeof(double) * np * np));
     GPB_TRY(ensure(c->W, c->W_cap, sizeof(double) * np * np));
     GPB_TRY(ensure(c->Kinv, c->Kinv_cap, sizeof(double) * np * np));
-    GPB_TRY(ensure(c->partials, c->partials_cap, trace_partials_size(npad)));
+    GPB_TRY(ensure(c->partials, c->partials_cap, std::max(trace_partials_size(npad), col_dot_ws_bytes(npad, npad))));
     GPB_TRY(ensure(c->grad_dev, c->grad_cap, sizeof(double) * (nt + 2)));
     CovParams cp;
     MeanParams mp;
     GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
     make_mean_params(c, theta, mp);
     int info_h = 0;
-    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, true, c->alpha_work, &info_h));
-    // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
-    GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
+    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_NONE, nullptr, &info_h));
     c->timer.mark("trtri");
     GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
         GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
         return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
     }));
+    // alpha = K^-1 r through the explicit inverse, as the reference does here (regression.py:556-559):
+    // v = W r, alpha = W^T v -- two fully parallel matrix-vector passes instead of 2 N/128 dependent block steps
+    c->timer.mark("alpha");
+    GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->resid, c->vec, c->s));
+    GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->partials, c->s));
+    // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
+    GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
     c->timer.mark("lauum");
     GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
     c->timer.mark("trace");
@@ -546,7 +558,7 @@ int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* inf
     GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
     make_mean_params(c, theta, mp);
     int info_h = 0;
-    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, true, c->alpha_work, &info_h));
+    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_BOTH, c->alpha_work, &info_h));
     c->timer.mark("trtri");
     GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
         GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));

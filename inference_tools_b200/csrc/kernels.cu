@@ -27,7 +27,9 @@ __device__ __forceinline__ double cov_from_d2(const CovParams& cp, const double 
             kv += cp.amp2[c] * exp(-z);
         } else {
             const double q = cp.rq_alpha[c];
-            kv += cp.amp2[c] * pow(1.0 + z / q, -q);   // covariance.py:341, 348
+            // (1 + Z/q)^-q evaluated as exp(-q ln F), the form the reference itself uses at covariance.py:356-358;
+            // a few ulp from the ** of :341/:348 and less than half the cost of a double-precision pow()
+            kv += cp.amp2[c] * exp(-q * log(1.0 + z / q));
         }
     }
     return kv;
@@ -243,6 +245,35 @@ __global__ void __launch_bounds__(256) row_dot_kernel(const double* __restrict__
     if (lane == 0) out[r] = a;
 }
 
+// out[c] = sum_r S[r][c] * vec[r]: stage 1, CTA (bx, by) reduces rows [1024 by, 1024 by + 1024) for columns 128 bx ..
+// into part[by][c]; stage 2 adds the row chunks in order (fixed summation order, no atomics)
+__global__ void __launch_bounds__(256) col_dot_partial_kernel(const double* __restrict__ S, int64_t ld, int nrows,
+                                                              const double* __restrict__ vec, double* __restrict__ part,
+                                                              int ncols) {
+    __shared__ double sm[2][TILE];
+    const int col = blockIdx.x * TILE + (threadIdx.x & (TILE - 1)), half = threadIdx.x >> 7;
+    const int r0 = blockIdx.y * 1024 + half * 512;
+    const int r1 = min(nrows, r0 + 512);
+    double a0 = 0.0, a1 = 0.0;
+    const double* p = S + (int64_t)r0 * ld + col;
+    int r = r0;
+    for (; r + 1 < r1; r += 2, p += 2 * ld) {
+        a0 = fma(p[0], vec[r], a0);
+        a1 = fma(p[ld], vec[r + 1], a1);
+    }
+    if (r < r1) a0 = fma(p[0], vec[r], a0);
+    sm[half][threadIdx.x & (TILE - 1)] = a0 + a1;
+    __syncthreads();
+    if (half == 0) part[(int64_t)blockIdx.y * ncols + col] = sm[0][threadIdx.x] + sm[1][threadIdx.x];
+}
+__global__ void col_dot_final_kernel(const double* __restrict__ part, int nchunks, int ncols, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double a = 0.0;
+    for (int k = 0; k < nchunks; ++k) a += part[(int64_t)k * ncols + c];
+    out[c] = a;
+}
+
 // one warp per query: Gram matrix of its nstack solved rows
 template <int NS>
 __global__ void __launch_bounds__(256) row_gram_kernel(const double* __restrict__ X, int64_t ld, int mq, int nstack,
@@ -440,6 +471,20 @@ int launch_cross_stack(const CovParams& cp, const double* q, int mq, int nstack,
 int launch_row_dot(const double* S, int64_t ld, int rows, int ncols, const double* vec, double* out, cudaStream_t s) {
     row_dot_kernel<<<(rows + 7) / 8, 256, 0, s>>>(S, ld, rows, ncols, vec, out);
     GPB_LAUNCH_CHECK();
+}
+
+size_t col_dot_ws_bytes(int nrows, int ncols) { return sizeof(double) * (size_t)((nrows + 1023) / 1024) * ncols; }
+
+int launch_col_dot(const double* S, int64_t ld, int nrows, int ncols, const double* vec, double* out, double* ws,
+                   cudaStream_t s) {
+    const int nchunks = (nrows + 1023) / 1024;
+    dim3 grid(ncols / TILE, nchunks);
+    col_dot_partial_kernel<<<grid, 256, 0, s>>>(S, ld, nrows, vec, ws, ncols);
+    GPB_CUDA(cudaGetLastError());
+    col_dot_final_kernel<<<(ncols + 255) / 256, 256, 0, s>>>(ws, nchunks, ncols, out);
+    GPB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return 0;
 }
 
 int launch_row_gram(const double* X, int64_t ld, int mq, int nstack, int ncols, double* G, cudaStream_t s) {

@@ -23,6 +23,10 @@ int launch_cross_stack(const CovParams& cp, const double* q, int mq, int nstack,
                        double* S, int64_t ld, cudaStream_t s);
 // out[r] = sum_j S[r][j] * vec[j]  (one warp per row, fixed-order reduction)
 int launch_row_dot(const double* S, int64_t ld, int rows, int ncols, const double* vec, double* out, cudaStream_t s);
+// out[c] = sum_r S[r][c] * vec[r]  (ncols % 128 == 0; ws holds col_dot_ws_bytes(nrows, ncols))
+size_t col_dot_ws_bytes(int nrows, int ncols);
+int launch_col_dot(const double* S, int64_t ld, int nrows, int ncols, const double* vec, double* out, double* ws,
+                   cudaStream_t s);
 // G[q][a][b] = sum_j X[q*ns+a][j] X[q*ns+b][j]
 int launch_row_gram(const double* X, int64_t ld, int mq, int nstack, int ncols, double* G, cudaStream_t s);
 // predictive mean/sigma (regression.py:212-216): mu = dot + mean(q); sig = sqrt|kqq - G|
