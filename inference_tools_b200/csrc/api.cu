@@ -613,9 +613,9 @@ enum PredMode { PM_PREDICT, PM_GRADIENT, PM_SPATIAL, PM_EI };
 bool is_pure_se(const gpb_ctx* c) { return c->ncomp == 1 && c->kinds[0] == COV_SE; }
 
 int64_t chunk_rows(const gpb_ctx* c) {
-    // rows of the stacked cross-covariance per pass: one full wave of 2 CTAs/SM on the 128-wide leaf
-    // solves (148 * 128) when N is large, more when the rows are short
-    const int64_t base = 148 * 128;
+    // rows of the stacked cross-covariance per pass: one full wave of 3 CTAs/SM on the 128-wide leaf
+    // solves (222 row tiles x 2 column tiles = 444 CTAs) when N is large, more when the rows are short
+    const int64_t base = 222 * 128;
     if (c->npad >= 8192) return base;
     if (c->npad >= 2048) return base * 2;
     return base * 4;

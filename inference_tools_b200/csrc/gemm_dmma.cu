@@ -6,9 +6,11 @@
 // shared-memory traffic per flop, which is what lets a tile kernel sit on the pipe limit.
 //
 // Tiling: CTA tile 128 x 64, 4 warps (2 x 2), warp tile 64 x 32 = 8 x 4 DMMA tiles (64 accumulator
-// doubles per thread), BK = 16, 3-stage cp.async pipeline, 2 CTAs resident per SM so one CTA's
-// epilogue (C read-modify-write) overlaps the other's main loop.  Shared-memory rows are padded to
-// 20 doubles: the fragment read (row g, column t) then hits bank pairs (4g + t) mod 16 -- conflict free.
+// doubles per thread), BK = 16, double-buffered cp.async pipeline, 3 CTAs resident per SM (166 registers,
+// 61 KB of shared memory each) so that every warp scheduler always has a warp with DMMAs ready while the
+// other two sit at a barrier, wait for fragments or run an epilogue (C read-modify-write).  Shared-memory
+// rows are padded to 20 doubles: the fragment read (row g, column t) then hits bank pairs (4g + t) mod 16
+// -- conflict free.
 //
 // Every blocked driver in this library (Cholesky trailing update, panel solve through the inverted
 // diagonal block, triangular inverse, K^-1 = Z Z^T, batched predict solve) is expressed in this one
@@ -23,10 +25,11 @@ namespace {
 
 constexpr int KALIGN = 16;  // K and every k-range boundary are multiples of this
 // Tile configurations (warp tile = 8*WMT x 8*WNT DMMA tiles, WMW x WNW warps per CTA):
-//   wide  <8,4,2,2>: CTA 128 x 64, 4 warps of 64 x 32, 2 CTAs/SM -- throughput configuration (default)
+//   wide  <8,4,2,2,16,2,3>: CTA 128 x 64, 4 warps of 64 x 32, BK = 16, 2-stage pipeline, 3 CTAs/SM -- throughput
+//                    configuration (default)
 //   small <4,2,2,2>: CTA  64 x 32, 4 warps, 4+ CTAs/SM -- latency configuration for launches that cannot fill the
 //                    machine with big tiles (the leaves and low levels of the recursive drivers)
-template <int WMT, int WNT, int WMW, int WNW, int BK_ = 16, int STAGES_ = 3>  // DMMA tiles per warp, warps per CTA, k-tile, stages
+template <int WMT, int WNT, int WMW, int WNW, int BK_ = 16, int STAGES_ = 3, int CTAS_ = 0>  // DMMA tiles per warp, warps per CTA, k-tile, stages, CTAs/SM
 struct Cfg {
     static constexpr int BK = BK_, STAGES = STAGES_;
     static constexpr int LDSK = BK + 4;  // padded k-major smem row (20 or 36 doubles: mod 16 == 4 -> conflict free)
@@ -38,7 +41,7 @@ struct Cfg {
     static constexpr int A_STAGE = BM * LDSK;  // >= BK * LDSM_A
     static constexpr int B_STAGE = BN * LDSK;  // >= BK * LDSM_B
     static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);  // 92160 / 46080
-    static constexpr int MIN_CTAS = BM == 128 ? 2 : 4;
+    static constexpr int MIN_CTAS = CTAS_ ? CTAS_ : (BM == 128 ? 2 : 4);
 };
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
@@ -287,12 +290,15 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     // big tiles unless they cannot fill one wave of 2 CTAs per SM (148 SMs)
     const int64_t tm = a.M / 128, tn = a.N / 64;
     const int64_t big_tiles = (a.flags & GEMM_LOWER) ? tm * (tm + 1) : tm * tn;
-    // Configurations tried on B200 at 8192^3 (profiles/gemm_ncu_full_r1.md): <8,4,2,2> BK=16 x 3 stages 34.7 TF/s (kept);
-    // 8 warps of 32 x 32 <4,4,4,2> 33.7; BK=32 x 2 stages <8,4,2,2,32,2> 34.1; supertile rasterisation: no change.
+    // Configurations measured on B200 at 8192^3: <8,4,2,2> BK=16, 2 stages, 3 CTAs/SM (166 registers, 61 KB) 35.8 TF/s
+    // (default: a third resident warp per scheduler covers the other two's barrier / fragment-load gaps); the same
+    // tile with 3 stages and 2 CTAs/SM 34.7; 8 warps of 32 x 32 <4,4,4,2> 33.7; BK=32 x 2 stages 34.1;
+    // supertile rasterisation: no change.
     static const int force = getenv("GPB200_GEMM_TILE") ? atoi(getenv("GPB200_GEMM_TILE")) : 0;  // 2 = small, 3 = wide
     const int pick = force ? force : (big_tiles < 296 ? 2 : 3);
     if (pick == 2) return launch_cfg<Cfg<4, 2, 2, 2>>(a, s);
-    return launch_cfg<Cfg<8, 4, 2, 2>>(a, s);
+    if (pick == 6) return launch_cfg<Cfg<8, 4, 2, 2>>(a, s);  // previous default: 3 stages, 2 CTAs/SM (34.7 TF/s)
+    return launch_cfg<Cfg<8, 4, 2, 2, 16, 2, 3>>(a, s);
 }
 
 int64_t gemm_launch_count() { return g_gemm_launches; }
