@@ -19,110 +19,210 @@ namespace {
 // Factor one 128x128 diagonal block in place (lower triangle) and write inv(L_block) (full block,
 // zero upper triangle) to dinv.  info: 1-based global index of the first non-positive pivot.
 //
-// Register-resident right-looking sweep: 256 threads as a 16 x 16 grid, thread (ty,tx) owns the 64
-// elements (ty + 16a, tx + 16b) of the block AND of the running inverse in registers.  Step j publishes
-// column j of the factor and row j of the partially solved identity through 2 KB of shared memory (one
-// __syncthreads per step, double buffered); every thread then applies the rank-1 update to its own
-// registers:  A[i][k] -= l_ij l_kj (potrf)  and  B[i][c] -= l_ij W[j][c] (forward substitution of L W = I).
-// The whole kernel needs 4 KB of shared memory, so it can be scheduled next to resident GEMM CTAs.
+// Blocked inside the CTA: the block is kept in shared memory as 36 lower 16 x 16 sub-blocks (row stride 20
+// doubles: conflict-free DMMA fragment reads), next to a running right-hand side B that starts as the identity and
+// ends as inv(L).  Per 16-column panel p:
+//   (a) warp 0 factors the 16 x 16 diagonal sub-block in registers, rows across lanes, pivots and columns
+//       exchanged with shuffles (no block barrier inside the 16-pivot chain);
+//   (b) one thread per row solves the sub-blocks below it against L_pp^T, and -- concurrently, one thread per
+//       column -- row block p of B is solved against L_pp (both are 16-step substitutions with broadcast reads);
+//   (c) the rank-16 trailing updates  A_IJ -= L_Ip L_Jp^T  and  B_IJ -= L_Ip W_pJ  run on the FP64 tensor pipe
+//       (mma.sync m8n8k4), one 16 x 16 sub-block per warp at a time; sub-block column p+1 is updated first so that
+//       warp 0 can already factor the next diagonal sub-block while warps 1..7 finish the rest.
+// This replaces 128 CTA-wide rank-1 steps (each broadcasting a column and a row through shared memory to all
+// threads) by 8 panels with three barriers each; the serial part is the 128-pivot chain inside (a).
+constexpr int SB = 16;                 // sub-block size
+constexpr int SLD = 20;                // sub-block row stride (doubles)
+constexpr int SBLK = SB * SLD;         // doubles per stored sub-block
+constexpr int NSB = NB / SB;           // 8 sub-blocks per dimension
+constexpr int DIAG_SMEM = (2 * (NSB * (NSB + 1) / 2) * SBLK + NB + 8) * (int)sizeof(double);
+
+__device__ __forceinline__ int sblk(int I, int J) { return (I * (I + 1) / 2 + J) * SBLK; }
+
+__device__ __forceinline__ void dmma_nn(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld,
                                                             double* __restrict__ dinv, int* __restrict__ info,
                                                             int row_offset) {
-    __shared__ double cbuf[2][NB];  // column j of A (unscaled)
-    __shared__ double rbuf[2][NB];  // row j of B (unscaled)
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    double r[8][8], w[8][8];
+    extern __shared__ __align__(16) double dsm[];
+    double* Lb = dsm;                                   // lower sub-blocks of A, then of L
+    double* Wb = dsm + (NSB * (NSB + 1) / 2) * SBLK;    // lower sub-blocks of the running inverse
+    double* rinv_s = Wb + (NSB * (NSB + 1) / 2) * SBLK; // 1 / L_jj
+    int* fail_s = reinterpret_cast<int*>(rinv_s + NB);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int er = tid >> 4, ec = tid & 15;             // element (row, col) of a sub-block owned in copy loops
+
+    if (tid == 0) *fail_s = 0;
+    {   // all 36 global loads of this thread are issued before the first shared-memory store (one latency, not 36)
+        double v[NSB * (NSB + 1) / 2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+        for (int I = 0; I < NSB; ++I)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            if (b <= a) {
-                r[a][b] = A[(int64_t)(ty + 16 * a) * ld + tx + 16 * b];
-                w[a][b] = (a == b && tx == ty) ? 1.0 : 0.0;
-            } else {
-                r[a][b] = 0.0;
-                w[a][b] = 0.0;
+            for (int J = 0; J <= I; ++J) v[I * (I + 1) / 2 + J] = A[(int64_t)(SB * I + er) * ld + SB * J + ec];
+#pragma unroll
+        for (int I = 0; I < NSB; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J) {
+                Lb[sblk(I, J) + er * SLD + ec] = v[I * (I + 1) / 2 + J];
+                Wb[sblk(I, J) + er * SLD + ec] = (I == J && er == ec) ? 1.0 : 0.0;
             }
-        }
-    bool failed = false;
+    }
+    __syncthreads();
+
+    // (a) 16 x 16 diagonal sub-block p: one warp, rows across lanes (lanes 16..31 mirror 0..15)
+    auto factor_sub = [&](int p) {
+        double* Lpp = Lb + sblk(p, p);
+        const int i = lane & 15;
+        double a[SB];
 #pragma unroll
-    for (int bj = 0; bj < 8; ++bj) {
-        for (int jj = 0; jj < 16; ++jj) {
-            const int j = 16 * bj + jj;
-            const int buf = jj & 1;
-            if (tx == jj) {
+        for (int k = 0; k < SB; ++k) a[k] = Lpp[i * SLD + k];
+        int bad = 0;
 #pragma unroll
-                for (int a = bj; a < 8; ++a) cbuf[buf][ty + 16 * a] = r[a][bj];
-            }
-            if (ty == jj) {
-#pragma unroll
-                for (int b = 0; b <= bj; ++b) rbuf[buf][tx + 16 * b] = w[bj][b];
-            }
-            __syncthreads();
-            const double ajj = cbuf[buf][j];
-            if (!(ajj > 0.0)) {  // also catches NaN; uniform across the CTA
-                failed = true;
-                if (tid == 0) atomicCAS(info, 0, row_offset + j + 1);
+        for (int j = 0; j < SB; ++j) {
+            const double pj = __shfl_sync(0xffffffffu, a[j], j);
+            if (!(pj > 0.0)) {  // also catches NaN; uniform across the warp
+                bad = j + 1;
                 break;
             }
-            const double dj = sqrt(ajj);
-            const double rinv = 1.0 / dj;
-            double ci[8], ck[8], wj[8];
+            const double rinv = rsqrt(pj);
+            const double lij = a[j] * rinv;  // L_ij for lanes i >= j (lane j: sqrt(pj))
+            a[j] = lij;
+            if (lane == j) rinv_s[SB * p + j] = rinv;
 #pragma unroll
-            for (int a = bj; a < 8; ++a) ci[a] = cbuf[buf][ty + 16 * a] * rinv;  // l_ij for my rows
-#pragma unroll
-            for (int b = bj; b < 8; ++b) ck[b] = cbuf[buf][tx + 16 * b] * rinv;  // l_kj for my columns
-#pragma unroll
-            for (int b = 0; b <= bj; ++b) wj[b] = rbuf[buf][tx + 16 * b] * rinv;  // W[j][c] for my columns
-#pragma unroll
-            for (int a = bj; a < 8; ++a) {
-                const bool row_below = (a > bj) || (ty > jj);  // i > j
-                if (row_below) {
-#pragma unroll
-                    for (int b = bj; b <= a; ++b) {
-                        const bool col_right = (b > bj) || (tx > jj);  // k > j
-                        const bool lower = (a > b) || (tx <= ty);      // k <= i
-                        if (col_right && lower) r[a][b] = fma(-ci[a], ck[b], r[a][b]);
-                    }
-#pragma unroll
-                    for (int b = 0; b <= bj; ++b) {
-                        const bool col_left = (b < bj) || (tx <= jj);  // c <= j
-                        if (col_left) w[a][b] = fma(-ci[a], wj[b], w[a][b]);
-                    }
-                }
-            }
-            // the owners keep the finished column j of L and row j of W
-            if (tx == jj) {
-#pragma unroll
-                for (int a = bj; a < 8; ++a) {
-                    if ((a > bj) || (ty > jj)) r[a][bj] = ci[a];
-                    else if (ty == jj) r[a][bj] = dj;
-                }
-            }
-            if (ty == jj) {
-#pragma unroll
-                for (int b = 0; b <= bj; ++b) w[bj][b] = wj[b];
+            for (int k = j + 1; k < SB; ++k) {
+                const double lkj = __shfl_sync(0xffffffffu, lij, k);
+                a[k] = fma(-lij, lkj, a[k]);  // meaningful for k <= i
             }
         }
-        if (failed) break;
+        if (bad) {
+            if (lane == 0) {
+                *fail_s = 1;
+                atomicCAS(info, 0, row_offset + SB * p + bad);
+            }
+        } else if (lane < SB) {
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                if (k <= i) Lpp[i * SLD + k] = a[k];
+        }
+    };
+    // (c) one rank-16 update of a 16 x 16 sub-block on the tensor pipe:
+    //     is_l: A_IJ -= L_Ip L_Jp^T      else: B_IJ -= L_Ip W_pJ
+    auto update_sub = [&](int p, int I, int J, bool is_l) {
+        const int g = lane >> 2, t = lane & 3;
+        const double* Ab = Lb + sblk(I, p);
+        double* Cb = (is_l ? Lb : Wb) + sblk(I, J);
+        double a[2][4], b[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) a[mt][ks] = -Ab[(8 * mt + g) * SLD + 4 * ks + t];
+        if (is_l) {  // B(n,k) = L_Jp[n][k]
+            const double* Bb = Lb + sblk(J, p);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) b[nt][ks] = Bb[(8 * nt + g) * SLD + 4 * ks + t];
+        } else {     // B(n,k) = W_pJ[k][n]
+            const double* Bb = Wb + sblk(p, J);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) b[nt][ks] = Bb[(4 * ks + t) * SLD + 8 * nt + g];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                double2* cp = reinterpret_cast<double2*>(Cb + (8 * mt + g) * SLD + 8 * nt + 2 * t);
+                double2 c = *cp;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) dmma_nn(c.x, c.y, a[mt][ks], b[nt][ks]);
+                *cp = c;
+            }
+    };
+
+    if (warp == 0) factor_sub(0);
+    __syncthreads();
+    for (int p = 0; p < NSB && !*fail_s; ++p) {
+        const double* Lpp = Lb + sblk(p, p);
+        // ---- (b) substitutions against L_pp: rows of the sub-blocks below (threads 0..127), columns of row block p
+        //          of the running inverse (threads 128..255)
+        {
+            const bool row_task = tid < 128;
+            const int t = row_task ? tid : tid - 128;
+            const int blk_i = t >> 4, e = t & 15;
+            const bool active = row_task ? (blk_i < NSB - 1 - p) : (blk_i <= p);
+            if (active) {
+                // row task: x = row e of L_(p+1+blk_i, p); column task: x = column e of W_(p, blk_i)
+                double* base = row_task ? Lb + sblk(p + 1 + blk_i, p) + e * SLD : Wb + sblk(p, blk_i) + e;
+                const int stride = row_task ? 1 : SLD;
+                double x[SB];
+#pragma unroll
+                for (int k = 0; k < SB; ++k) x[k] = base[k * stride];
+#pragma unroll
+                for (int j = 0; j < SB; ++j) {
+                    x[j] *= rinv_s[SB * p + j];
+#pragma unroll
+                    for (int k = j + 1; k < SB; ++k) x[k] = fma(-x[j], Lpp[k * SLD + j], x[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < SB; ++k) base[k * stride] = x[k];
+            }
+        }
+        __syncthreads();
+        if (p == NSB - 1) break;
+        // ---- (c1) bring sub-block column p+1 of A up to date: it is all the next panel's factorisation needs
+        const int nrem = NSB - 1 - p;  // sub-block rows below the panel
+        if (warp < nrem) update_sub(p, p + 1 + warp, p + 1, true);
+        __syncthreads();
+        // ---- (a) of panel p+1 on warp 0, overlapped with (c2): the remaining updates of panel p on warps 1..7
+        if (warp == 0) {
+            factor_sub(p + 1);
+        } else {
+            const int nL = (nrem - 1) * nrem / 2;  // A_IJ, p+2 <= J <= I
+            const int nW = nrem * (p + 1);         // B_IJ, I > p, J <= p
+            for (int q = warp - 1; q < nL + nW; q += 7) {
+                if (q < nL) {
+                    int r = 0;
+                    while ((r + 1) * (r + 2) / 2 <= q) ++r;
+                    update_sub(p, p + 2 + r, p + 2 + (q - r * (r + 1) / 2), true);
+                } else {
+                    const int qq = q - nL;
+                    update_sub(p, p + 1 + qq / (p + 1), qq % (p + 1), false);
+                }
+            }
+        }
+        __syncthreads();
     }
-    if (failed) {
+    if (*fail_s) {
         for (int idx = tid; idx < NB * NB; idx += 256) dinv[idx] = 0.0;
         return;
     }
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int i = ty + 16 * a, k = tx + 16 * b;
-            if (b <= a && k <= i) A[(int64_t)i * ld + k] = r[a][b];
-            dinv[i * NB + k] = (b <= a && k <= i) ? w[a][b] : 0.0;
+    for (int I = 0; I < NSB; ++I)
+        for (int J = 0; J < NSB; ++J) {
+            const int gi = SB * I + er, gj = SB * J + ec;
+            if (J <= I) {
+                if (gj <= gi) A[(int64_t)gi * ld + gj] = Lb[sblk(I, J) + er * SLD + ec];
+                dinv[gi * NB + gj] = (gj <= gi) ? Wb[sblk(I, J) + er * SLD + ec] : 0.0;
+            } else {
+                dinv[gi * NB + gj] = 0.0;
+            }
         }
 }
 
 int launch_diag(double* A, int64_t ld, int blk, const LinalgWs& ws, cudaStream_t s) {
-    potrf_diag_kernel<<<1, 256, 0, s>>>(A, ld, ws.dinv + (int64_t)blk * NB * NB, ws.info, blk * NB);
+    static bool configured_dev[64] = {};
+    int dev = 0;
+    GPB_CUDA(cudaGetDevice(&dev));
+    if (!configured_dev[dev & 63]) {
+        GPB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+        configured_dev[dev & 63] = true;
+    }
+    potrf_diag_kernel<<<1, 256, DIAG_SMEM, s>>>(A, ld, ws.dinv + (int64_t)blk * NB * NB, ws.info, blk * NB);
     GPB_CUDA(cudaGetLastError());
     count_launch();
     return 0;
