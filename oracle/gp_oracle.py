@@ -13,7 +13,8 @@ container: tests/golden/make_golden.py generates tests/golden/*.npz from the liv
 tests/test_oracle_golden.py checks this module against those fixtures.
 
 Model description used throughout:
-    comps : sequence of kernel kinds, each one of "SE", "RQ", "WHITE", "HETERO"
+    comps : sequence of terms; a term is a kernel kind "SE" | "RQ" | "WHITE" | "HETERO", or a change-point term
+            ("CP", axis, (region_0, region_1, ...)) whose regions are sequences of kernel kinds (covariance.py:371-605)
     mean  : "const" | "linear" | "quadratic"
     theta : [mean params | cov params] (regression.py:150-155), cov params concatenated in
             component order (covariance.py:61, 692-697)
@@ -39,17 +40,66 @@ def n_mean_params(mean: str, d: int) -> int:
     return {"const": 1, "linear": 1 + d, "quadratic": 1 + 2 * d}[mean]
 
 
+class Leaves(list):
+    """Flattened covariance description: list of (kind, theta_slice_values, region_index_or_None, theta_offset) plus the
+    change-point data `cp` = (axis, locations, widths, theta_offset_of_first_cp_param) or None.  Parameter order follows
+    the reference: per term in sum order (covariance.py:61); inside a ChangePoint the region kernels first, then
+    (location, width) per change-point (covariance.py:484-489)."""
+    cp = None
+    n_theta = 0
+
+
+def flatten(comps, tc, n, d):
+    tc = np.asarray(tc, dtype=float)
+    out = Leaves()
+    o = 0
+    for term in comps:
+        if isinstance(term, str):
+            p = n_cov_params(term, n, d)
+            out.append((term, tc[o:o + p], None, o))
+            o += p
+        else:
+            _, axis, regions = term
+            assert out.cp is None, "one ChangePoint per model"
+            for r, region in enumerate(regions):
+                for kind in region:
+                    p = n_cov_params(kind, n, d)
+                    out.append((kind, tc[o:o + p], r, o))
+                    o += p
+            ncp = len(regions) - 1
+            cpp = tc[o:o + 2 * ncp].reshape(ncp, 2)
+            out.cp = (axis, cpp[:, 0].copy(), cpp[:, 1].copy(), o, len(regions))
+            o += 2 * ncp
+    out.n_theta = o
+    assert o == tc.size, "wrong number of hyper-parameters"
+    return out
+
+
 def split_theta(theta, comps, mean, n, d):
     theta = np.asarray(theta, dtype=float)
     pm = n_mean_params(mean, d)
-    tm, tc = theta[:pm], theta[pm:]
-    parts, o = [], 0
-    for k in comps:
-        p = n_cov_params(k, n, d)
-        parts.append(tc[o:o + p])
-        o += p
-    assert o == tc.size, "wrong number of hyper-parameters"
-    return tm, parts
+    return theta[:pm], flatten(comps, theta[pm:], n, d)
+
+
+def _logistic(xa, loc, width):
+    """covariance.py:592-595"""
+    return 1.0 / (1.0 + np.exp(-(xa - loc) / width))
+
+
+def region_weights(leaves, pts):
+    """g_r(x) with coeff_r(u, v) = g_r(u) g_r(v): g_0 = 1 - f_0, g_r = f_{r-1} (1 - f_r), g_last = f_last
+    (covariance.py:520-531: kernel_coeffs[-1] *= w1; kernel_coeffs.append(w2))."""
+    axis, locs, widths, _, nreg = leaves.cp
+    f = [_logistic(pts[:, axis], locs[a], widths[a]) for a in range(nreg - 1)]
+    g = []
+    for r in range(nreg):
+        w = np.ones(pts.shape[0])
+        if r > 0:
+            w = w * f[r - 1]
+        if r < nreg - 1:
+            w = w * (1 - f[r])
+        g.append(w)
+    return g
 
 
 # ----------------------------------------------------------------------------- covariance functions
@@ -67,20 +117,30 @@ def cross_cov(comps, parts, u, v):
     """cov(u, v, theta): covariance.py:240-245 (SE), :335-341 (RQ); noise kernels return zeros
     (:160-161, :671-672); composite = sum (:86-89)."""
     out = np.zeros((u.shape[0], v.shape[0]))
-    for kind, th in zip(comps, parts):
+    if parts.cp is not None:
+        gu, gv = region_weights(parts, u), region_weights(parts, v)
+    for kind, th, reg, _ in parts:
         if kind == "SE":
             a, ls = np.exp(th[0]), np.exp(th[1:])
-            out += a**2 * np.exp(-_scaled_half_sqdist(u, v, ls))
+            k = a**2 * np.exp(-_scaled_half_sqdist(u, v, ls))
         elif kind == "RQ":
             a, q, ls = np.exp(th[0]), np.exp(th[1]), np.exp(th[2:])
             z = _scaled_half_sqdist(u, v, ls)
-            out += a**2 * (1 + z / q) ** (-q)
+            k = a**2 * (1 + z / q) ** (-q)
+        else:
+            continue
+        out += k if reg is None else gu[reg][:, None] * k * gv[reg][None, :]
     return out
 
 
-def prior_var(comps, parts):
-    """k(q,q): a^2 summed over the smooth components (noise kernels contribute 0)."""
-    return sum(np.exp(th[0]) ** 2 for kind, th in zip(comps, parts) if kind in ("SE", "RQ"))
+def prior_var(comps, parts, q=None):
+    """k(q,q): a^2 summed over the smooth components (noise kernels contribute 0), times the squared region weight
+    of the query point under a ChangePoint."""
+    if parts.cp is None:
+        return sum(np.exp(th[0]) ** 2 for kind, th, _, _ in parts if kind in ("SE", "RQ"))
+    g = region_weights(parts, q)
+    return sum(np.exp(th[0]) ** 2 * (1.0 if reg is None else g[reg] ** 2)
+               for kind, th, reg, _ in parts if kind in ("SE", "RQ"))
 
 
 def train_cov_rows(comps, parts, x, r0, r1, noise_var=None):
@@ -90,13 +150,15 @@ def train_cov_rows(comps, parts, x, r0, r1, noise_var=None):
     n = x.shape[0]
     blk = cross_cov(comps, parts, x[r0:r1], x)
     idx = np.arange(r0, r1)
-    for kind, th in zip(comps, parts):
+    g = region_weights(parts, x[r0:r1]) if parts.cp is not None else None
+    for kind, th, reg, _ in parts:
+        w2 = 1.0 if reg is None else g[reg] ** 2
         if kind in ("SE", "RQ"):
-            blk[idx - r0, idx] += np.exp(th[0]) ** 2 * EPS_JITTER
+            blk[idx - r0, idx] += w2 * np.exp(th[0]) ** 2 * EPS_JITTER
         elif kind == "WHITE":
-            blk[idx - r0, idx] += np.exp(2 * th[0])
+            blk[idx - r0, idx] += w2 * np.exp(2 * th[0])
         elif kind == "HETERO":
-            blk[idx - r0, idx] += np.exp(2 * th[r0:r1])
+            blk[idx - r0, idx] += w2 * np.exp(2 * th[r0:r1])
     if noise_var is not None:
         blk[idx - r0, idx] += noise_var[r0:r1]
     assert blk.shape == (r1 - r0, n)
@@ -114,44 +176,83 @@ def train_cov(comps, parts, x, noise_var=None, y_cov=None, block=2048):
     return k
 
 
-def cov_and_grads(comps, parts, x):
-    """covariance_and_gradients WITHOUT sig: covariance.py:268-276 (SE), :350-365 (RQ), :171-175
-    (White), :682-686 (Hetero), :97-105 (sum).  Dense (small-N use only: tests)."""
+def _leaf_cov_and_grads(kind, th, x):
+    """One plain kernel on the training data: (K, [dK/dtheta]) (covariance.py:268-276, 350-365, 171-175, 682-686)."""
     n, d = x.shape
     eye = np.eye(n)
+    grads = []
+    if kind == "SE":
+        a, ls = np.exp(th[0]), np.exp(th[1:])
+        k = a**2 * (np.exp(-_scaled_half_sqdist(x, x, ls)) + EPS_JITTER * eye)
+        grads.append(2.0 * k)
+        for i in range(d):
+            dx2 = (x[:, i, None] - x[None, :, i]) ** 2
+            grads.append((dx2 / ls[i] ** 2) * k)
+    elif kind == "RQ":
+        a, q, ls = np.exp(th[0]), np.exp(th[1]), np.exp(th[2:])
+        z = _scaled_half_sqdist(x, x, ls)
+        f = 1 + z / q
+        lnf = np.log(f)
+        k = a**2 * (np.exp(-q * lnf) + EPS_JITTER * eye)
+        grads.append(2.0 * k)
+        grads.append(-k * (lnf * q - z / f))
+        g = 2 * k / f
+        for i in range(d):
+            grads.append(g * (0.5 * (x[:, i, None] - x[None, :, i]) ** 2 / ls[i] ** 2))
+    elif kind == "WHITE":
+        k = np.exp(2 * th[0]) * eye
+        grads.append(2.0 * k)
+    else:
+        s2 = np.exp(2 * th)
+        k = np.diag(s2)
+        for i in range(n):
+            g = np.zeros((n, n))
+            g[i, i] = 2.0 * s2[i]
+            grads.append(g)
+    return k, grads
+
+
+def cov_and_grads(comps, parts, x):
+    """covariance_and_gradients WITHOUT sig, gradients in theta order: plain kernels (covariance.py:268-276, 350-365,
+    171-175, 682-686), sums (:97-105), ChangePoint (:541-584; the change-point gradients use the UNWEIGHTED region
+    covariances exactly as the reference does, which is exact for two regions).  Dense (small-N use only)."""
+    n, d = x.shape
     ktot = np.zeros((n, n))
     grads = []
-    for kind, th in zip(comps, parts):
-        if kind == "SE":
-            a, ls = np.exp(th[0]), np.exp(th[1:])
-            k = a**2 * (np.exp(-_scaled_half_sqdist(x, x, ls)) + EPS_JITTER * eye)
-            grads.append(2.0 * k)
-            for i in range(d):
-                dx2 = (x[:, i, None] - x[None, :, i]) ** 2
-                grads.append((dx2 / ls[i] ** 2) * k)
-        elif kind == "RQ":
-            a, q, ls = np.exp(th[0]), np.exp(th[1]), np.exp(th[2:])
-            z = _scaled_half_sqdist(x, x, ls)
-            f = 1 + z / q
-            lnf = np.log(f)
-            k = a**2 * (np.exp(-q * lnf) + EPS_JITTER * eye)
-            grads.append(2.0 * k)
-            grads.append(-k * (lnf * q - z / f))
-            g = 2 * k / f
-            for i in range(d):
-                grads.append(g * (0.5 * (x[:, i, None] - x[None, :, i]) ** 2 / ls[i] ** 2))
-        elif kind == "WHITE":
-            k = np.exp(2 * th[0]) * eye
-            grads.append(2.0 * k)
-        elif kind == "HETERO":
-            s2 = np.exp(2 * th)
-            k = np.diag(s2)
-            for i in range(n):
-                g = np.zeros((n, n))
-                g[i, i] = 2.0 * s2[i]
-                grads.append(g)
-        ktot = ktot + k
+    g = region_weights(parts, x) if parts.cp is not None else None
+    region_k = {}
+    pending_cp = parts.cp is not None
+    for idx, (kind, th, reg, _) in enumerate(parts):
+        k, gk = _leaf_cov_and_grads(kind, th, x)
+        if reg is None:
+            if pending_cp and region_k:        # first term after the ChangePoint block: emit its own gradients first
+                grads.extend(_cp_grads(parts, x, region_k))
+                pending_cp = False
+            ktot = ktot + k
+            grads.extend(gk)
+        else:
+            coeff = g[reg][:, None] * g[reg][None, :]
+            ktot = ktot + k * coeff
+            grads.extend([m * coeff for m in gk])
+            region_k[reg] = region_k.get(reg, 0) + k
+    if pending_cp and region_k:
+        grads.extend(_cp_grads(parts, x, region_k))
     return ktot, grads
+
+
+def _cp_grads(parts, x, region_k):
+    """covariance.py:574-583 with logistic_and_gradient (:597-602)."""
+    axis, locs, widths, _, nreg = parts.cp
+    out = []
+    for a in range(nreg - 1):
+        z = (x[:, axis] - locs[a]) / widths[a]
+        w = 1.0 / (1.0 + np.exp(-z))
+        dfdc = -w * (1 - w) / widths[a]
+        for dw in (dfdc, dfdc * z):
+            A = -dw[:, None] * (1 - w)[None, :]
+            B = dw[:, None] * w[None, :]
+            out.append(region_k[a] * (A + A.T) + region_k[a + 1] * (B + B.T))
+    return out
 
 
 # ----------------------------------------------------------------------------- mean functions
@@ -206,9 +307,9 @@ class Fit:
         q = self._points(q)
         mu = np.empty(q.shape[0])
         var = np.empty(q.shape[0])
-        kqq = prior_var(self.comps, self.parts)
         for s in range(0, q.shape[0], chunk):
             qq = q[s:s + chunk]
+            kqq = prior_var(self.comps, self.parts, qq)
             kqx = cross_cov(self.comps, self.parts, qq, self.x)
             mu[s:s + chunk] = kqx @ self.alpha + mean_vec(self.mean, self.tm, qq, self.xbar)
             v = solve_triangular(self.L, kqx.T, lower=True)
@@ -226,7 +327,7 @@ class Fit:
     def _se_theta(self):
         if self.comps != ("SE",):
             raise NotImplementedError("gradient_terms exists only for SquaredExponential (covariance.py:38-44, 257-266)")
-        th = self.parts[0]
+        th = self.parts[0][1]
         return np.exp(th[0]), np.exp(th[1:])
 
     # regression.py:351-385 with covariance.py:257-266.  R is a length-d vector broadcast over
@@ -427,27 +528,44 @@ def neg_log_ei_gradient(mu, sig, dmu, dvar, y_max):
 
 
 # ----------------------------------------------------------------------------- bounds
-def cov_bounds(comps, x, y):
-    """estimate_hyperpar_bounds: covariance.py:228-238 (SE), :323-333 (RQ), :151-158 (White),
-    :662-669 (Hetero).  mean_ij|dx| is over all N^2 ordered pairs including the zero diagonal."""
+def _kind_bounds(kind, x, y):
     n, d = x.shape
     out = []
-    for kind in comps:
-        if kind in ("SE", "RQ"):
-            s = np.log(y.std())
-            out.append((s - 4, s + 4))
-            if kind == "RQ":
-                out.append((-2, 6))
-            for i in range(d):
-                col = x[:, i]
-                mad = 0.0
-                for r0 in range(0, n, 1024):
-                    mad += np.abs(col[r0:r0 + 1024, None] - col[None, :]).sum()
-                mad /= n * n
-                out.append((np.log(mad) - 4, np.log(col.max() - col.min()) + 2))
+    if kind in ("SE", "RQ"):
+        s = np.log(y.std())
+        out.append((s - 4, s + 4))
+        if kind == "RQ":
+            out.append((-2, 6))
+        for i in range(d):
+            col = x[:, i]
+            mad = 0.0
+            for r0 in range(0, n, 1024):
+                mad += np.abs(col[r0:r0 + 1024, None] - col[None, :]).sum()
+            mad /= n * n
+            out.append((np.log(mad) - 4, np.log(col.max() - col.min()) + 2))
+    else:
+        s = np.log(np.ptp(y))
+        out.extend([(s - 8, s + 2)] * (1 if kind == "WHITE" else n))
+    return out
+
+
+def cov_bounds(comps, x, y):
+    """estimate_hyperpar_bounds: covariance.py:228-238 (SE), :323-333 (RQ), :151-158 (White), :662-669 (Hetero),
+    :496-511 (ChangePoint: region kernels, then (location, width) bounds per change-point).  mean_ij|dx| is over all
+    N^2 ordered pairs including the zero diagonal."""
+    out = []
+    for term in comps:
+        if isinstance(term, str):
+            out.extend(_kind_bounds(term, x, y))
         else:
-            s = np.log(np.ptp(y))
-            out.extend([(s - 8, s + 2)] * (1 if kind == "WHITE" else n))
+            _, axis, regions = term
+            for region in regions:
+                for kind in region:
+                    out.extend(_kind_bounds(kind, x, y))
+            lo, hi = x[:, axis].min(), x[:, axis].max()
+            for _ in range(len(regions) - 1):
+                out.append((lo, hi))
+                out.append((5e-3 * (hi - lo), 0.5 * (hi - lo)))
     return out
 
 

@@ -26,7 +26,7 @@ def golden_names(prefix_exclude=("fit_",)):
 def load_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     d = {k: g[k] for k in g.files}
-    d["comps"] = tuple(str(c) for c in np.atleast_1d(d["comps"]))
+    d["comps"] = tuple(parse_term(str(c)) for c in np.atleast_1d(d["comps"]))
     d["mean"] = str(d["mean"])
     if d["x"].ndim == 1:
         d["x"] = d["x"].reshape(-1, 1)
@@ -34,6 +34,14 @@ def load_golden(name):
     if "q" in d:
         d["q"] = d["q"].reshape(-1, d["x"].shape[1])
     return d
+
+
+def parse_term(text):
+    """'SE' -> 'SE';  'CP:0:SE|RQ+WHITE' -> ("CP", 0, (("SE",), ("RQ", "WHITE")))  (tests/golden/make_golden.py)"""
+    if not text.startswith("CP:"):
+        return text
+    _, axis, regions = text.split(":")
+    return ("CP", int(axis), tuple(tuple(r.split("+")) for r in regions.split("|")))
 
 
 def rel_err(a, b):
@@ -45,7 +53,8 @@ def make_kernel(gp, comps):
     cls = {"SE": gp.SquaredExponential, "RQ": gp.RationalQuadratic, "WHITE": gp.WhiteNoise, "HETERO": gp.HeteroscedasticNoise}
     k = None
     for c in comps:
-        k = cls[c]() if k is None else k + cls[c]()
+        inst = cls[c]() if isinstance(c, str) else gp.ChangePoint(kernels=[make_kernel(gp, r) for r in c[2]], axis=c[1])
+        k = inst if k is None else k + inst
     return k
 
 

@@ -36,11 +36,24 @@ MEANS = {"const": "ConstantMean", "linear": "LinearMean", "quadratic": "Quadrati
 
 
 def make_kernel(gp, comps):
+    """comps: kinds, or ("CP", axis, (region kinds...)) for a ChangePoint (one kernel per region here)"""
     k = None
     for c in comps:
-        inst = getattr(gp, KINDS[c])()
+        if isinstance(c, str):
+            inst = getattr(gp, KINDS[c])()
+        else:
+            _, axis, regions = c
+            inst = gp.ChangePoint(kernels=[make_kernel(gp, r) for r in regions], axis=axis)
         k = inst if k is None else k + inst
     return k
+
+
+def comps_repr(comps):
+    """string form stored in the fixture, e.g. 'CP:0:SE|RQ,WHITE'"""
+    out = []
+    for c in comps:
+        out.append(c if isinstance(c, str) else "CP:%d:%s" % (c[1], "|".join("+".join(r) for r in c[2])))
+    return ",".join(out)
 
 
 def synth(seed, n, d, sigma_n=0.05):
@@ -54,8 +67,21 @@ def default_theta(comps, mean, n, d, rng):
     """A well-conditioned evaluation point with a small seeded perturbation."""
     tm = {"const": [0.3], "linear": [0.3] + [0.2] * d, "quadratic": [0.3] + [0.2] * d + [-0.1] * d}[mean]
     tc = []
+    flat = []
     for c in comps:
-        if c == "SE":
+        if isinstance(c, str):
+            flat.append(c)
+        else:
+            for r in c[2]:
+                flat.extend(r)
+            nreg = len(c[2])
+            flat.extend(["CPP"] * (nreg - 1))
+    cp_seen = 0
+    for c in flat:
+        if c == "CPP":
+            cp_seen += 1
+            tc += [cp_seen / (flat.count("CPP") + 1.0), 0.08]
+        elif c == "SE":
             tc += [0.1] + [np.log(0.3)] * d
         elif c == "RQ":
             tc += [0.1, 1.0] + [np.log(0.3)] * d
@@ -64,6 +90,9 @@ def default_theta(comps, mean, n, d, rng):
         elif c == "HETERO":
             tc += list(np.log(0.05) + 0.3 * rng.standard_normal(n))
     th = np.array(tm + tc, dtype=float)
+    if "CPP" in flat:
+        th[:len(tm)] += 0.05 * rng.standard_normal(len(tm))
+        return th
     th[:len(tm) + (0 if "HETERO" in comps else len(tc))] += 0.05 * rng.standard_normal(len(tm) + (0 if "HETERO" in comps else len(tc)))
     return th
 
@@ -78,7 +107,8 @@ def case(gp, name, seed, n, d, comps, mean, m_query=64, with_err=True, store_k=F
     g = gp.GpRegressor(x, y, **kw)
     q = rng.uniform(-0.1, 1.1, (m_query, d))
     out = dict(x=x, y=y, y_err=y_err if with_err else np.zeros(0), theta=theta, q=q,
-               comps=np.array(comps), mean=np.array(mean), labels=np.array(g.hyperpar_labels),
+               comps=np.array(comps_repr(comps).split(",")) if any(not isinstance(c, str) for c in comps) else np.array(comps),
+               mean=np.array(mean), labels=np.array(g.hyperpar_labels),
                bounds=np.array(g.hp_bounds, dtype=float), alpha=g.alpha, mu_train=g.mu,
                L_diag=np.diagonal(g.L).copy())
     if store_k:
@@ -180,6 +210,11 @@ def main():
     case(gp, "se_d3_n1024_const", 25, 1024, 3, ("SE",), "const", m_query=256)
     case(gp, "rqwhite_d5_n1024_const", 26, 1024, 5, ("RQ", "WHITE"), "const", m_query=256)
     case(gp, "se_d2_n700_linear", 27, 700, 2, ("SE",), "linear", m_query=128)
+    # ChangePoint kernels (covariance.py:371-605)
+    case(gp, "cp_sese_d1_n40_const", 41, 40, 1, (("CP", 0, (("SE",), ("SE",))),), "const", store_k=True)
+    case(gp, "cp_serq_white_d2_n36_linear", 42, 36, 2, (("CP", 1, (("SE",), ("RQ",))), "WHITE"), "linear", store_k=True)
+    case(gp, "cp_sesese_d1_n48_const", 43, 48, 1, (("CP", 0, (("SE",), ("SE",), ("SE",))),), "const", store_k=True)
+    case(gp, "cp_sese_d3_n300_const", 44, 300, 3, (("CP", 2, (("SE",), ("SE",))),), "const")
     # multistart fits
     fit_case(gp, "fit_se_d1_n60", 31, 60, 1, ("SE",), "const")
     fit_case(gp, "fit_rqwhite_d2_n80", 32, 80, 2, ("RQ", "WHITE"), "const")
