@@ -56,6 +56,12 @@ int gpb_set_data(gpb_ctx* ctx, const double* x, int64_t n, int d, const double* 
                  const double* y_cov);
 /* kernel= / mean= arguments (regression.py:136-143): component kinds in sum order. */
 int gpb_set_model(gpb_ctx* ctx, const int* cov_kinds, int ncomp, int mean_kind);
+/* Same with an explicit parameter layout, needed for ChangePoint kernels (covariance.py:371-605): the leaves (plain
+ * kernels) in evaluation order, theta_offs[c] = offset of leaf c's first parameter inside theta_cov, regions[c] = index
+ * of the change-point region the leaf belongs to or -1; n_regions = 0 when there is no ChangePoint; the change-point
+ * parameters (location_a, width_a), a = 0 .. n_regions-2, start at cp_theta_off (covariance.py:484-489). */
+int gpb_set_model_ex(gpb_ctx* ctx, const int* cov_kinds, const int* theta_offs, const int* regions, int ncomp,
+                     int n_regions, int cp_axis, int cp_theta_off, int n_cov_params_total, int mean_kind);
 int gpb_num_hyperpars(gpb_ctx* ctx, int* n_mean, int* n_cov);
 
 /* CovarianceFunction.build_covariance(theta) (covariance.py:247-255, 343-348, 163-169, 674-680, 91-95);

@@ -13,7 +13,7 @@ COV_SE, COV_RQ, COV_WHITE, COV_HETERO = 0, 1, 2, 3
 MEAN_CONST, MEAN_LINEAR, MEAN_QUADRATIC = 0, 1, 2
 GET_K_XX, GET_L, GET_ALPHA, GET_MU = 0, 1, 2, 3
 EI_VALUE, EI_NEG_LOG, EI_NEG_LOG_GRAD = 0, 1, 2
-MAX_DIM, MAX_COMP = 8, 4
+MAX_DIM, MAX_COMP, MAX_REG = 8, 4, 4
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -29,6 +29,7 @@ SIGNATURES = {
     "gpb_ctx_destroy": (None, [_ctx_p]),
     "gpb_set_data": (C.c_int, [_ctx_p, _dp, C.c_int64, C.c_int, _dp, _dp, _dp]),
     "gpb_set_model": (C.c_int, [_ctx_p, _ip, C.c_int, C.c_int]),
+    "gpb_set_model_ex": (C.c_int, [_ctx_p, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gpb_num_hyperpars": (C.c_int, [_ctx_p, _ip, _ip]),
     "gpb_build_covariance": (C.c_int, [_ctx_p, _dp, C.c_int, _dp]),
     "gpb_covariance_and_gradients": (C.c_int, [_ctx_p, _dp, _dp, _dp]),
@@ -137,9 +138,17 @@ class Engine:
         yc = None if y_cov is None else _f64(y_cov)
         self._check(self.lib.gpb_set_data(self._ctx, _ptr(x), self.n, self.d, _ptr(y), _ptr(nv), _ptr(yc)))
 
-    def set_model(self, kinds, mean_kind):
+    def set_model(self, kinds, mean_kind, layout=None):
+        """kinds: leaf kernel kinds in sum order.  layout (optional, from CovarianceFunction.layout()): dict with
+        theta_offs, regions, n_regions, cp_axis, cp_theta_off, n_params for models containing a ChangePoint."""
         arr = (C.c_int * len(kinds))(*kinds)
-        self._check(self.lib.gpb_set_model(self._ctx, arr, len(kinds), mean_kind))
+        if layout is None:
+            self._check(self.lib.gpb_set_model(self._ctx, arr, len(kinds), mean_kind))
+        else:
+            offs = (C.c_int * len(kinds))(*layout["theta_offs"])
+            regs = (C.c_int * len(kinds))(*layout["regions"])
+            self._check(self.lib.gpb_set_model_ex(self._ctx, arr, offs, regs, len(kinds), layout["n_regions"],
+                                                  layout["cp_axis"], layout["cp_theta_off"], layout["n_params"], mean_kind))
         a, b = C.c_int(0), C.c_int(0)
         self._check(self.lib.gpb_num_hyperpars(self._ctx, C.byref(a), C.byref(b)))
         self.n_mean, self.n_cov = a.value, b.value

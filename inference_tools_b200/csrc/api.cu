@@ -51,10 +51,19 @@ int make_cov_params(gpb_ctx* c, const double* tc, CovParams& cp) {
     cp.d = c->d;
     cp.jitter = 1e-12;
     cp.hetero_log_sigma = nullptr;
+    cp.n_regions = c->n_regions;
+    cp.cp_axis = c->cp_axis;
+    cp.cp_theta_off = c->cp_theta_off;
+    for (int a = 0; a + 1 < c->n_regions; ++a) {  // covariance.py:592-595: theta = (location, width), not in log space
+        cp.cp_loc[a] = tc[c->cp_theta_off + 2 * a];
+        cp.cp_width[a] = tc[c->cp_theta_off + 2 * a + 1];
+    }
+    for (int i = 0; i < MAX_COMP; ++i) cp.region[i] = -1;
     for (int i = 0; i < c->ncomp; ++i) {
         const int off = c->theta_off[i];
         cp.kind[i] = c->kinds[i];
         cp.theta_off[i] = off;
+        cp.region[i] = c->region[i];
         if (c->kinds[i] == COV_SE) {
             const double a = std::exp(tc[off]);
             cp.amp2[i] = a * a;
@@ -301,19 +310,12 @@ int gpb_set_data(gpb_ctx* c, const double* x, int64_t n, int d, const double* y,
         for (int64_t i = 0; i < n; ++i) acc += x[i * d + k];
         c->xbar[k] = (double)(acc / (long double)n);
     }
-    if (c->model_set) {  // Hetero parameter count follows n
-        int off = 0;
-        for (int i = 0; i < c->ncomp; ++i) {
-            c->theta_off[i] = off;
-            off += n_cov_params(c->kinds[i], c->n, c->d);
-        }
-        c->n_cov = off;
-        c->n_mean = c->mean_kind == MEAN_CONST ? 1 : (c->mean_kind == MEAN_LINEAR ? 1 + d : 1 + 2 * d);
-    }
+    c->model_set = false;  // parameter layout depends on n (HeteroscedasticNoise): gpb_set_model must follow
     return 0;
 }
 
-int gpb_set_model(gpb_ctx* c, const int* cov_kinds, int ncomp, int mean_kind) {
+int gpb_set_model_ex(gpb_ctx* c, const int* cov_kinds, const int* theta_offs, const int* regions, int ncomp,
+                     int n_regions, int cp_axis, int cp_theta_off, int n_cov_params_total, int mean_kind) {
     GPB_TRY(use(c));
     if (ncomp < 1 || ncomp > MAX_COMP) {
         set_error("gpb_set_model: 1.." + std::to_string(MAX_COMP) + " covariance components supported");
@@ -323,16 +325,29 @@ int gpb_set_model(gpb_ctx* c, const int* cov_kinds, int ncomp, int mean_kind) {
         set_error("gpb_set_model: call gpb_set_data first");
         return -2;
     }
-    int off = 0, n_hetero = 0;
+    if (n_regions != 0 && (n_regions < 2 || n_regions > MAX_REG || cp_axis < 0 || cp_axis >= c->d)) {
+        set_error("gpb_set_model: a ChangePoint needs 2.." + std::to_string(MAX_REG) + " regions and a valid axis");
+        return -2;
+    }
+    int n_hetero = 0;
     for (int i = 0; i < ncomp; ++i) {
         if (cov_kinds[i] < COV_SE || cov_kinds[i] > COV_HETERO) {
             set_error("gpb_set_model: unknown covariance kind");
             return -2;
         }
+        const int reg = regions ? regions[i] : -1;
+        if (reg >= n_regions || reg < -1) {
+            set_error("gpb_set_model: region index out of range");
+            return -2;
+        }
         n_hetero += cov_kinds[i] == COV_HETERO;
         c->kinds[i] = cov_kinds[i];
-        c->theta_off[i] = off;
-        off += n_cov_params(cov_kinds[i], c->n, c->d);
+        c->theta_off[i] = theta_offs[i];
+        c->region[i] = reg;
+        if (theta_offs[i] < 0 || theta_offs[i] + n_cov_params(cov_kinds[i], c->n, c->d) > n_cov_params_total) {
+            set_error("gpb_set_model: parameter offsets exceed the hyper-parameter vector");
+            return -2;
+        }
     }
     if (n_hetero > 1) {
         set_error("gpb_set_model: at most one HeteroscedasticNoise component");
@@ -343,12 +358,30 @@ int gpb_set_model(gpb_ctx* c, const int* cov_kinds, int ncomp, int mean_kind) {
         return -2;
     }
     c->ncomp = ncomp;
-    c->n_cov = off;
+    c->n_cov = n_cov_params_total;
+    c->n_regions = n_regions;
+    c->cp_axis = cp_axis;
+    c->cp_theta_off = cp_theta_off;
     c->mean_kind = mean_kind;
     c->n_mean = mean_kind == MEAN_CONST ? 1 : (mean_kind == MEAN_LINEAR ? 1 + c->d : 1 + 2 * c->d);
     c->model_set = true;
     c->fitted = false;
     return 0;
+}
+
+int gpb_set_model(gpb_ctx* c, const int* cov_kinds, int ncomp, int mean_kind) {
+    GPB_TRY(use(c));
+    if (ncomp < 1 || ncomp > MAX_COMP || c->n == 0) {
+        set_error("gpb_set_model: call gpb_set_data first and pass 1.." + std::to_string(MAX_COMP) + " components");
+        return -2;
+    }
+    int offs[MAX_COMP], regs[MAX_COMP], off = 0;
+    for (int i = 0; i < ncomp; ++i) {
+        offs[i] = off;
+        regs[i] = -1;
+        off += n_cov_params(cov_kinds[i], c->n, c->d);
+    }
+    return gpb_set_model_ex(c, cov_kinds, offs, regs, ncomp, 0, 0, 0, off, mean_kind);
 }
 
 int gpb_num_hyperpars(gpb_ctx* c, int* n_mean, int* n_cov) {
@@ -544,6 +577,10 @@ int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int
 int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* info) {
     GPB_TRY(use(c));
     GPB_TRY(need_model(c));
+    if (c->n_regions && grad) {
+        set_error("gpb_loo: the leave-one-out gradient is not implemented for ChangePoint kernels");
+        return -3;
+    }
     c->timer.reset();
     const size_t np = (size_t)c->npad;
     const int npad = (int)c->npad, n = (int)c->n, nt = c->n_mean + c->n_cov;
@@ -610,7 +647,7 @@ namespace {
 
 enum PredMode { PM_PREDICT, PM_GRADIENT, PM_SPATIAL, PM_EI };
 
-bool is_pure_se(const gpb_ctx* c) { return c->ncomp == 1 && c->kinds[0] == COV_SE; }
+bool is_pure_se(const gpb_ctx* c) { return c->ncomp == 1 && c->kinds[0] == COV_SE && c->n_regions == 0; }
 
 int64_t chunk_rows(const gpb_ctx* c) {
     // rows of the stacked cross-covariance per pass: one full wave of 3 CTAs/SM on the 128-wide leaf
@@ -643,9 +680,6 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
         GPB_TRY(ensure(c->o2, c->o2_cap, sizeof(double) * (size_t)qmax));          // sig
         if (stacked) GPB_TRY(ensure(c->o3, c->o3_cap, sizeof(double) * (size_t)qmax * d * 2));  // dmu | dvar
     }
-    double kqq = 0.0;
-    for (int i = 0; i < c->ncomp; ++i)
-        if (c->kinds[i] <= COV_RQ) kqq += c->cp_fit.amp2[i];
     if (mode == PM_GRADIENT) {  // R = (a / l)^2  (covariance.py:266)
         GPB_TRY(ensure(c->R_dev, c->R_cap, sizeof(double) * MAX_DIM));
         double R[MAX_DIM];
@@ -673,7 +707,7 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
         c->timer.mark("finalize");
         switch (mode) {
             case PM_PREDICT:
-                GPB_TRY(launch_finalize_predict(c->mp_fit, qp, mq, ns, c->dots, c->G, kqq, o_a + q0, o_b + q0, c->s));
+                GPB_TRY(launch_finalize_predict(c->cp_fit, c->mp_fit, qp, mq, ns, c->dots, c->G, o_a + q0, o_b + q0, c->s));
                 break;
             case PM_GRADIENT:
                 GPB_TRY(launch_finalize_gradient(c->dots, c->G, mq, d, c->R_dev, o_a + q0 * d, o_b + q0 * d * d, c->s));
@@ -682,7 +716,7 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
                 GPB_TRY(launch_finalize_spatial(c->dots, c->G, mq, d, o_a + q0 * d, o_b + q0 * d, c->s));
                 break;
             case PM_EI:
-                GPB_TRY(launch_finalize_predict(c->mp_fit, qp, mq, ns, c->dots, c->G, kqq, c->o1, c->o2, c->s));
+                GPB_TRY(launch_finalize_predict(c->cp_fit, c->mp_fit, qp, mq, ns, c->dots, c->G, c->o1, c->o2, c->s));
                 if (stacked)
                     GPB_TRY(launch_finalize_spatial(c->dots, c->G, mq, d, c->o3, c->o3 + (size_t)qmax * d, c->s));
                 GPB_TRY(launch_ei(c->o1, c->o2, stacked ? c->o3 : nullptr, stacked ? c->o3 + (size_t)qmax * d : nullptr,
@@ -799,7 +833,7 @@ int gpb_posterior(gpb_ctx* c, const double* q, int64_t m, double* mu, double* si
     GPB_TRY(launch_cross_stack(c->cp_fit, qd, (int)m, 1, c->x, n, npad, c->S, npad, c->s));
     if (mp > m) GPB_CUDA(cudaMemsetAsync(c->S + (size_t)m * npad, 0, sizeof(double) * (size_t)(mp - m) * npad, c->s));
     GPB_TRY(launch_row_dot(c->S, npad, (int)m, npad, c->alpha, c->dots, c->s));
-    GPB_TRY(launch_finalize_predict(c->mp_fit, qd, (int)m, 1, c->dots, nullptr, 0.0, mud, nullptr, c->s));
+    GPB_TRY(launch_finalize_predict(c->cp_fit, c->mp_fit, qd, (int)m, 1, c->dots, nullptr, mud, nullptr, c->s));
     GPB_CUDA(cudaMemcpyAsync(mu, mud, sizeof(double) * m, cudaMemcpyDeviceToHost, c->s));
     if (sigma) {
         GPB_TRY(trsm_right_lt(c->S, npad, mp, c->Lfit, npad, npad, 0, ws_of(c, c->dinv_fit), c->s));

@@ -30,7 +30,8 @@ void set_error(const std::string& msg);  // api.cu; message returned by gpb_last
 // ---------------------------------------------------------------- blocking constants
 constexpr int NB = 128;          // diagonal-block / padding granularity of every dense matrix
 constexpr int MAX_DIM = 8;       // spatial dimensions held in constant-size kernel parameter structs
-constexpr int MAX_COMP = 4;      // covariance components in a composite kernel
+constexpr int MAX_COMP = 4;      // covariance components (leaves) in a composite kernel
+constexpr int MAX_REG = 4;       // regions of a ChangePoint kernel (covariance.py:371-605)
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
@@ -81,6 +82,12 @@ struct CovParams {
     double inv_l2[MAX_COMP][MAX_DIM];    // 1 / l_k^2
     const double* hetero_log_sigma;      // device pointer (N entries) for COV_HETERO, else nullptr
     double jitter;                       // 1e-12 (covariance.py:221, 318)
+    // ChangePoint (covariance.py:371-605): leaf c belongs to region[c] (-1 = not under a change-point); the leaf's
+    // covariance is weighted by g_r(u) g_r(v), g_0 = 1 - f_0, g_r = f_{r-1} (1 - f_r), g_last = f_last,
+    // f_a(x) = 1 / (1 + exp(-(x[cp_axis] - cp_loc[a]) / cp_width[a]))
+    int region[MAX_COMP];
+    int n_regions, cp_axis, cp_theta_off;
+    double cp_loc[MAX_REG - 1], cp_width[MAX_REG - 1];
 };
 struct MeanParams {
     int kind, d;

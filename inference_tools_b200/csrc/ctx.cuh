@@ -61,6 +61,7 @@ struct gpb_ctx {
     bool has_noise = false, has_ycov = false;
     double xbar[MAX_DIM] = {0};
     int ncomp = 0, kinds[MAX_COMP] = {0}, theta_off[MAX_COMP] = {0}, mean_kind = 0, n_mean = 0, n_cov = 0;
+    int region[MAX_COMP] = {-1, -1, -1, -1}, n_regions = 0, cp_axis = 0, cp_theta_off = 0;  // ChangePoint layout
     bool model_set = false;
     double* theta_dev = nullptr;
     size_t theta_dev_cap = 0;

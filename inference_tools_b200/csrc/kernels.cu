@@ -7,29 +7,33 @@
 // so a warp stores 32 consecutive doubles (256 B) per row.  The kernels are FP64-ALU bound
 // (~3d + 30 DFMA per element), not HBM bound: 8 N^2 bytes at N = 32768 is 1.3 ms of HBM time.
 #include "kernels.cuh"
+#include "cov_device.cuh"
 
 namespace gpb {
 namespace {
 
 constexpr int TILE = 128;
 
-// sum over the smooth components of a^2 f(z_c), z_c = sum_k 0.5 d2_k / l_ck^2
-__device__ __forceinline__ double cov_from_d2(const CovParams& cp, const double (&d2)[MAX_DIM]) {
+// sum over the smooth components of w_c a^2 f(z_c), z_c = sum_k 0.5 d2_k / l_ck^2; gi/gj = region weights of the two
+// points (ignored unless the model has a ChangePoint)
+__device__ __forceinline__ double cov_from_d2(const CovParams& cp, const double (&d2)[MAX_DIM],
+                                              const double (&gi)[MAX_REG], const double (&gj)[MAX_REG]) {
     double kv = 0.0;
     for (int c = 0; c < cp.ncomp; ++c) {
         const int kind = cp.kind[c];
         if (kind > COV_RQ) continue;
+        const double w = cp.n_regions ? leaf_weight(cp, c, gi, gj) : 1.0;
         double z = 0.0;
 #pragma unroll
         for (int k = 0; k < MAX_DIM; ++k)
             if (k < cp.d) z += (0.5 * d2[k]) * cp.inv_l2[c][k];
         if (kind == COV_SE) {
-            kv += cp.amp2[c] * exp(-z);
+            kv += w * cp.amp2[c] * exp(-z);
         } else {
             const double q = cp.rq_alpha[c];
             // (1 + Z/q)^-q evaluated as exp(-q ln F), the form the reference itself uses at covariance.py:356-358;
             // a few ulp from the ** of :341/:348 and less than half the cost of a double-precision pow()
-            kv += cp.amp2[c] * exp(-q * log(1.0 + z / q));
+            kv += w * cp.amp2[c] * exp(-q * log(1.0 + z / q));
         }
     }
     return kv;
@@ -37,13 +41,15 @@ __device__ __forceinline__ double cov_from_d2(const CovParams& cp, const double 
 
 // diagonal additions of the data covariance: a^2 * 1e-12 per smooth component (covariance.py:254-255,
 // 348), sigma^2 (White :168-169), exp(2 theta_i) (Hetero :679-680), y_err^2 (regression.py:320)
-__device__ __forceinline__ double diag_terms(const CovParams& cp, int gi, const double* noise_var) {
+__device__ __forceinline__ double diag_terms(const CovParams& cp, int gi, const double* noise_var,
+                                             const double (&g)[MAX_REG]) {
     double v = 0.0;
     for (int c = 0; c < cp.ncomp; ++c) {
         const int kind = cp.kind[c];
-        if (kind <= COV_RQ) v += cp.amp2[c] * cp.jitter;
-        else if (kind == COV_WHITE) v += cp.amp2[c];
-        else v += exp(2.0 * cp.hetero_log_sigma[gi]);
+        const double w = cp.n_regions ? leaf_weight(cp, c, g, g) : 1.0;
+        if (kind <= COV_RQ) v += w * cp.amp2[c] * cp.jitter;
+        else if (kind == COV_WHITE) v += w * cp.amp2[c];
+        else v += w * exp(2.0 * cp.hetero_log_sigma[gi]);
     }
     if (noise_var) v += noise_var[gi];
     return v;
@@ -62,6 +68,7 @@ __global__ void __launch_bounds__(256) assemble_train_kernel(const CovParams cp,
                                                              const double* __restrict__ y_cov, double* __restrict__ K,
                                                              int64_t ld, int mirror) {
     __shared__ double xs[TILE * MAX_DIM];
+    __shared__ double gs[TILE][MAX_REG];
     int bi, bj;
     lower_tile(blockIdx.x, bi, bj);
     const int row0 = bi * TILE, col0 = bj * TILE;
@@ -69,21 +76,32 @@ __global__ void __launch_bounds__(256) assemble_train_kernel(const CovParams cp,
     const int d = cp.d;
     for (int idx = tid; idx < TILE * d; idx += 256) xs[idx] = x[(int64_t)row0 * d + idx];
     const int gj = col0 + col;
-    double xj[MAX_DIM];
+    double xj[MAX_DIM], wj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d) ? x[(int64_t)gj * d + k] : 0.0;
+    if (cp.n_regions) {
+        region_weights(cp, x[(int64_t)gj * d + cp.cp_axis], wj);
+        if (tid < TILE) {
+            double g[MAX_REG];
+            region_weights(cp, x[(int64_t)(row0 + tid) * d + cp.cp_axis], g);
+#pragma unroll
+            for (int q = 0; q < MAX_REG; ++q) gs[tid][q] = g[q];
+        }
+    }
     __syncthreads();
     for (int r = 0; r < TILE / 2; ++r) {
         const int i = half * (TILE / 2) + r;
         const int gi = row0 + i;
-        double d2[MAX_DIM];
+        double d2[MAX_DIM], wi[MAX_REG];
 #pragma unroll
         for (int k = 0; k < MAX_DIM; ++k) {
             const double df = (k < d) ? xs[i * d + k] - xj[k] : 0.0;
             d2[k] = df * df;
         }
-        double v = cov_from_d2(cp, d2);
-        if (gi == gj) v += diag_terms(cp, gi, noise_var);
+#pragma unroll
+        for (int q = 0; q < MAX_REG; ++q) wi[q] = cp.n_regions ? gs[i][q] : 0.0;
+        double v = cov_from_d2(cp, d2, wi, wj);
+        if (gi == gj) v += diag_terms(cp, gi, noise_var, wi);
         if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
         else if (y_cov) v += y_cov[(int64_t)gi * n + gj];
         K[(int64_t)gi * ld + gj] = v;
@@ -97,26 +115,38 @@ __global__ void __launch_bounds__(256) assemble_block_kernel(const CovParams cp,
                                                              const double* __restrict__ noise_var, int row0, int col0,
                                                              double* __restrict__ out, int64_t ld) {
     __shared__ double xs[TILE * MAX_DIM];
+    __shared__ double gs[TILE][MAX_REG];
     const int r0 = row0 + blockIdx.y * TILE, c0 = col0 + blockIdx.x * TILE;
     const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
     const int d = cp.d;
     for (int idx = tid; idx < TILE * d; idx += 256) xs[idx] = x[(int64_t)r0 * d + idx];
     const int gj = c0 + col;
-    double xj[MAX_DIM];
+    double xj[MAX_DIM], wj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d) ? x[(int64_t)gj * d + k] : 0.0;
+    if (cp.n_regions) {
+        region_weights(cp, x[(int64_t)gj * d + cp.cp_axis], wj);
+        if (tid < TILE) {
+            double g[MAX_REG];
+            region_weights(cp, x[(int64_t)(r0 + tid) * d + cp.cp_axis], g);
+#pragma unroll
+            for (int q = 0; q < MAX_REG; ++q) gs[tid][q] = g[q];
+        }
+    }
     __syncthreads();
     for (int r = 0; r < TILE / 2; ++r) {
         const int i = half * (TILE / 2) + r;
         const int gi = r0 + i;
-        double d2[MAX_DIM];
+        double d2[MAX_DIM], wi[MAX_REG];
 #pragma unroll
         for (int k = 0; k < MAX_DIM; ++k) {
             const double df = (k < d) ? xs[i * d + k] - xj[k] : 0.0;
             d2[k] = df * df;
         }
-        double v = cov_from_d2(cp, d2);
-        if (gi == gj) v += diag_terms(cp, gi, noise_var);
+#pragma unroll
+        for (int q = 0; q < MAX_REG; ++q) wi[q] = cp.n_regions ? gs[i][q] : 0.0;
+        double v = cov_from_d2(cp, d2, wi, wj);
+        if (gi == gj) v += diag_terms(cp, gi, noise_var, wi);
         if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
         out[(int64_t)(gi - row0) * ld + (gj - col0)] = v;
     }
@@ -137,36 +167,65 @@ __global__ void assemble_grads_kernel(const CovParams cp, const double* __restri
         const double df = (k < d) ? x[(int64_t)i * d + k] - x[(int64_t)j * d + k] : 0.0;
         d2[k] = df * df;
     }
+    double gi[MAX_REG] = {0.0, 0.0, 0.0, 0.0}, gj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
+    if (cp.n_regions) {
+        region_weights(cp, x[(int64_t)i * d + cp.cp_axis], gi);
+        region_weights(cp, x[(int64_t)j * d + cp.cp_axis], gj);
+    }
     double ktot = 0.0;
-    int p = 0;
+    double kreg[MAX_REG] = {0.0, 0.0, 0.0, 0.0};  // unweighted covariance of each ChangePoint region
     for (int c = 0; c < cp.ncomp; ++c) {
         const int kind = cp.kind[c];
+        const double w = cp.n_regions ? leaf_weight(cp, c, gi, gj) : 1.0;
+        int p = cp.theta_off[c];
+        double kv = 0.0;
         if (kind == COV_SE) {
             double z = 0.0;
             for (int k = 0; k < d; ++k) z += (0.5 * d2[k]) * cp.inv_l2[c][k];
-            const double kv = cp.amp2[c] * (exp(-z) + (i == j ? cp.jitter : 0.0));
-            ktot += kv;
-            dK[plane * p++ + e] = 2.0 * kv;
-            for (int k = 0; k < d; ++k) dK[plane * p++ + e] = (d2[k] * cp.inv_l2[c][k]) * kv;
+            kv = cp.amp2[c] * (exp(-z) + (i == j ? cp.jitter : 0.0));
+            dK[plane * p++ + e] = w * 2.0 * kv;
+            for (int k = 0; k < d; ++k) dK[plane * p++ + e] = w * (d2[k] * cp.inv_l2[c][k]) * kv;
         } else if (kind == COV_RQ) {
             double z = 0.0;
             for (int k = 0; k < d; ++k) z += (0.5 * d2[k]) * cp.inv_l2[c][k];
             const double q = cp.rq_alpha[c];
             const double F = 1.0 + z / q, lnF = log(F);
-            const double kv = cp.amp2[c] * (exp(-q * lnF) + (i == j ? cp.jitter : 0.0));
-            ktot += kv;
-            dK[plane * p++ + e] = 2.0 * kv;
-            dK[plane * p++ + e] = -kv * (lnF * q - z / F);
+            kv = cp.amp2[c] * (exp(-q * lnF) + (i == j ? cp.jitter : 0.0));
+            dK[plane * p++ + e] = w * 2.0 * kv;
+            dK[plane * p++ + e] = w * -kv * (lnF * q - z / F);
             const double G = 2.0 * kv / F;
-            for (int k = 0; k < d; ++k) dK[plane * p++ + e] = G * ((0.5 * d2[k]) * cp.inv_l2[c][k]);
+            for (int k = 0; k < d; ++k) dK[plane * p++ + e] = w * G * ((0.5 * d2[k]) * cp.inv_l2[c][k]);
         } else if (kind == COV_WHITE) {
-            const double kv = (i == j) ? cp.amp2[c] : 0.0;
-            ktot += kv;
-            dK[plane * p++ + e] = 2.0 * kv;
+            kv = (i == j) ? cp.amp2[c] : 0.0;
+            dK[plane * p++ + e] = w * 2.0 * kv;
         } else {
-            const double s2 = (i == j) ? exp(2.0 * cp.hetero_log_sigma[i]) : 0.0;
-            ktot += s2;
-            for (int m = 0; m < n; ++m) dK[plane * p++ + e] = (m == i) ? 2.0 * s2 : 0.0;
+            kv = (i == j) ? exp(2.0 * cp.hetero_log_sigma[i]) : 0.0;
+            for (int m = 0; m < n; ++m) dK[plane * p++ + e] = (m == i) ? w * 2.0 * kv : 0.0;
+        }
+        ktot += w * kv;
+        const int r = cp.region[c];
+#pragma unroll
+        for (int q2 = 0; q2 < MAX_REG; ++q2)
+            if (q2 == r) kreg[q2] += kv;
+    }
+    // change-point parameters (covariance.py:574-583): dK = K_a (A + A^T) + K_{a+1} (B + B^T),
+    // A = -dw (1 - w)^T, B = dw w^T, dw = df/dc or df/dwidth (logistic_and_gradient :597-602)
+    for (int a = 0; a + 1 < cp.n_regions; ++a) {
+        const double zi = (x[(int64_t)i * d + cp.cp_axis] - cp.cp_loc[a]) / cp.cp_width[a];
+        const double zj = (x[(int64_t)j * d + cp.cp_axis] - cp.cp_loc[a]) / cp.cp_width[a];
+        const double fi = 1.0 / (1.0 + exp(-zi)), fj = 1.0 / (1.0 + exp(-zj));
+        const double dci = -fi * (1.0 - fi) / cp.cp_width[a], dcj = -fj * (1.0 - fj) / cp.cp_width[a];
+        double ka = 0.0, kb = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < MAX_REG; ++q2) {
+            if (q2 == a) ka = kreg[q2];
+            if (q2 == a + 1) kb = kreg[q2];
+        }
+        for (int v = 0; v < 2; ++v) {
+            const double dwi = v ? dci * zi : dci, dwj = v ? dcj * zj : dcj;
+            const double AAt = -(dwi * (1.0 - fj) + dwj * (1.0 - fi));
+            const double BBt = dwi * fj + dwj * fi;
+            dK[plane * (cp.cp_theta_off + 2 * a + v) + e] = ka * AAt + kb * BBt;
         }
     }
     K[e] = ktot;
@@ -184,7 +243,12 @@ __global__ void cross_cov_kernel(const CovParams cp, const double* __restrict__ 
         const double df = (k < d) ? u[(int64_t)i * d + k] - v[(int64_t)j * d + k] : 0.0;
         d2[k] = df * df;
     }
-    out[(int64_t)i * ld + j] = cov_from_d2(cp, d2);
+    double wi[MAX_REG] = {0.0, 0.0, 0.0, 0.0}, wj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
+    if (cp.n_regions) {
+        region_weights(cp, u[(int64_t)i * d + cp.cp_axis], wi);
+        region_weights(cp, v[(int64_t)j * d + cp.cp_axis], wj);
+    }
+    out[(int64_t)i * ld + j] = cov_from_d2(cp, d2, wi, wj);
 }
 
 // Stacked cross-covariance rows of one query chunk.  grid = (npad/128, ceil(mq/128)).
@@ -192,15 +256,25 @@ __global__ void __launch_bounds__(256) cross_stack_kernel(const CovParams cp, co
                                                           int nstack, const double* __restrict__ x, int n,
                                                           double* __restrict__ S, int64_t ld) {
     __shared__ double qs[TILE * MAX_DIM];
+    __shared__ double gs[TILE][MAX_REG];
     const int col0 = blockIdx.x * TILE, q0 = blockIdx.y * TILE;
     const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
     const int d = cp.d;
     const int nq = min(TILE, mq - q0);
     for (int idx = tid; idx < nq * d; idx += 256) qs[idx] = q[(int64_t)q0 * d + idx];
     const int gj = col0 + col;
-    double xj[MAX_DIM];
+    double xj[MAX_DIM], wj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d && gj < n) ? x[(int64_t)gj * d + k] : 0.0;
+    if (cp.n_regions) {
+        if (gj < n) region_weights(cp, x[(int64_t)gj * d + cp.cp_axis], wj);
+        if (tid < nq) {
+            double g[MAX_REG];
+            region_weights(cp, q[(int64_t)(q0 + tid) * d + cp.cp_axis], g);
+#pragma unroll
+            for (int r = 0; r < MAX_REG; ++r) gs[tid][r] = g[r];
+        }
+    }
     __syncthreads();
     for (int r = 0; r < TILE / 2; ++r) {
         const int i = half * (TILE / 2) + r;
@@ -211,7 +285,10 @@ __global__ void __launch_bounds__(256) cross_stack_kernel(const CovParams cp, co
             df[k] = (k < d) ? xj[k] - qs[i * d + k] : 0.0;
             d2[k] = df[k] * df[k];
         }
-        const double kv = (gj < n) ? cov_from_d2(cp, d2) : 0.0;
+        double wi[MAX_REG];
+#pragma unroll
+        for (int r2 = 0; r2 < MAX_REG; ++r2) wi[r2] = cp.n_regions ? gs[i][r2] : 0.0;
+        const double kv = (gj < n) ? cov_from_d2(cp, d2, wi, wj) : 0.0;
         double* dst = S + (int64_t)(q0 + i) * nstack * ld + gj;
         dst[0] = kv;
         if (nstack > 1) {
@@ -324,13 +401,22 @@ __device__ __forceinline__ double mean_at(const MeanParams& mp, const double* pt
     return m;
 }
 
-__global__ void finalize_predict_kernel(const MeanParams mp, const double* __restrict__ q, int mq, int nstack,
-                                        const double* __restrict__ dots, const double* __restrict__ G, double kqq,
+__global__ void finalize_predict_kernel(const CovParams cp, const MeanParams mp, const double* __restrict__ q, int mq,
+                                        int nstack, const double* __restrict__ dots, const double* __restrict__ G,
                                         double* __restrict__ mu, double* __restrict__ sig) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= mq) return;
     mu[i] = dots[(int64_t)i * nstack] + mean_at(mp, q + (int64_t)i * mp.d);
-    if (sig) sig[i] = sqrt(fabs(kqq - G[(int64_t)i * nstack * nstack]));
+    if (sig) {
+        // k(q, q): a^2 of every smooth component (noise kernels contribute 0, covariance.py:160-161, 671-672),
+        // weighted by the query point's squared region weight under a ChangePoint
+        double g[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
+        if (cp.n_regions) region_weights(cp, q[(int64_t)i * cp.d + cp.cp_axis], g);
+        double kqq = 0.0;
+        for (int c = 0; c < cp.ncomp; ++c)
+            if (cp.kind[c] <= COV_RQ) kqq += (cp.n_regions ? leaf_weight(cp, c, g, g) : 1.0) * cp.amp2[c];
+        sig[i] = sqrt(fabs(kqq - G[(int64_t)i * nstack * nstack]));
+    }
 }
 
 __global__ void finalize_gradient_kernel(const double* __restrict__ dots, const double* __restrict__ G, int mq, int d,
@@ -496,9 +582,9 @@ int launch_row_gram(const double* X, int64_t ld, int mq, int nstack, int ncols, 
     GPB_LAUNCH_CHECK();
 }
 
-int launch_finalize_predict(const MeanParams& mp, const double* q, int mq, int nstack, const double* dots,
-                            const double* G, double kqq, double* mu, double* sig, cudaStream_t s) {
-    finalize_predict_kernel<<<(mq + 255) / 256, 256, 0, s>>>(mp, q, mq, nstack, dots, G, kqq, mu, sig);
+int launch_finalize_predict(const CovParams& cp, const MeanParams& mp, const double* q, int mq, int nstack,
+                            const double* dots, const double* G, double* mu, double* sig, cudaStream_t s) {
+    finalize_predict_kernel<<<(mq + 255) / 256, 256, 0, s>>>(cp, mp, q, mq, nstack, dots, G, mu, sig);
     GPB_LAUNCH_CHECK();
 }
 

@@ -29,9 +29,9 @@ int launch_col_dot(const double* S, int64_t ld, int nrows, int ncols, const doub
                    cudaStream_t s);
 // G[q][a][b] = sum_j X[q*ns+a][j] X[q*ns+b][j]
 int launch_row_gram(const double* X, int64_t ld, int mq, int nstack, int ncols, double* G, cudaStream_t s);
-// predictive mean/sigma (regression.py:212-216): mu = dot + mean(q); sig = sqrt|kqq - G|
-int launch_finalize_predict(const MeanParams& mp, const double* q, int mq, int nstack, const double* dots,
-                            const double* G, double kqq, double* mu, double* sig, cudaStream_t s);
+// predictive mean/sigma (regression.py:212-216): mu = dot + mean(q); sig = sqrt|k(q,q) - G|
+int launch_finalize_predict(const CovParams& cp, const MeanParams& mp, const double* q, int mq, int nstack,
+                            const double* dots, const double* G, double* mu, double* sig, cudaStream_t s);
 // gradient() outputs (regression.py:379-380): mean[q][a] = dots[q*ns+1+a]; cov[q][a][b] = R[b] - G[q][a+1][b+1]
 int launch_finalize_gradient(const double* dots, const double* G, int mq, int d, const double* R_dev, double* mean,
                              double* cov, cudaStream_t s);

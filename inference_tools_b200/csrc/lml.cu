@@ -6,6 +6,7 @@
 // the lower tiles of Kinv per smooth component (HBM-read bound: 4 N^2 bytes), with per-tile partial sums
 // reduced in a fixed order (bit-reproducible).  Noise kernels only need diag(alpha alpha^T - Kinv).
 #include "kernels.cuh"
+#include "cov_device.cuh"
 
 namespace gpb {
 namespace {
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
                                                            double* __restrict__ partials) {
     __shared__ double xs[TILE * MAX_DIM];
     __shared__ double as[TILE];
+    __shared__ double ws[TILE];   // ChangePoint weight of this leaf's region at the row points
     __shared__ double red[8][NACC];
     int bi, bj;
     lower_tile(blockIdx.x, bi, bj);
@@ -37,6 +39,18 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
     for (int idx = tid; idx < TILE * d; idx += 256) xs[idx] = x[(int64_t)row0 * d + idx];
     if (tid < TILE) as[tid] = alpha[row0 + tid];
     const int gj = col0 + col;
+    double wcol = 1.0;
+    if (cp.n_regions && cp.region[c] >= 0) {
+        double g[MAX_REG];
+        region_weights(cp, x[(int64_t)gj * d + cp.cp_axis], g);
+        wcol = pick_region(g, cp.region[c]);
+        if (tid < TILE) {
+            region_weights(cp, x[(int64_t)(row0 + tid) * d + cp.cp_axis], g);
+            ws[tid] = pick_region(g, cp.region[c]);
+        }
+    } else if (tid < TILE) {
+        ws[tid] = 1.0;
+    }
     double xj[MAX_DIM], il2[MAX_DIM];
 #pragma unroll
     for (int k = 0; k < MAX_DIM; ++k) {
@@ -55,7 +69,8 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
         const int gi = row0 + i;
         if (gi < gj || gi >= n || gj >= n) continue;
         const double w = (gi == gj) ? 1.0 : 2.0;  // symmetry: strict lower counted twice
-        const double Q = w * (as[i] * aj - Kinv[(int64_t)gi * ld + gj]);
+        // dK of a leaf under a ChangePoint carries the region coefficient g_r(x_i) g_r(x_j) (covariance.py:570-572)
+        const double Q = w * (ws[i] * wcol) * (as[i] * aj - Kinv[(int64_t)gi * ld + gj]);
         double s[MAX_DIM];  // 0.5 dx^2 / l^2 per dimension
         double z = 0.0;
 #pragma unroll
@@ -120,6 +135,109 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
     }
 }
 
+// change-point parameters (location, width) of change-point `a` (covariance.py:574-583):
+//   dK = K_a (A + A^T) + K_{a+1} (B + B^T),  A = -dw (1 - f)^T,  B = dw f^T,  dw = df/dc or df/dwidth,
+// with K_a the UNWEIGHTED covariance of region a (its leaves summed, own diagonal terms included), as the reference
+// computes it.  partials[tile][0..1] = 1/2 sum Q dK for (location, width).
+__global__ void __launch_bounds__(256) trace_cp_kernel(const CovParams cp, int a, const double* __restrict__ x, int n,
+                                                       const double* __restrict__ alpha,
+                                                       const double* __restrict__ Kinv, int64_t ld,
+                                                       double* __restrict__ partials) {
+    __shared__ double xs[TILE * MAX_DIM];
+    __shared__ double as[TILE];
+    __shared__ double fs[TILE], zs[TILE];
+    __shared__ double red[8][2];
+    int bi, bj;
+    lower_tile(blockIdx.x, bi, bj);
+    const int row0 = bi * TILE, col0 = bj * TILE;
+    const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
+    const int d = cp.d;
+    for (int idx = tid; idx < TILE * d; idx += 256) xs[idx] = x[(int64_t)row0 * d + idx];
+    const double loc = cp.cp_loc[a], width = cp.cp_width[a];
+    if (tid < TILE) {
+        as[tid] = alpha[row0 + tid];
+        const double z = (x[(int64_t)(row0 + tid) * d + cp.cp_axis] - loc) / width;
+        zs[tid] = z;
+        fs[tid] = 1.0 / (1.0 + exp(-z));
+    }
+    const int gj = col0 + col;
+    double xj[MAX_DIM];
+#pragma unroll
+    for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d) ? x[(int64_t)gj * d + k] : 0.0;
+    const double zj = (x[(int64_t)gj * d + cp.cp_axis] - loc) / width;
+    const double fj = 1.0 / (1.0 + exp(-zj));
+    const double dcj = -fj * (1.0 - fj) / width;
+    const double aj = alpha[gj];
+    double acc0 = 0.0, acc1 = 0.0;
+    __syncthreads();
+    for (int r = 0; r < TILE / 2; ++r) {
+        const int i = half * (TILE / 2) + r;
+        const int gi = row0 + i;
+        if (gi < gj || gi >= n || gj >= n) continue;
+        const double Q = ((gi == gj) ? 0.5 : 1.0) * (as[i] * aj - Kinv[(int64_t)gi * ld + gj]);  // 1/2 * symmetry weight
+        double d2[MAX_DIM];
+#pragma unroll
+        for (int k = 0; k < MAX_DIM; ++k) {
+            const double df = (k < d) ? xs[i * d + k] - xj[k] : 0.0;
+            d2[k] = df * df;
+        }
+        double ka = 0.0, kb = 0.0;
+        for (int c = 0; c < cp.ncomp; ++c) {
+            const int reg = cp.region[c];
+            if (reg != a && reg != a + 1) continue;
+            double kv = 0.0;
+            if (cp.kind[c] <= COV_RQ) {
+                double z = 0.0;
+#pragma unroll
+                for (int k = 0; k < MAX_DIM; ++k)
+                    if (k < d) z += (0.5 * d2[k]) * cp.inv_l2[c][k];
+                const double base = (cp.kind[c] == COV_SE) ? exp(-z) : exp(-cp.rq_alpha[c] * log(1.0 + z / cp.rq_alpha[c]));
+                kv = cp.amp2[c] * (base + (gi == gj ? cp.jitter : 0.0));
+            } else if (gi == gj) {
+                kv = (cp.kind[c] == COV_WHITE) ? cp.amp2[c] : exp(2.0 * cp.hetero_log_sigma[gi]);
+            }
+            if (reg == a) ka += kv;
+            else kb += kv;
+        }
+        const double fi = fs[i], zi = zs[i];
+        const double dci = -fi * (1.0 - fi) / width;
+        acc0 = fma(Q, ka * -(dci * (1.0 - fj) + dcj * (1.0 - fi)) + kb * (dci * fj + dcj * fi), acc0);
+        const double dwi = dci * zi, dwj = dcj * zj;
+        acc1 = fma(Q, ka * -(dwi * (1.0 - fj) + dwj * (1.0 - fi)) + kb * (dwi * fj + dwj * fi), acc1);
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+    }
+    if (lane == 0) {
+        red[warp][0] = acc0;
+        red[warp][1] = acc1;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][tid];
+        partials[(int64_t)blockIdx.x * NACC + tid] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_pair_kernel(const double* __restrict__ partials, int ntiles, int off,
+                                                          double* __restrict__ grad) {
+    __shared__ double sm[256];
+    const int p = blockIdx.x;
+    double v = 0.0;
+    for (int t = threadIdx.x; t < ntiles; t += 256) v += partials[(int64_t)t * NACC + p];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) grad[off + p] = sm[0];
+}
+
 // single CTA: mean-parameter gradients, White / Hetero gradients from diag(alpha alpha^T - Kinv)
 __global__ void __launch_bounds__(1024) diag_terms_kernel(const CovParams cp, const MeanParams mp, int n_theta_mean, const double* __restrict__ x, int n,
                                                           const double* __restrict__ alpha,
@@ -159,12 +277,28 @@ __global__ void __launch_bounds__(1024) diag_terms_kernel(const CovParams cp, co
     for (int c = 0; c < cp.ncomp; ++c) {
         if (cp.kind[c] == COV_WHITE) {
             double v = 0.0;
-            for (int i = tid; i < n; i += 1024) v += alpha[i] * alpha[i] - Kinv[(int64_t)i * ld + i];
+            for (int i = tid; i < n; i += 1024) {
+                double w2 = 1.0;
+                if (cp.n_regions && cp.region[c] >= 0) {
+                    double g[MAX_REG];
+                    region_weights(cp, x[(int64_t)i * cp.d + cp.cp_axis], g);
+                    w2 = pick_region(g, cp.region[c]);
+                    w2 *= w2;
+                }
+                v += w2 * (alpha[i] * alpha[i] - Kinv[(int64_t)i * ld + i]);
+            }
             v = block_sum(v);
             if (tid == 0) grad[n_theta_mean + cp.theta_off[c]] = cp.amp2[c] * v;  // 0.5 * sum Q_ii * 2 sigma^2
         } else if (cp.kind[c] == COV_HETERO) {
             for (int i = tid; i < n; i += 1024) {
-                const double s2 = exp(2.0 * cp.hetero_log_sigma[i]);
+                double w2 = 1.0;
+                if (cp.n_regions && cp.region[c] >= 0) {
+                    double g[MAX_REG];
+                    region_weights(cp, x[(int64_t)i * cp.d + cp.cp_axis], g);
+                    w2 = pick_region(g, cp.region[c]);
+                    w2 *= w2;
+                }
+                const double s2 = w2 * exp(2.0 * cp.hetero_log_sigma[i]);
                 grad[n_theta_mean + cp.theta_off[c] + i] = s2 * (alpha[i] * alpha[i] - Kinv[(int64_t)i * ld + i]);
             }
         }
@@ -188,6 +322,15 @@ int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean,
         GPB_CUDA(cudaGetLastError());
         reduce_partials_kernel<<<NACC, 256, 0, s>>>(partials, ntiles, cp.d, cp.kind[c] == COV_RQ,
                                                     n_theta_mean + cp.theta_off[c], grad_dev);
+        GPB_CUDA(cudaGetLastError());
+        count_launch(2);
+    }
+    for (int a = 0; a + 1 < cp.n_regions; ++a) {
+        // off-diagonal symmetry: the strict lower triangle counts twice, folded with the 1/2 into Q's weight, but
+        // dK is not symmetric in (i, j) term by term -- (A + A^T) and (B + B^T) are, so the fold is exact
+        trace_cp_kernel<<<ntiles, 256, 0, s>>>(cp, a, x, n, alpha, Kinv, ld, partials);
+        GPB_CUDA(cudaGetLastError());
+        reduce_pair_kernel<<<2, 256, 0, s>>>(partials, ntiles, n_theta_mean + cp.cp_theta_off + 2 * a, grad_dev);
         GPB_CUDA(cudaGetLastError());
         count_launch(2);
     }

@@ -8,6 +8,7 @@ from inference_tools_b200.gp.covariance import (
     RationalQuadratic,
     WhiteNoise,
     HeteroscedasticNoise,
+    ChangePoint,
 )
 
 __all__ = [
@@ -23,4 +24,5 @@ __all__ = [
     "RationalQuadratic",
     "WhiteNoise",
     "HeteroscedasticNoise",
+    "ChangePoint",
 ]

@@ -16,7 +16,7 @@ import numpy as np
 
 from inference_tools_b200 import _lib
 
-SUPPORTED = "SquaredExponential, RationalQuadratic, WhiteNoise, HeteroscedasticNoise and sums of them"
+SUPPORTED = "SquaredExponential, RationalQuadratic, WhiteNoise, HeteroscedasticNoise, ChangePoint and sums of them"
 
 
 def mean_abs_difference(col: np.ndarray) -> float:
@@ -51,10 +51,22 @@ class CovarianceFunction(ABC):
 
     # ---- engine description
     def kinds(self) -> list:
-        return [self.kind]
+        return [leaf["kind"] for leaf in self.layout()["leaves"]]
 
     def _components(self):
         return [self]
+
+    def layout(self) -> dict:
+        """Flattened description handed to the engine (gpb_set_model_ex): `leaves` = plain kernels in evaluation order,
+        each with its parameter offset inside this function's theta and the ChangePoint region it belongs to (-1 = none);
+        `cp` = None or dict(axis, theta_off, n_regions).  Needs pass_spatial_data first (parameter counts)."""
+        return {"leaves": [{"kind": self.kind, "off": 0, "region": -1}], "cp": None, "n_params": self.n_params}
+
+    def engine_layout(self) -> dict:
+        lay = self.layout()
+        cp = lay["cp"] or {"axis": 0, "theta_off": 0, "n_regions": 0}
+        return {"theta_offs": [leaf["off"] for leaf in lay["leaves"]], "regions": [leaf["region"] for leaf in lay["leaves"]],
+                "n_regions": cp["n_regions"], "cp_axis": cp["axis"], "cp_theta_off": cp["theta_off"], "n_params": lay["n_params"]}
 
     def _ensure_engine(self):
         if self._x is None:
@@ -62,7 +74,7 @@ class CovarianceFunction(ABC):
         if self._engine is None:
             eng = _lib.Engine()
             eng.set_data(self._x, np.zeros(self._x.shape[0]))
-            eng.set_model(self.kinds(), _lib.MEAN_CONST)
+            eng.set_model(self.kinds(), _lib.MEAN_CONST, self.engine_layout())
             self._engine = eng
         return self._engine
 
@@ -119,16 +131,26 @@ class CompositeCovariance(CovarianceFunction):
         for c in covariance_components:
             if not isinstance(c, CovarianceFunction) or isinstance(c, CompositeCovariance):
                 raise TypeError(f"unsupported covariance component {type(c)}; supported: {SUPPORTED}")
-        if len(covariance_components) > _lib.MAX_COMP:
-            raise ValueError(f"at most {_lib.MAX_COMP} covariance components are supported")
         self.components = covariance_components
         self.bounds = None
 
-    def kinds(self):
-        return [c.kind for c in self.components]
-
     def _components(self):
-        return self.components
+        out = []
+        for comp in self.components:
+            out.extend(comp._components())
+        return out
+
+    def layout(self):
+        leaves, cp, off = [], None, 0
+        for comp in self.components:
+            lay = comp.layout()
+            leaves.extend({"kind": leaf["kind"], "off": leaf["off"] + off, "region": leaf["region"]} for leaf in lay["leaves"])
+            if lay["cp"] is not None:
+                if cp is not None:
+                    raise ValueError("at most one ChangePoint kernel per covariance function is supported")
+                cp = dict(lay["cp"], theta_off=lay["cp"]["theta_off"] + off)
+            off += lay["n_params"]
+        return {"leaves": leaves, "cp": cp, "n_params": off}
 
     def pass_spatial_data(self, x: np.ndarray):
         for comp in self.components:
@@ -244,6 +266,112 @@ class HeteroscedasticNoise(CovarianceFunction):
         self.bounds = [(s - 8, s + 2) for _ in range(self.n_params)]
 
 
+class ChangePoint(CovarianceFunction):
+    r"""Divides the input space into regions along one axis, each modelled by its own kernel
+    (reference covariance.py:371-605):  K_cp(u, v) = sum_r g_r(u) K_r(u, v) g_r(v) with logistic region weights
+    f_i(x) = 1 / (1 + exp(-(x - c_i) / w_i)), g_0 = 1 - f_0, g_r = f_{r-1} (1 - f_r), g_last = f_last.
+    theta = [theta of K_0, ..., theta of K_{n-1}, c_0, w_0, c_1, w_1, ...] (locations and widths are not in log space).
+
+    :param kernels: the kernel classes / objects (K0, K1, ...), one per region (plain kernels or sums of them)
+    :param int axis: the spatial axis along which the regions are divided
+    :param location_bounds: n-1 (lower, upper) pairs for the change-point locations
+    :param width_bounds: n-1 (lower, upper) pairs for the change-point widths
+    """
+
+    kind = -2  # not a leaf: described through layout()
+
+    def __init__(self, kernels, axis: int = 0, location_bounds=None, width_bounds=None):
+        super().__init__()
+        from inspect import isclass
+
+        self.cov = [K() if isclass(K) and issubclass(K, CovarianceFunction) else K for K in kernels]
+        for K in self.cov:
+            if not isinstance(K, CovarianceFunction) or isinstance(K, ChangePoint):
+                raise TypeError(
+                    """\n
+                    \r[ ChangePoint error ]
+                    \r>> Each of the specified covariance kernels must be an instance of
+                    \r>> a class which inherits from the 'CovarianceFunction' abstract
+                    \r>> base-class.
+                    """
+                )
+        self.n_kernels = len(kernels)
+        if not 2 <= self.n_kernels <= _lib.MAX_REG:
+            raise ValueError(f"[ ChangePoint error ] between 2 and {_lib.MAX_REG} region kernels are supported")
+        for name, given in (("location_bounds", location_bounds), ("width_bounds", width_bounds)):
+            if given is not None and len(given) != self.n_kernels - 1:
+                raise ValueError(
+                    f"""\n
+                    \r[ ChangePoint error ]
+                    \r>> The length of '{name}' must be one less than the number of kernels
+                    """
+                )
+        self.location_bounds = None if location_bounds is None else [check_bounds(b) for b in location_bounds]
+        self.width_bounds = None if width_bounds is None else [check_bounds(b) for b in width_bounds]
+        self.axis = axis
+        self.bounds = None
+
+    def _components(self):
+        out = []
+        for K in self.cov:
+            out.extend(K._components())
+        return out
+
+    def layout(self):
+        leaves, off = [], 0
+        for r, K in enumerate(self.cov):
+            lay = K.layout()
+            if lay["cp"] is not None:
+                raise ValueError("ChangePoint kernels cannot be nested")
+            leaves.extend({"kind": leaf["kind"], "off": leaf["off"] + off, "region": r} for leaf in lay["leaves"])
+            off += lay["n_params"]
+        cp = {"axis": self.axis, "theta_off": off, "n_regions": self.n_kernels}
+        return {"leaves": leaves, "cp": cp, "n_params": off + 2 * (self.n_kernels - 1)}
+
+    def pass_spatial_data(self, x: np.ndarray):
+        for K in self.cov:
+            K.pass_spatial_data(x)
+        self._register_data(x)
+        counts = [K.n_params for K in self.cov] + [2] * (self.n_kernels - 1)
+        self.n_params = sum(counts)
+        slices = slice_builder(counts)
+        self.cov_slc, self.cp_slc = slices[: self.n_kernels], slices[self.n_kernels:]
+        self.hyperpar_labels = []
+        for i, K in enumerate(self.cov):
+            self.hyperpar_labels.extend(f"ChngPnt K{i}: {lab}" for lab in K.hyperpar_labels)
+        for i in range(self.n_kernels - 1):
+            self.hyperpar_labels.extend([f"ChngPnt{i} location", f"ChngPnt{i} width"])
+        self.x_cp = x[:, self.axis]
+
+    def estimate_hyperpar_bounds(self, y: np.ndarray):
+        xr = self.x_cp.min(), self.x_cp.max()
+        dx = xr[1] - xr[0]
+        self.bounds = []
+        for K in self.cov:
+            K.estimate_hyperpar_bounds(y)
+            self.bounds.extend(K.bounds)
+        if self.location_bounds is None:
+            self.location_bounds = [xr] * (self.n_kernels - 1)
+        if self.width_bounds is None:
+            self.width_bounds = [(5e-3 * dx, 0.5 * dx)] * (self.n_kernels - 1)
+        for loc, wid in zip(self.location_bounds, self.width_bounds):
+            self.bounds.extend([loc, wid])
+
+    @staticmethod
+    def logistic(x, theta):
+        z = (x - theta[0]) / theta[1]
+        return 1.0 / (1.0 + np.exp(-z))
+
+
+def check_bounds(bounds):
+    """covariance.py:700-705"""
+    if bounds is not None:
+        assert type(bounds) in [list, tuple, np.ndarray]
+        assert len(bounds) == 2
+        assert bounds[1] > bounds[0]
+    return bounds
+
+
 def slice_builder(lengths: list) -> list:
     """Consecutive parameter slices of the components (covariance.py:692-697)."""
     out, start = [], 0
@@ -258,7 +386,8 @@ def as_engine_covariance(kernel) -> CovarianceFunction:
     from inspect import isclass
 
     cov = kernel() if isclass(kernel) else kernel
-    if not isinstance(cov, CovarianceFunction) or any(c.kind < 0 for c in cov._components()):
+    if not isinstance(cov, CovarianceFunction) or any(c.kind < 0 for c in cov._components()) \
+            or len(cov._components()) > _lib.MAX_COMP:
         raise TypeError(
             f"""\n
             [ GpRegressor error ]

@@ -141,7 +141,7 @@ class GpRegressor:
     def _new_engine(self, device=None) -> _lib.Engine:
         eng = _lib.Engine(self._device if device is None else device)
         eng.set_data(self.x, self.y, self._noise_var, self._y_cov)
-        eng.set_model(self.cov.kinds(), self.mean.kind)
+        eng.set_model(self.cov.kinds(), self.mean.kind, self.cov.engine_layout())
         if eng.n_mean + eng.n_cov != self.n_hyperpars:
             raise RuntimeError("engine / host hyper-parameter layout mismatch")
         return eng

@@ -494,3 +494,67 @@ def test_heteroscedastic_noise_in_more_than_one_dimension():
     lml_o, grad_o = orc.marginal_likelihood_gradient(x, y, ("SE", "HETERO"), "const", theta, e**2)
     assert abs(lml - lml_o) <= TOL * abs(lml_o) and np.abs(grad - grad_o).max() <= TOL * np.abs(grad_o).max()
     assert len(m.hyperpar_labels) == 64 and m.hyperpar_labels[4] == "K2: log_sigma_1"
+
+
+@pytest.mark.parametrize("build", [
+    lambda: gp.SquaredExponential(), lambda: gp.RationalQuadratic(), lambda: gp.WhiteNoise(), lambda: gp.HeteroscedasticNoise(),
+    lambda: gp.RationalQuadratic() + gp.WhiteNoise(), lambda: gp.RationalQuadratic() + gp.HeteroscedasticNoise(),
+    lambda: gp.ChangePoint(kernels=[gp.SquaredExponential, gp.SquaredExponential]),
+    lambda: gp.ChangePoint(kernels=[gp.SquaredExponential, gp.RationalQuadratic]) + gp.WhiteNoise(),
+])
+def test_reference_covariance_gradient_check(build):
+    """tests/test_covariance.py:43-71 re-pointed at the CUDA plug-ins: analytic dK/dtheta against central differences of
+    build_covariance at random theta inside the automatic bounds, same data, same error metric and tolerance."""
+    cov = build()
+    rng = np.random.default_rng(2)
+    n = 20
+    x = np.linspace(0, 10, n)
+    y = np.sin(x) + 3.0 + rng.normal(size=n) * 0.1
+    cov.pass_spatial_data(x.reshape(n, 1))
+    cov.estimate_hyperpar_bounds(y)
+    low = np.array([a for a, b in cov.bounds], dtype=float)
+    high = np.array([b for a, b in cov.bounds], dtype=float)
+    rng = np.random.default_rng(7)
+    for _ in range(15):
+        theta = rng.uniform(low=low, high=high, size=cov.n_params)
+        K, dK = cov.covariance_and_gradients(theta)
+        assert np.allclose(K, cov.build_covariance(theta), rtol=1e-12, atol=1e-300)
+        big = np.abs(K) / np.abs(K).max() > 1e-4
+        for i in range(cov.n_params):
+            dt = np.zeros(cov.n_params)
+            dt[i] = theta[i] * 1e-6 if theta[i] != 0 else 1e-6
+            fd = (cov.build_covariance(theta + dt) - cov.build_covariance(theta - dt)) / (2 * dt[i])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                err = np.abs((dK[i] - fd) / K)[big]
+            assert err.max() < 1e-5
+
+
+@pytest.mark.parametrize("with_white", [False, True])
+def test_change_point_regression_end_to_end(with_white):
+    """tests/gp/test_GpRegressor.py:45-58 smoke for the ChangePoint kernels, plus parity with the oracle at the fitted
+    hyper-parameters."""
+    rng = np.random.default_rng(1)
+    n = 60
+    x = np.sort(rng.uniform(0, 2, n))
+    y = np.where(x < 1.0, np.sin(12 * x), 0.3 * np.sin(2 * x)) + rng.normal(0, 0.05, n)
+    kern = gp.ChangePoint(kernels=[gp.SquaredExponential, gp.SquaredExponential])
+    comps = (("CP", 0, (("SE",), ("SE",))),)
+    if with_white:
+        kern = kern + gp.WhiteNoise()
+        comps = comps + ("WHITE",)
+    np.random.seed(3)
+    m = gp.GpRegressor(x, y, y_err=np.full(n, 0.05), kernel=kern, n_starts=3)
+    assert m.hyperpar_labels[1] == ("K1: ChngPnt K0: SqrExp log-amplitude" if with_white else "ChngPnt K0: SqrExp log-amplitude")
+    mu, sig = m(x)
+    assert np.all(np.isfinite(mu)) and np.all(sig >= 0)
+    theta = np.asarray(m.hyperpars, dtype=float)
+    ref = orc.Fit(x, y, comps, "const", theta, np.full(n, 0.05**2))
+    q = np.linspace(0, 2, 101)
+    mu, sig = m(q)
+    mu_o, sig_o = ref.predict(q)
+    assert rel_err(mu, mu_o) < 1e-8 and np.abs(sig - sig_o).max() < 1e-8
+    lml_o, grad_o = orc.marginal_likelihood_gradient(x, y, comps, "const", theta + 0.05, np.full(n, 0.05**2))
+    lml, grad = m.marginal_likelihood_gradient(theta + 0.05)
+    assert abs(lml - lml_o) <= 1e-9 * abs(lml_o) and np.abs(grad - grad_o).max() <= 1e-8 * np.abs(grad_o).max()
+    with pytest.raises(NotImplementedError):
+        m.gradient(q[:3])
