@@ -110,6 +110,9 @@ int gpb_dist_unique_id(char* out128);
 int gpb_dist_init(gpb_ctx* ctx, int rank, int world, const char* id128);
 int gpb_dist_lml(gpb_ctx* ctx, const double* theta, int block, double* lml, int* info, double* seconds_out3);
 int gpb_dist_finalize(gpb_ctx* ctx);
+/* layout of the sweep for one rank (host-only, no GPU): block columns, owned ones, doubles of panel / staging storage */
+int gpb_dist_plan(int64_t n, int block, int world, int rank, int* n_blocks, int* n_owned, int64_t* panel_doubles,
+                  int64_t* staging_doubles, int* owners_or_null);
 
 /* CUDA-event phase timings (milliseconds) of the most recent call on this context:
  * names is a ';'-separated list written into name_buf, ms[i] the matching durations. */

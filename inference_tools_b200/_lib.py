@@ -50,6 +50,7 @@ SIGNATURES = {
     "gpb_dist_init": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_char_p]),
     "gpb_dist_lml": (C.c_int, [_ctx_p, _dp, C.c_int, _dp, _ip, _dp]),
     "gpb_dist_finalize": (C.c_int, [_ctx_p]),
+    "gpb_dist_plan": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _ip]),
     "gpb_timers": (C.c_int, [_ctx_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
     "gpb_dev_alloc": (C.c_int, [_ctx_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "gpb_dev_free": (C.c_int, [_ctx_p, C.c_void_p]),
@@ -319,3 +320,16 @@ def nccl_unique_id() -> bytes:
     if lib.gpb_dist_unique_id(buf) != 0:
         raise EngineError(lib.gpb_last_error().decode())
     return buf.raw
+
+
+def dist_plan(n: int, block: int, world: int, rank: int) -> dict:
+    """Block-column-cyclic layout of the distributed Cholesky for one rank (host-only; no GPU needed)."""
+    lib = load_library()
+    nb, no = C.c_int(0), C.c_int(0)
+    pd, sd = C.c_int64(0), C.c_int64(0)
+    npad = (n + 127) // 128 * 128
+    owners = (C.c_int * ((npad + block - 1) // block + 1))()
+    if lib.gpb_dist_plan(n, block, world, rank, C.byref(nb), C.byref(no), C.byref(pd), C.byref(sd), owners) != 0:
+        raise EngineError(lib.gpb_last_error().decode())
+    return {"n_blocks": nb.value, "n_owned": no.value, "panel_doubles": pd.value, "staging_doubles": sd.value,
+            "owners": list(owners[: nb.value])}

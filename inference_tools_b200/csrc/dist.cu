@@ -182,6 +182,33 @@ int gpb_dist_init(gpb_ctx* c, int rank, int world, const char* id128) {
     return 0;
 }
 
+// Host-only description of the block-column-cyclic layout used by gpb_dist_lml (no GPU needed): for `rank` of `world`,
+// the number of owned block columns, the doubles of panel storage and of broadcast staging, and (optionally) the owner
+// of every block column.  Tests use it to check that the ranks tile the matrix exactly once.
+int gpb_dist_plan(int64_t n, int block, int world, int rank, int* n_blocks, int* n_owned, int64_t* panel_doubles,
+                  int64_t* staging_doubles, int* owners_or_null) {
+    if (n <= 0 || block < NB || block % NB || world < 1 || rank < 0 || rank >= world) {
+        set_error("gpb_dist_plan: bad arguments");
+        return -2;
+    }
+    const int64_t npad = round_up(n, NB), rows_aug = npad + NB;
+    const int nblk = (int)((npad + block - 1) / block);
+    int owned = 0;
+    int64_t total = 0;
+    for (int j = 0; j < nblk; ++j) {
+        if (owners_or_null) owners_or_null[j] = j % world;
+        if (j % world == rank) {
+            ++owned;
+            total += (rows_aug - (int64_t)j * block) * block;
+        }
+    }
+    *n_blocks = nblk;
+    *n_owned = owned;
+    *panel_doubles = total;
+    *staging_doubles = 2 * rows_aug * block;
+    return 0;
+}
+
 int gpb_dist_finalize(gpb_ctx* c) {
     GPB_TRY(ctx_use(c));
     dist_destroy(c);

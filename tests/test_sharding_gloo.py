@@ -25,6 +25,27 @@ def test_shard_range_properties():
         shard_range(10, 2, 2)
 
 
+def test_block_cyclic_plan_tiles_the_matrix_once():
+    """host side of the distributed Cholesky (dist.cu): every block column has exactly one owner, owners are cyclic,
+    and the per-rank panel storage adds up to the (augmented) lower block triangle."""
+    from inference_tools_b200 import _lib
+    for n, block, world in ((131072, 1024, 8), (5000, 256, 3), (700, 128, 2), (128, 128, 4)):
+        plans = [_lib.dist_plan(n, block, world, r) for r in range(world)]
+        nblk = plans[0]["n_blocks"]
+        npad = (n + 127) // 128 * 128
+        assert nblk == -(-npad // block)
+        assert all(p["owners"] == [j % world for j in range(nblk)] for p in plans)
+        assert sum(p["n_owned"] for p in plans) == nblk
+        assert max(p["n_owned"] for p in plans) - min(p["n_owned"] for p in plans) <= 1
+        expect = sum((npad + 128 - j * block) * block for j in range(nblk))
+        assert sum(p["panel_doubles"] for p in plans) == expect
+        assert all(p["staging_doubles"] == 2 * (npad + 128) * block for p in plans)
+    big = _lib.dist_plan(131072, 1024, 8, 0)
+    assert (big["panel_doubles"] + big["staging_doubles"]) * 8 < 12e9          # fits one B200 many times over
+    with pytest.raises(_lib.EngineError):
+        _lib.dist_plan(100, 100, 2, 0)
+
+
 def _worker(rank, world, port, m, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
