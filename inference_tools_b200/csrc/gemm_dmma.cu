@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) dgemm_kernel(const Ge
 
 }  // namespace
 
+int gemm_nt_tma(const GemmArgs& a, cudaStream_t s, double* flops_out);  // gemm_tma.cu
+
 static int64_t g_gemm_launches = 0;
 static double g_gemm_flops = 0.0;
 
@@ -298,6 +300,18 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     const int pick = force ? force : (big_tiles < 296 ? 2 : 3);
     if (pick == 2) return launch_cfg<Cfg<4, 2, 2, 2>>(a, s);
     if (pick == 6) return launch_cfg<Cfg<8, 4, 2, 2>>(a, s);  // previous default: 3 stages, 2 CTAs/SM (34.7 TF/s)
+    static const int use_tma = getenv("GPB200_GEMM_TMA") ? atoi(getenv("GPB200_GEMM_TMA")) : 1;
+    if (use_tma && pick == 3) {  // TMA-staged variant (gemm_tma.cu) for k-major operands
+        double fl = 0.0;
+        const int rc = gemm_nt_tma(a, s, &fl);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            ++g_gemm_launches;
+            count_launch();
+            g_gemm_flops += fl;
+            return 0;
+        }
+    }
     return launch_cfg<Cfg<8, 4, 2, 2, 16, 2, 3>>(a, s);
 }
 

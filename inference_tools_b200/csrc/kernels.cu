@@ -16,13 +16,14 @@ constexpr int TILE = 128;
 
 // sum over the smooth components of w_c a^2 f(z_c), z_c = sum_k 0.5 d2_k / l_ck^2; gi/gj = region weights of the two
 // points (ignored unless the model has a ChangePoint)
+template <bool CP = true>
 __device__ __forceinline__ double cov_from_d2(const CovParams& cp, const double (&d2)[MAX_DIM],
                                               const double (&gi)[MAX_REG], const double (&gj)[MAX_REG]) {
     double kv = 0.0;
     for (int c = 0; c < cp.ncomp; ++c) {
         const int kind = cp.kind[c];
         if (kind > COV_RQ) continue;
-        const double w = cp.n_regions ? leaf_weight(cp, c, gi, gj) : 1.0;
+        const double w = (CP && cp.n_regions) ? leaf_weight(cp, c, gi, gj) : 1.0;
         double z = 0.0;
 #pragma unroll
         for (int k = 0; k < MAX_DIM; ++k)
@@ -41,12 +42,13 @@ __device__ __forceinline__ double cov_from_d2(const CovParams& cp, const double 
 
 // diagonal additions of the data covariance: a^2 * 1e-12 per smooth component (covariance.py:254-255,
 // 348), sigma^2 (White :168-169), exp(2 theta_i) (Hetero :679-680), y_err^2 (regression.py:320)
+template <bool CP = true>
 __device__ __forceinline__ double diag_terms(const CovParams& cp, int gi, const double* noise_var,
                                              const double (&g)[MAX_REG]) {
     double v = 0.0;
     for (int c = 0; c < cp.ncomp; ++c) {
         const int kind = cp.kind[c];
-        const double w = cp.n_regions ? leaf_weight(cp, c, g, g) : 1.0;
+        const double w = (CP && cp.n_regions) ? leaf_weight(cp, c, g, g) : 1.0;
         if (kind <= COV_RQ) v += w * cp.amp2[c] * cp.jitter;
         else if (kind == COV_WHITE) v += w * cp.amp2[c];
         else v += w * exp(2.0 * cp.hetero_log_sigma[gi]);
@@ -63,12 +65,13 @@ __device__ __forceinline__ void lower_tile(int t, int& bi, int& bj) {
     bj = t - r * (r + 1) / 2;
 }
 
+template <bool CP>
 __global__ void __launch_bounds__(256) assemble_train_kernel(const CovParams cp, const double* __restrict__ x, int n,
                                                              const double* __restrict__ noise_var,
                                                              const double* __restrict__ y_cov, double* __restrict__ K,
                                                              int64_t ld, int mirror) {
     __shared__ double xs[TILE * MAX_DIM];
-    __shared__ double gs[TILE][MAX_REG];
+    __shared__ double gs[CP ? TILE : 1][MAX_REG];
     int bi, bj;
     lower_tile(blockIdx.x, bi, bj);
     const int row0 = bi * TILE, col0 = bj * TILE;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(256) assemble_train_kernel(const CovParams cp,
     double xj[MAX_DIM], wj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d) ? x[(int64_t)gj * d + k] : 0.0;
-    if (cp.n_regions) {
+    if (CP && cp.n_regions) {
         region_weights(cp, x[(int64_t)gj * d + cp.cp_axis], wj);
         if (tid < TILE) {
             double g[MAX_REG];
@@ -99,9 +102,9 @@ __global__ void __launch_bounds__(256) assemble_train_kernel(const CovParams cp,
             d2[k] = df * df;
         }
 #pragma unroll
-        for (int q = 0; q < MAX_REG; ++q) wi[q] = cp.n_regions ? gs[i][q] : 0.0;
-        double v = cov_from_d2(cp, d2, wi, wj);
-        if (gi == gj) v += diag_terms(cp, gi, noise_var, wi);
+        for (int q = 0; q < MAX_REG; ++q) wi[q] = (CP && cp.n_regions) ? gs[CP ? i : 0][q] : 0.0;
+        double v = cov_from_d2<CP>(cp, d2, wi, wj);
+        if (gi == gj) v += diag_terms<CP>(cp, gi, noise_var, wi);
         if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
         else if (y_cov) v += y_cov[(int64_t)gi * n + gj];
         K[(int64_t)gi * ld + gj] = v;
@@ -111,11 +114,12 @@ __global__ void __launch_bounds__(256) assemble_train_kernel(const CovParams cp,
 
 // Rectangular block rows [row0, ..) x cols [col0, ..) of K(theta)+diag terms into a panel buffer
 // (distributed Cholesky: every rank assembles only the block columns it owns).  grid = (ncols/128, nrows/128)
+template <bool CP>
 __global__ void __launch_bounds__(256) assemble_block_kernel(const CovParams cp, const double* __restrict__ x, int n,
                                                              const double* __restrict__ noise_var, int row0, int col0,
                                                              double* __restrict__ out, int64_t ld) {
     __shared__ double xs[TILE * MAX_DIM];
-    __shared__ double gs[TILE][MAX_REG];
+    __shared__ double gs[CP ? TILE : 1][MAX_REG];
     const int r0 = row0 + blockIdx.y * TILE, c0 = col0 + blockIdx.x * TILE;
     const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
     const int d = cp.d;
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(256) assemble_block_kernel(const CovParams cp,
     double xj[MAX_DIM], wj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d) ? x[(int64_t)gj * d + k] : 0.0;
-    if (cp.n_regions) {
+    if (CP && cp.n_regions) {
         region_weights(cp, x[(int64_t)gj * d + cp.cp_axis], wj);
         if (tid < TILE) {
             double g[MAX_REG];
@@ -144,9 +148,9 @@ __global__ void __launch_bounds__(256) assemble_block_kernel(const CovParams cp,
             d2[k] = df * df;
         }
 #pragma unroll
-        for (int q = 0; q < MAX_REG; ++q) wi[q] = cp.n_regions ? gs[i][q] : 0.0;
-        double v = cov_from_d2(cp, d2, wi, wj);
-        if (gi == gj) v += diag_terms(cp, gi, noise_var, wi);
+        for (int q = 0; q < MAX_REG; ++q) wi[q] = (CP && cp.n_regions) ? gs[CP ? i : 0][q] : 0.0;
+        double v = cov_from_d2<CP>(cp, d2, wi, wj);
+        if (gi == gj) v += diag_terms<CP>(cp, gi, noise_var, wi);
         if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
         out[(int64_t)(gi - row0) * ld + (gj - col0)] = v;
     }
@@ -252,11 +256,12 @@ __global__ void cross_cov_kernel(const CovParams cp, const double* __restrict__ 
 }
 
 // Stacked cross-covariance rows of one query chunk.  grid = (npad/128, ceil(mq/128)).
+template <bool CP>
 __global__ void __launch_bounds__(256) cross_stack_kernel(const CovParams cp, const double* __restrict__ q, int mq,
                                                           int nstack, const double* __restrict__ x, int n,
                                                           double* __restrict__ S, int64_t ld) {
     __shared__ double qs[TILE * MAX_DIM];
-    __shared__ double gs[TILE][MAX_REG];
+    __shared__ double gs[CP ? TILE : 1][MAX_REG];
     const int col0 = blockIdx.x * TILE, q0 = blockIdx.y * TILE;
     const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
     const int d = cp.d;
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(256) cross_stack_kernel(const CovParams cp, co
     double xj[MAX_DIM], wj[MAX_REG] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < MAX_DIM; ++k) xj[k] = (k < d && gj < n) ? x[(int64_t)gj * d + k] : 0.0;
-    if (cp.n_regions) {
+    if (CP && cp.n_regions) {
         if (gj < n) region_weights(cp, x[(int64_t)gj * d + cp.cp_axis], wj);
         if (tid < nq) {
             double g[MAX_REG];
@@ -287,8 +292,8 @@ __global__ void __launch_bounds__(256) cross_stack_kernel(const CovParams cp, co
         }
         double wi[MAX_REG];
 #pragma unroll
-        for (int r2 = 0; r2 < MAX_REG; ++r2) wi[r2] = cp.n_regions ? gs[i][r2] : 0.0;
-        const double kv = (gj < n) ? cov_from_d2(cp, d2, wi, wj) : 0.0;
+        for (int r2 = 0; r2 < MAX_REG; ++r2) wi[r2] = (CP && cp.n_regions) ? gs[CP ? i : 0][r2] : 0.0;
+        const double kv = (gj < n) ? cov_from_d2<CP>(cp, d2, wi, wj) : 0.0;
         double* dst = S + (int64_t)(q0 + i) * nstack * ld + gj;
         dst[0] = kv;
         if (nstack > 1) {
@@ -522,14 +527,16 @@ __global__ void copy2d_kernel(const double* __restrict__ src, int64_t lds, doubl
 int launch_assemble_train(const CovParams& cp, const double* x, int n, int npad, const double* noise_var,
                           const double* y_cov, double* K, int64_t ld, int mirror, cudaStream_t s) {
     const int nb = npad / TILE;
-    assemble_train_kernel<<<nb * (nb + 1) / 2, 256, 0, s>>>(cp, x, n, noise_var, y_cov, K, ld, mirror);
+    if (cp.n_regions) assemble_train_kernel<true><<<nb * (nb + 1) / 2, 256, 0, s>>>(cp, x, n, noise_var, y_cov, K, ld, mirror);
+    else assemble_train_kernel<false><<<nb * (nb + 1) / 2, 256, 0, s>>>(cp, x, n, noise_var, y_cov, K, ld, mirror);
     GPB_LAUNCH_CHECK();
 }
 
 int launch_assemble_block(const CovParams& cp, const double* x, int n, const double* noise_var, int row0, int nrows,
                           int col0, int ncols, double* out, int64_t ld, cudaStream_t s) {
     dim3 grid(ncols / TILE, nrows / TILE);
-    assemble_block_kernel<<<grid, 256, 0, s>>>(cp, x, n, noise_var, row0, col0, out, ld);
+    if (cp.n_regions) assemble_block_kernel<true><<<grid, 256, 0, s>>>(cp, x, n, noise_var, row0, col0, out, ld);
+    else assemble_block_kernel<false><<<grid, 256, 0, s>>>(cp, x, n, noise_var, row0, col0, out, ld);
     GPB_LAUNCH_CHECK();
 }
 
@@ -550,7 +557,8 @@ int launch_cross_cov(const CovParams& cp, const double* u, int m, const double* 
 int launch_cross_stack(const CovParams& cp, const double* q, int mq, int nstack, const double* x, int n, int npad,
                        double* S, int64_t ld, cudaStream_t s) {
     dim3 grid(npad / TILE, (mq + TILE - 1) / TILE);
-    cross_stack_kernel<<<grid, 256, 0, s>>>(cp, q, mq, nstack, x, n, S, ld);
+    if (cp.n_regions) cross_stack_kernel<true><<<grid, 256, 0, s>>>(cp, q, mq, nstack, x, n, S, ld);
+    else cross_stack_kernel<false><<<grid, 256, 0, s>>>(cp, q, mq, nstack, x, n, S, ld);
     GPB_LAUNCH_CHECK();
 }
 
