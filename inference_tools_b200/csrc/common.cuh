@@ -64,7 +64,6 @@ struct GemmArgs {
     int flags;
 };
 int gemm_nt(const GemmArgs& a, cudaStream_t s);
-int64_t gemm_launch_count();   // number of GEMM kernel launches so far (bench "gpu_launches")
 void count_launch(int n = 1);  // every other kernel launch is counted through this
 int64_t launch_count();
 

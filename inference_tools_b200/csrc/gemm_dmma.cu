@@ -230,7 +230,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) dgemm_kernel(const Ge
 
 int gemm_nt_tma(const GemmArgs& a, cudaStream_t s, double* flops_out);  // gemm_tma.cu
 
-static int64_t g_gemm_launches = 0;
 static double g_gemm_flops = 0.0;
 
 template <class C>
@@ -255,7 +254,6 @@ int launch_cfg(const GemmArgs& a, cudaStream_t s) {
     const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) : (int64_t)tm * tn;
     kern<<<(unsigned)tiles, THREADS, C::SMEM_BYTES, s>>>(a, tn);
     GPB_CUDA(cudaGetLastError());
-    ++g_gemm_launches;
     count_launch();
     // algorithmic flops of this launch (2 * BM * BN * k-extent per computed tile)
     if (!(a.flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) {
@@ -306,7 +304,6 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
         const int rc = gemm_nt_tma(a, s, &fl);
         if (rc < 0) return rc;
         if (rc == 0) {
-            ++g_gemm_launches;
             count_launch();
             g_gemm_flops += fl;
             return 0;
@@ -315,7 +312,6 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     return launch_cfg<Cfg<8, 4, 2, 2, 16, 2, 3>>(a, s);
 }
 
-int64_t gemm_launch_count() { return g_gemm_launches; }
 double gemm_flops_issued() { return g_gemm_flops; }
 void credit_gemm_flops(double f) { g_gemm_flops += f; }
 

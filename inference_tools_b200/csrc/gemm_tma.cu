@@ -14,7 +14,6 @@
 #include <cstdlib>
 
 namespace gpb {
-void credit_gemm_flops(double f);
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, THREADS = 128;

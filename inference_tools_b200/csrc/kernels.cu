@@ -494,21 +494,6 @@ __global__ void residual_kernel(const MeanParams mp, const double* __restrict__ 
     }
 }
 
-__global__ void transpose_block_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst,
-                                       int64_t ldd, int rows, int cols, double scale) {
-    __shared__ double tile[32][33];
-    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int sr = by + r, sc = bx + threadIdx.x;
-        if (sr < rows && sc < cols) tile[r][threadIdx.x] = src[(int64_t)sr * lds + sc];
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int dr = bx + r, dc = by + threadIdx.x;  // dst is cols x rows
-        if (dr < cols && dc < rows) dst[(int64_t)dr * ldd + dc] = scale * tile[threadIdx.x][r];
-    }
-}
-
 __global__ void copy2d_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int64_t ldd,
                               int rows, int cols2) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,13 +603,6 @@ int launch_ei(const double* mu, const double* sig, const double* dmu, const doub
 int launch_residual(const MeanParams& mp, const double* x, const double* y, int n, int npad, double* resid,
                     double* mu_out, cudaStream_t s) {
     residual_kernel<<<(npad + 255) / 256, 256, 0, s>>>(mp, x, y, n, npad, resid, mu_out);
-    GPB_LAUNCH_CHECK();
-}
-
-int launch_transpose_block(const double* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, double scale,
-                           cudaStream_t s) {
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    transpose_block_kernel<<<grid, block, 0, s>>>(src, lds, dst, ldd, rows, cols, scale);
     GPB_LAUNCH_CHECK();
 }
 

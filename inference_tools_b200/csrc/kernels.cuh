@@ -45,8 +45,6 @@ int launch_ei(const double* mu, const double* sig, const double* dmu, const doub
 int launch_residual(const MeanParams& mp, const double* x, const double* y, int n, int npad, double* resid,
                     double* mu_out, cudaStream_t s);
 // small utility kernels
-int launch_transpose_block(const double* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, double scale,
-                           cudaStream_t s);
 int launch_copy2d(const double* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, cudaStream_t s);
 
 // ---- potrf.cu : blocked recursive Cholesky / triangular inverse / triangular solve drivers
