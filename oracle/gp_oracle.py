@@ -581,3 +581,62 @@ def mean_bounds(mean, x, y):
     if mean == "quadratic":
         out.extend([(-b, b) for b in gb])
     return out
+
+
+# ----------------------------------------------------------------------------- GpLinearInverter (inversion.py)
+class LinearInverter:
+    """Restatement of inference/gp/inversion.py: posterior of y = A x + noise with a GP prior on x.
+
+    comps / mean / theta as above; x_pos = parameter_spatial_positions (n x d); A = model_matrix (m x n)."""
+
+    def __init__(self, y, y_err, A, x_pos, comps, mean):
+        self.y, self.y_err = np.asarray(y, dtype=float), np.asarray(y_err, dtype=float)
+        self.A = np.asarray(A, dtype=float)
+        self.x = np.asarray(x_pos, dtype=float)
+        self.comps, self.mean = tuple(comps), mean
+        self.n, self.d = self.x.shape
+        self.xbar = self.x.mean(axis=0)
+        self.sigma = np.diag(self.y_err**2)            # inversion.py:134
+        self.inv_sigma = np.diag(self.y_err**-2.0)     # :135
+
+    def _prior(self, theta):
+        tm, parts = split_theta(theta, self.comps, self.mean, self.n, self.d)
+        K = train_cov(self.comps, parts, self.x)       # cov.build_covariance(theta) -- no data-error term (:149)
+        return K, mean_vec(self.mean, tm, self.x, self.xbar), tm, parts
+
+    def calculate_posterior(self, theta):
+        """inversion.py:138-155"""
+        K, mu, _, _ = self._prior(theta)
+        W = self.A.T @ self.inv_sigma @ self.A
+        u = self.A.T @ (self.inv_sigma @ (self.y - self.A @ mu))
+        from scipy.linalg import solve
+        cov = solve(np.eye(self.n) + K @ W, K)
+        return cov @ u + mu, cov
+
+    def marginal_likelihood(self, theta):
+        """inversion.py:174-188"""
+        K, mu, _, _ = self._prior(theta)
+        L = cholesky(self.A @ K @ self.A.T + self.sigma)
+        v = solve_triangular(L, self.y - self.A @ mu, lower=True)
+        return -0.5 * (v @ v) - np.log(np.diagonal(L)).sum()
+
+    def marginal_likelihood_gradient(self, theta):
+        """inversion.py:190-217"""
+        tm, parts = split_theta(theta, self.comps, self.mean, self.n, self.d)
+        K, grad_K = cov_and_grads(self.comps, parts, self.x)
+        J = self.A @ K @ self.A.T + self.sigma
+        grad_J = [self.A @ dK @ self.A.T for dK in grad_K]
+        mu = mean_vec(self.mean, tm, self.x, self.xbar)
+        grad_f = [self.A @ du for du in mean_grads(self.mean, self.x, self.xbar)]
+        f = self.A @ mu
+        L = cholesky(J)
+        iJ = solve_triangular(L, np.eye(L.shape[0]), lower=True)
+        iJ = iJ.T @ iJ
+        alpha = iJ @ (self.y - f)
+        lml = -0.5 * ((self.y - f) @ alpha) - np.log(np.diagonal(L)).sum()
+        grad = np.zeros(len(theta))
+        pm = len(tm)
+        grad[:pm] = [(alpha * df).sum() for df in grad_f]
+        Q = alpha[:, None] * alpha[None, :] - iJ
+        grad[pm:] = [0.5 * (Q * dJ.T).sum() for dJ in grad_J]
+        return lml, grad

@@ -191,6 +191,49 @@ def demo_case(gp):
     print(f"cfg1_demo: lml={lml:.6f}")
 
 
+def inverter_data():
+    """tests/gp/test_GpLinearInverter.py:41-64: gaussian-blur forward model of a sum of Lorentzians"""
+    from scipy.special import erfc
+
+    def normal_cdf(x, mu=0.0, sigma=1.0):
+        return 0.5 * erfc(-(x - mu) / (np.sqrt(2) * sigma))
+
+    def lorentzian(x, A, w, c):
+        return A / (1 + ((x - c) / w) ** 2)
+
+    n_data, n_basis = 32, 64
+    x = np.linspace(-1, 1, n_basis)
+    data_axis = np.linspace(-1, 1, n_data)
+    dx = 0.5 * (x[1] - x[0])
+    solution = lorentzian(x, 1.0, 0.1, 0.0) + lorentzian(x, 0.8, 0.15, 0.3) + lorentzian(x, 0.3, 0.1, -0.45)
+    A = np.zeros([n_data, n_basis])
+    for k in range(n_basis):
+        A[:, k] = normal_cdf(data_axis + dx, mu=x[k], sigma=0.075) - normal_cdf(data_axis - dx, mu=x[k], sigma=0.075)
+    rng = np.random.default_rng(123)
+    y = A @ solution + rng.normal(size=n_data, scale=0.02)
+    return x.reshape(-1, 1), y, np.zeros(n_data) + 0.02, A
+
+
+def inverter_case(gp, name, comps, mean, seed):
+    x, y, y_err, A = inverter_data()
+    inv = gp.GpLinearInverter(model_matrix=A, y=y, y_err=y_err, parameter_spatial_positions=x,
+                              prior_covariance_function=make_kernel(gp, comps), prior_mean_function=getattr(gp, MEANS[mean])())
+    rng = np.random.default_rng(seed)
+    thetas = rng.uniform(0.1, 1.0, size=(4, inv.n_hyperpars))
+    out = dict(x=x, y=y, y_err=y_err, A=A, comps=np.array(comps), mean=np.array(mean), thetas=thetas,
+               labels=np.array(inv.hyperpar_labels))
+    out["lml"] = np.array([inv.marginal_likelihood(t) for t in thetas])
+    lg = [inv.marginal_likelihood_gradient(t) for t in thetas]
+    out["lml_from_grad"] = np.array([v[0] for v in lg])
+    out["lml_grad"] = np.array([v[1] for v in lg])
+    post = [inv.calculate_posterior(t) for t in thetas]
+    out["post_mean"] = np.array([p[0] for p in post])
+    out["post_cov"] = np.array([p[1] for p in post])
+    out["post_mean_alt"] = np.array([inv.calculate_posterior_mean(t) for t in thetas])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: lml={out['lml']}")
+
+
 def main():
     warnings.simplefilter("ignore")
     gp = load_reference()
@@ -215,6 +258,11 @@ def main():
     case(gp, "cp_serq_white_d2_n36_linear", 42, 36, 2, (("CP", 1, (("SE",), ("RQ",))), "WHITE"), "linear", store_k=True)
     case(gp, "cp_sesese_d1_n48_const", 43, 48, 1, (("CP", 0, (("SE",), ("SE",), ("SE",))),), "const", store_k=True)
     case(gp, "cp_sese_d3_n300_const", 44, 300, 3, (("CP", 2, (("SE",), ("SE",))),), "const")
+    # GpLinearInverter (inversion.py)
+    inverter_case(gp, "linv_se_const", ("SE",), "const", 51)
+    inverter_case(gp, "linv_rq_linear", ("RQ",), "linear", 52)
+    inverter_case(gp, "linv_white_const", ("WHITE",), "const", 53)
+    inverter_case(gp, "linv_rqse_const", ("RQ", "SE"), "const", 54)
     # multistart fits
     fit_case(gp, "fit_se_d1_n60", 31, 60, 1, ("SE",), "const")
     fit_case(gp, "fit_rqwhite_d2_n80", 32, 80, 2, ("RQ", "WHITE"), "const")

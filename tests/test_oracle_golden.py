@@ -107,3 +107,22 @@ def test_ei_fixtures_cover_both_branches():
             lo += int((g["ei_Z"] < -3).sum())
             hi += int((g["ei_Z"] >= -3).sum())
     assert lo > 50 and hi > 50
+
+
+LINV = ["linv_se_const", "linv_rq_linear", "linv_white_const", "linv_rqse_const"]
+
+
+@pytest.mark.parametrize("name", LINV)
+def test_linear_inverter_matches_reference(name):
+    import os
+    from conftest import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    comps = tuple(str(c) for c in g["comps"])
+    inv = orc.LinearInverter(g["y"], g["y_err"], g["A"], g["x"], comps, str(g["mean"]))
+    for i, th in enumerate(g["thetas"]):
+        assert abs(inv.marginal_likelihood(th) - g["lml"][i]) <= 1e-10 * abs(g["lml"][i])
+        lml, grad = inv.marginal_likelihood_gradient(th)
+        assert abs(lml - g["lml_from_grad"][i]) <= 1e-10 * abs(g["lml_from_grad"][i])
+        assert np.abs(grad - g["lml_grad"][i]).max() <= 1e-9 * np.abs(g["lml_grad"][i]).max()
+        mu, cov = inv.calculate_posterior(th)
+        assert rel_err(mu, g["post_mean"][i]) < 1e-9 and rel_err(cov, g["post_cov"][i]) < 1e-9
