@@ -114,6 +114,19 @@ int gpb_dist_finalize(gpb_ctx* ctx);
 int gpb_dist_plan(int64_t n, int block, int world, int rank, int* n_blocks, int* n_owned, int64_t* panel_doubles,
                   int64_t* staging_doubles, int* owners_or_null);
 
+/* GpLinearInverter (reference inference/gp/inversion.py:11-249): posterior of y = A x + noise with a GP prior on x.
+ * The context's training inputs are the parameter_spatial_positions (gpb_set_data with y = zeros, no noise) and its
+ * model the prior covariance/mean (gpb_set_model*); theta = [mean, cov] as in inversion.py:126-133.
+ *   gpb_linv_set_problem   inversion.py:85-118 (A is m x n row-major, y and y_err length m)
+ *   gpb_linv_lml           inversion.py:170-187  marginal_likelihood
+ *   gpb_linv_lml_grad      inversion.py:189-217  marginal_likelihood_gradient
+ *   gpb_linv_posterior     inversion.py:138-168  calculate_posterior / calculate_posterior_mean (cov may be NULL)
+ * info = 0, or the 1-based index of the first non-positive pivot of chol(A K A^T + Sigma). */
+int gpb_linv_set_problem(gpb_ctx* ctx, const double* A, int64_t m, const double* y, const double* y_err);
+int gpb_linv_lml(gpb_ctx* ctx, const double* theta, double* lml, int* info);
+int gpb_linv_lml_grad(gpb_ctx* ctx, const double* theta, double* lml, double* grad, int* info);
+int gpb_linv_posterior(gpb_ctx* ctx, const double* theta, double* mean, double* cov_or_null, int* info);
+
 /* CUDA-event phase timings (milliseconds) of the most recent call on this context:
  * names is a ';'-separated list written into name_buf, ms[i] the matching durations. */
 int gpb_timers(gpb_ctx* ctx, char* name_buf, int name_buf_len, double* ms, int max_entries, int* n_entries);

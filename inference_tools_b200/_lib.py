@@ -51,6 +51,10 @@ SIGNATURES = {
     "gpb_dist_lml": (C.c_int, [_ctx_p, _dp, C.c_int, _dp, _ip, _dp]),
     "gpb_dist_finalize": (C.c_int, [_ctx_p]),
     "gpb_dist_plan": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _ip]),
+    "gpb_linv_set_problem": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
+    "gpb_linv_lml": (C.c_int, [_ctx_p, _dp, _dp, _ip]),
+    "gpb_linv_lml_grad": (C.c_int, [_ctx_p, _dp, _dp, _dp, _ip]),
+    "gpb_linv_posterior": (C.c_int, [_ctx_p, _dp, _dp, _dp, _ip]),
     "gpb_timers": (C.c_int, [_ctx_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
     "gpb_dev_alloc": (C.c_int, [_ctx_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "gpb_dev_free": (C.c_int, [_ctx_p, C.c_void_p]),
@@ -289,6 +293,35 @@ class Engine:
 
     def dist_finalize(self):
         self._check(self.lib.gpb_dist_finalize(self._ctx))
+
+    # ---------------------------------------------------------------- linear inversion (inversion.py)
+    def linv_set_problem(self, A, y, y_err):
+        A, y, y_err = _f64(A), _f64(y), _f64(y_err)
+        if A.ndim != 2 or A.shape[1] != self.n or y.shape != (A.shape[0],) or y_err.shape != y.shape:
+            raise ValueError("linv_set_problem: A must be (m, n) with n the number of positions; y, y_err length m")
+        self.linv_m = A.shape[0]
+        self._check(self.lib.gpb_linv_set_problem(self._ctx, _ptr(A), A.shape[0], _ptr(y), _ptr(y_err)))
+
+    def linv_lml(self, theta):
+        th = _f64(theta)
+        val, info = C.c_double(0), C.c_int(0)
+        self._check(self.lib.gpb_linv_lml(self._ctx, _ptr(th), C.byref(val), C.byref(info)))
+        return val.value, info.value
+
+    def linv_lml_grad(self, theta):
+        th = _f64(theta)
+        val, info = C.c_double(0), C.c_int(0)
+        grad = np.empty(self.n_mean + self.n_cov)
+        self._check(self.lib.gpb_linv_lml_grad(self._ctx, _ptr(th), C.byref(val), _ptr(grad), C.byref(info)))
+        return val.value, grad, info.value
+
+    def linv_posterior(self, theta, want_cov=True):
+        th = _f64(theta)
+        info = C.c_int(0)
+        mean = np.empty(self.n)
+        cov = np.empty((self.n, self.n)) if want_cov else None
+        self._check(self.lib.gpb_linv_posterior(self._ctx, _ptr(th), _ptr(mean), _ptr(cov), C.byref(info)))
+        return mean, cov, info.value
 
     def timers(self):
         names = C.create_string_buffer(1024)

@@ -262,6 +262,7 @@ void gpb_ctx_destroy(gpb_ctx* c) {
     for (double* p : ptrs)
         if (p) cudaFree(p);
     dist_destroy(c);
+    linv_destroy(c);
     clear_graphs(c);
     if (c->info_dev) cudaFree(c->info_dev);
     c->timer.reset();
@@ -281,6 +282,7 @@ int gpb_set_data(gpb_ctx* c, const double* x, int64_t n, int d, const double* y,
         *p = nullptr;
     }
     clear_graphs(c);
+    linv_destroy(c);  // A is padded to this context's npad
     c->n = n;
     c->d = d;
     c->npad = round_up(n, NB);

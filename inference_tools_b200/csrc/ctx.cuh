@@ -1,4 +1,4 @@
-// Context object shared by api.cu and dist.cu.
+// Context object shared by api.cu, dist.cu and inverter.cu.
 #pragma once
 #include "../../include/gpb200.h"
 #include "kernels.cuh"
@@ -49,6 +49,7 @@ int ensure(T*& p, size_t& cap, size_t bytes) {
 }  // namespace gpb
 
 struct gpb_dist;  // dist.cu
+struct gpb_linv;  // inverter.cu
 using gpb::MAX_COMP;
 using gpb::MAX_DIM;
 
@@ -94,6 +95,7 @@ struct gpb_ctx {
     std::map<std::string, GraphEntry> graphs;
     bool use_graphs = true;
     gpb_dist* dist = nullptr;
+    gpb_linv* linv = nullptr;
 };
 
 
@@ -104,4 +106,5 @@ int ctx_need_model(gpb_ctx* c);
 int ctx_make_cov_params(gpb_ctx* c, const double* theta_cov, CovParams& cp);
 void ctx_make_mean_params(gpb_ctx* c, const double* theta_mean, MeanParams& mp);
 void dist_destroy(gpb_ctx* c);  // dist.cu
+void linv_destroy(gpb_ctx* c);  // inverter.cu
 }  // namespace gpb

@@ -1,6 +1,7 @@
 """Drop-in for ``inference.gp`` on the GpRegressor hot path (reference inference/gp/__init__.py)."""
 from inference_tools_b200.gp.regression import GpRegressor
 from inference_tools_b200.gp.optimisation import GpOptimiser
+from inference_tools_b200.gp.inversion import GpLinearInverter
 from inference_tools_b200.gp.acquisition import ExpectedImprovement, UpperConfidenceBound, MaxVariance
 from inference_tools_b200.gp.mean import ConstantMean, LinearMean, QuadraticMean
 from inference_tools_b200.gp.covariance import (
@@ -14,6 +15,7 @@ from inference_tools_b200.gp.covariance import (
 __all__ = [
     "GpRegressor",
     "GpOptimiser",
+    "GpLinearInverter",
     "ExpectedImprovement",
     "UpperConfidenceBound",
     "MaxVariance",

@@ -2,6 +2,7 @@
 reference-shaped Python API, against (a) the committed fixtures generated from the unmodified reference
 and (b) the numpy oracle on seeded inputs.  Tolerance: 1e-9 relative (BASELINE.json north_star) on mean,
 sigma, LML and its gradient; the gradient is compared norm-relative."""
+import os
 import pickle
 import warnings
 
@@ -9,7 +10,7 @@ import numpy as np
 import pytest
 from numpy.linalg import LinAlgError
 
-from conftest import golden_names, load_golden, make_kernel, make_mean, rel_err, synth
+from conftest import GOLDEN_DIR, golden_names, load_golden, make_kernel, make_mean, rel_err, synth
 import inference_tools_b200.gp as gp
 from inference_tools_b200 import _lib
 from oracle import gp_oracle as orc
@@ -558,3 +559,105 @@ def test_change_point_regression_end_to_end(with_white):
     assert abs(lml - lml_o) <= 1e-9 * abs(lml_o) and np.abs(grad - grad_o).max() <= 1e-8 * np.abs(grad_o).max()
     with pytest.raises(NotImplementedError):
         m.gradient(q[:3])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GpLinearInverter (reference inference/gp/inversion.py; tests/gp/test_GpLinearInverter.py)
+LINV = ["linv_se_const", "linv_rq_linear", "linv_white_const", "linv_rqse_const"]
+
+
+def _inverter(g, **kw):
+    comps = tuple(str(c) for c in g["comps"])
+    return gp.GpLinearInverter(
+        y=g["y"], y_err=g["y_err"], model_matrix=g["A"], parameter_spatial_positions=g["x"],
+        prior_covariance_function=make_kernel(gp, comps), prior_mean_function=make_mean(gp, str(g["mean"])), **kw)
+
+
+@pytest.mark.parametrize("name", LINV)
+def test_linear_inverter_against_reference_fixtures(name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    inv = _inverter(g)
+    assert inv.hyperpar_labels == [str(s) for s in g["labels"]]
+    for i, th in enumerate(g["thetas"]):
+        lml = inv.marginal_likelihood(th)
+        assert abs(lml - g["lml"][i]) <= TOL * abs(g["lml"][i])
+        lml2, grad = inv.marginal_likelihood_gradient(th)
+        assert abs(lml2 - g["lml_from_grad"][i]) <= TOL * abs(g["lml_from_grad"][i])
+        assert np.abs(grad - g["lml_grad"][i]).max() <= 1e-8 * np.abs(g["lml_grad"][i]).max()
+        mu, cov = inv.calculate_posterior(th)
+        assert rel_err(mu, g["post_mean"][i]) < TOL and rel_err(cov, g["post_cov"][i]) < TOL
+        assert rel_err(inv.calculate_posterior_mean(th), g["post_mean_alt"][i]) < TOL
+
+
+@pytest.mark.parametrize("m,n,d,comps,mean", [
+    (200, 300, 2, ("SE",), "const"),
+    (500, 260, 1, ("RQ", "WHITE"), "linear"),
+    (130, 1000, 3, ("SE", "RQ"), "quadratic"),
+])
+def test_linear_inverter_against_oracle(m, n, d, comps, mean):
+    """Sizes that cross the 128-padding in both m and n, m < n and m > n."""
+    rng = np.random.default_rng(m + n)
+    x = rng.uniform(0, 1, (n, d))
+    A = rng.uniform(0, 1, (m, n)) * (rng.uniform(0, 1, (m, n)) < 0.1)
+    A /= A.sum(axis=1, keepdims=True)  # sparse averaging rows: cond(J) ~ 1e5, so 1e-9 on the LML is meaningful
+    truth = np.sin(4 * x).sum(axis=1)
+    y_err = np.full(m, 0.05)
+    y = A @ truth + rng.normal(0, 0.05, m)
+    inv = gp.GpLinearInverter(y, y_err, A, x, make_kernel(gp, comps), make_mean(gp, mean))
+    ref = orc.LinearInverter(y, y_err, A, x, comps, mean)
+    theta = rng.uniform(-0.5, 0.5, inv.n_hyperpars)
+    lml_o, grad_o = ref.marginal_likelihood_gradient(theta)
+    lml, grad = inv.marginal_likelihood_gradient(theta)
+    assert abs(lml - lml_o) <= TOL * abs(lml_o) and abs(inv.marginal_likelihood(theta) - lml_o) <= TOL * abs(lml_o)
+    assert np.abs(grad - grad_o).max() <= 1e-8 * np.abs(grad_o).max()
+    mu_o, cov_o = ref.calculate_posterior(theta)
+    mu, cov = inv.calculate_posterior(theta)
+    assert rel_err(mu, mu_o) < 1e-8 and rel_err(cov, cov_o) < 1e-8
+
+
+@pytest.mark.parametrize("cov_func", ["SE", "RQ", "WHITE", "RQ+SE"])
+def test_linear_inverter_reference_acceptance(cov_func):
+    """tests/gp/test_GpLinearInverter.py:75-130: optimise, chi-square of the forward prediction <= 1.5, posterior-mean
+    shortcut agrees, analytic gradient within 1e-3 of finite differences at 20 random points."""
+    g = np.load(os.path.join(GOLDEN_DIR, "linv_se_const.npz"))  # same data for every kernel
+    kern = {"SE": gp.SquaredExponential(), "RQ": gp.RationalQuadratic(), "WHITE": gp.WhiteNoise(),
+            "RQ+SE": gp.RationalQuadratic() + gp.SquaredExponential()}[cov_func]
+    inv = gp.GpLinearInverter(model_matrix=g["A"], y=g["y"], y_err=g["y_err"], parameter_spatial_positions=g["x"],
+                              prior_covariance_function=kern)
+    theta_opt = inv.optimize_hyperparameters(initial_guess=np.ones(inv.n_hyperpars))
+    mu, cov = inv.calculate_posterior(theta_opt)
+    assert np.allclose(mu, inv.calculate_posterior_mean(theta_opt))
+    assert (((g["y"] - g["A"] @ mu) / g["y_err"]) ** 2).mean() <= 1.5
+    rng = np.random.default_rng(1)
+    for theta in rng.uniform(0.1, 1.0, size=(20, inv.n_hyperpars)):
+        _, grad = inv.marginal_likelihood_gradient(theta)
+        fd = np.zeros_like(theta)
+        for k in range(theta.size):
+            dt = np.zeros_like(theta)
+            dt[k] = 1e-5 * max(abs(theta[k]), 1.0)
+            fd[k] = (inv.marginal_likelihood(theta + dt) - inv.marginal_likelihood(theta - dt)) / (2 * dt[k])
+        assert np.abs(fd / grad - 1.0).max() < 1e-3
+
+
+def test_linear_inverter_argument_checks_and_failures():
+    g = np.load(os.path.join(GOLDEN_DIR, "linv_se_const.npz"))
+    y, y_err, A, x = g["y"], g["y_err"], g["A"], g["x"]
+    with pytest.raises(ValueError):
+        gp.GpLinearInverter(y, y_err, A.ravel(), x)
+    with pytest.raises(ValueError):
+        gp.GpLinearInverter(y, y_err[:-1], A, x)
+    with pytest.raises(ValueError):
+        gp.GpLinearInverter(y[:-1], y_err[:-1], A, x)
+    with pytest.raises(ValueError):
+        gp.GpLinearInverter(y, y_err, A, x.ravel())
+    with pytest.raises(ValueError):
+        gp.GpLinearInverter(y, y_err, A, x[:-1])
+    inv = gp.GpLinearInverter(y, y_err, A, x)
+    with pytest.raises(ValueError):
+        inv.optimize_hyperparameters(np.ones(inv.n_hyperpars + 1))
+    bad = gp.GpLinearInverter(y, np.zeros_like(y_err), np.zeros_like(A), x)  # J = 0: not positive definite
+    with pytest.raises(LinAlgError):
+        bad.marginal_likelihood(np.ones(bad.n_hyperpars))
+    clone = pickle.loads(pickle.dumps(inv))
+    th = np.full(inv.n_hyperpars, 0.3)
+    assert clone.marginal_likelihood(th) == inv.marginal_likelihood(th)
