@@ -266,6 +266,7 @@ void gpb_ctx_destroy(gpb_ctx* c) {
     clear_graphs(c);
     if (c->info_dev) cudaFree(c->info_dev);
     c->timer.reset();
+    gemm_i8_release(c->s);
     cudaStreamDestroy(c->s);
     delete c;
 }

@@ -64,6 +64,7 @@ struct GemmArgs {
     int flags;
 };
 int gemm_nt(const GemmArgs& a, cudaStream_t s);
+void gemm_i8_release(cudaStream_t s);  // gemm_i8.cu: frees the digit-plane workspace tied to a stream
 void count_launch(int n = 1);  // every other kernel launch is counted through this
 int64_t launch_count();
 

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) dgemm_kernel(const Ge
 }  // namespace
 
 int gemm_nt_tma(const GemmArgs& a, cudaStream_t s, double* flops_out);  // gemm_tma.cu
+int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out);   // gemm_i8.cu
 
 static double g_gemm_flops = 0.0;
 
@@ -290,6 +291,18 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     // big tiles unless they cannot fill one wave of 2 CTAs per SM (148 SMs)
     const int64_t tm = a.M / 128, tn = a.N / 64;
     const int64_t big_tiles = (a.flags & GEMM_LOWER) ? tm * (tm + 1) : tm * tn;
+    // INT8 tensor-core path (gemm_i8.cu: exact digit splitting, 28 int8 GEMMs per FP64 GEMM) for long k extents
+    static const int use_i8 = getenv("GPB200_GEMM_I8") ? atoi(getenv("GPB200_GEMM_I8")) : 0;
+    static const int i8_min_k = getenv("GPB200_GEMM_I8_MINK") ? atoi(getenv("GPB200_GEMM_I8_MINK")) : 1024;
+    if (use_i8 && a.K >= i8_min_k && (big_tiles >= 148 || use_i8 == 2)) {  // 2 = force (tests)
+        double fl = 0.0;
+        const int rc = gemm_nt_i8(a, s, &fl);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            g_gemm_flops += fl;
+            return 0;
+        }
+    }
     // Configurations measured on B200 at 8192^3: <8,4,2,2> BK=16, 2 stages, 3 CTAs/SM (166 registers, 61 KB) 35.8 TF/s
     // (default: a third resident warp per scheduler covers the other two's barrier / fragment-load gaps); the same
     // tile with 3 stages and 2 CTAs/SM 34.7; 8 warps of 32 x 32 <4,4,4,2> 33.7; BK=32 x 2 stages 34.1;
