@@ -122,3 +122,54 @@ extern "C" int gpb_test_inverse(int n, const double* A, double* W_out, double* K
     cudaFree(dA); cudaFree(dW); cudaFree(dK); cudaFree(dinv); cudaFree(tmp); cudaFree(dinfo); cudaFree(dX);
     return 0;
 }
+
+// D = alpha A B^T + beta C through one chosen GEMM implementation (impl 0: dispatcher, 1: INT8 tensor-core path).
+// A holds M*K doubles (K x M when flags has GEMM_A_MMAJOR), B holds N*K (K x N with GEMM_B_NMAJOR).
+namespace gpb { int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out); }
+extern "C" int gpb_test_gemm_impl(int impl, int M, int N, int K, const double* A, const double* B, const double* C,
+                                  double alpha, double beta, int flags, double* D, int reps, double* ms_out) {
+    double *dA, *dB, *dC = nullptr, *dD;
+    GPB_CUDA(cudaMalloc(&dA, sizeof(double) * (size_t)M * K));
+    GPB_CUDA(cudaMalloc(&dB, sizeof(double) * (size_t)N * K));
+    GPB_CUDA(cudaMalloc(&dD, sizeof(double) * (size_t)M * N));
+    GPB_CUDA(cudaMemcpy(dA, A, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice));
+    GPB_CUDA(cudaMemcpy(dB, B, sizeof(double) * (size_t)N * K, cudaMemcpyHostToDevice));
+    if (C) {
+        GPB_CUDA(cudaMalloc(&dC, sizeof(double) * (size_t)M * N));
+        GPB_CUDA(cudaMemcpy(dC, C, sizeof(double) * (size_t)M * N, cudaMemcpyHostToDevice));
+    }
+    GPB_CUDA(cudaMemset(dD, 0, sizeof(double) * (size_t)M * N));
+    GemmArgs g{M, N, K, dA, (flags & GEMM_A_MMAJOR) ? M : K, dB, (flags & GEMM_B_NMAJOR) ? N : K, dC, N, dD, N, nullptr, 0,
+               alpha, beta, flags};
+    auto run = [&]() -> int {
+        if (impl == 1) {
+            const int rc = gemm_nt_i8(g, 0, nullptr);
+            if (rc == 1) set_error("gpb_test_gemm_impl: the INT8 path does not apply to this call");
+            return rc == 0 ? 0 : -2;
+        }
+        return gemm_nt(g, 0);
+    };
+    GPB_TRY(run());
+    GPB_CUDA(cudaDeviceSynchronize());
+    GPB_CUDA(cudaMemcpy(D, dD, sizeof(double) * (size_t)M * N, cudaMemcpyDeviceToHost));
+    if (reps > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; ++r) GPB_TRY(run());
+        cudaEventRecord(e1);
+        GPB_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms_out) *ms_out = ms / reps;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    gemm_i8_release(0);
+    cudaFree(dA);
+    cudaFree(dB);
+    cudaFree(dC);
+    cudaFree(dD);
+    return 0;
+}

@@ -292,8 +292,8 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     const int64_t tm = a.M / 128, tn = a.N / 64;
     const int64_t big_tiles = (a.flags & GEMM_LOWER) ? tm * (tm + 1) : tm * tn;
     // INT8 tensor-core path (gemm_i8.cu: exact digit splitting, 28 int8 GEMMs per FP64 GEMM) for long k extents
-    static const int use_i8 = getenv("GPB200_GEMM_I8") ? atoi(getenv("GPB200_GEMM_I8")) : 0;
-    static const int i8_min_k = getenv("GPB200_GEMM_I8_MINK") ? atoi(getenv("GPB200_GEMM_I8_MINK")) : 1024;
+    static const int use_i8 = getenv("GPB200_GEMM_I8") ? atoi(getenv("GPB200_GEMM_I8")) : 1;
+    static const int i8_min_k = getenv("GPB200_GEMM_I8_MINK") ? atoi(getenv("GPB200_GEMM_I8_MINK")) : 512;  // measured break-even ~K = 256-384 (profiles/gemm_i8_r1_ksweep.json)
     if (use_i8 && a.K >= i8_min_k && (big_tiles >= 148 || use_i8 == 2)) {  // 2 = force (tests)
         double fl = 0.0;
         const int rc = gemm_nt_i8(a, s, &fl);

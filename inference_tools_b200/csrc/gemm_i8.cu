@@ -52,6 +52,7 @@ struct I8Args {
     int64_t ldd2;
     double alpha, beta;
     int flags, tiles_m, tiles_n;
+    int k_off, k_total;  // this launch covers [k_off, k_off + K) of the full k extent (int32 sums stay exact)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -136,11 +137,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
         bi = grp * RASTER + (r - bj * rows_in);
     }
     const int row0 = bi * BM, col0 = bj * BN;
-    int k_begin = 0, k_end = p.K;
+    int k_begin = 0, k_end = p.k_total;  // in the full k extent, then clipped to this launch's chunk
     if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, row0);
     if (p.flags & GEMM_TRIK_B) k_begin = max(k_begin, col0);
     if (p.flags & GEMM_TRIL_B) k_end = min(k_end, col0 + BN);
     if (p.flags & GEMM_TRIL_A) k_end = min(k_end, row0 + BM);
+    k_begin = max(k_begin, p.k_off) - p.k_off;
+    k_end = min(k_end, p.k_off + p.K) - p.k_off;
     const int NKB = max(0, k_end - k_begin) / KB;
 
     if (tid == 0) {
@@ -251,27 +254,60 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
     }
 }
 
-// One CTA per row: power-of-two scale from the row maximum over the row's valid k range, then the 7 balanced
-// base-256 digits of round(x 2^(55-e)), 16 consecutive k per thread (one 16-byte store per plane).
-// which = 0: rows of A (block height 128), 1: rows of B (block height 64) -- for the triangular k ranges.
-__global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ X, int64_t ld, int K, int rows,
-                                                         signed char* __restrict__ q, double* __restrict__ scale_out,
-                                                         double extra, int flags, int which) {
-    const int row = blockIdx.x, tid = threadIdx.x;
-    int k_lo = 0, k_hi = K;
+// valid k range [k_lo, k_hi) of an operand row, local to the chunk [k_off, k_off + K) of the full k extent.
+// which = 0: rows of A (tile height 128), 1: rows of B (tile height 64) -- the triangular flags are per tile.
+__device__ __forceinline__ void row_k_range(int row, int flags, int which, int k_off, int K, int& k_lo, int& k_hi) {
+    int lo = 0, hi = k_off + K;
     if (which == 0) {
-        if (flags & GEMM_TRIK_A) k_lo = (row / BM) * BM;
-        if (flags & GEMM_TRIL_A) k_hi = min(K, (row / BM + 1) * BM);
+        if (flags & GEMM_TRIK_A) lo = (row / BM) * BM;
+        if (flags & GEMM_TRIL_A) hi = min(hi, (row / BM + 1) * BM);
     } else {
-        if (flags & GEMM_TRIK_B) k_lo = (row / BN) * BN;
-        if (flags & GEMM_TRIL_B) k_hi = min(K, (row / BN + 1) * BN);
+        if (flags & GEMM_TRIK_B) lo = (row / BN) * BN;
+        if (flags & GEMM_TRIL_B) hi = min(hi, (row / BN + 1) * BN);
     }
+    k_lo = max(lo, k_off) - k_off;
+    k_hi = max(k_lo, hi - k_off);
+}
+// scale 2^-e with |x| 2^-e <= 127/128 for the row maximum m; mult = 2^(55-e); stored scale = extra * 2^e
+__device__ __forceinline__ void row_scale(double m, double extra, double& mult, double& scale) {
+    if (m > 1e-280 && m < 1e280) {
+        const int e = ilogb(m * (128.0 / 127.0)) + 1;
+        mult = scalbn(1.0, 55 - e);
+        scale = scalbn(extra, e);
+    } else {  // all-zero (padding) row, or non-finite / out-of-range values: NaN propagates to the row of D
+        mult = 0.0;
+        scale = (m == 0.0) ? 0.0 : nan("");
+    }
+}
+__device__ __forceinline__ double finite_abs_max(double amax, double v) {
+    const double a = fabs(v);
+    return (a <= 1.7e308) ? fmax(amax, a) : 1e300;  // NaN / Inf poison the row
+}
+// the 7 balanced base-256 digits of m = round(x 2^(55-e)); digit s goes to byte `lane` of word[s]
+__device__ __forceinline__ void put_digits(long long m, int lane, unsigned (&word)[S]) {
+#pragma unroll
+    for (int s = S - 1; s >= 1; --s) {
+        const int d = (int)(signed char)(m & 0xFF);
+        m = (m - d) >> 8;
+        word[s] |= ((unsigned)d & 0xFFu) << (lane * 8);
+    }
+    word[0] |= ((unsigned)(int)m & 0xFFu) << (lane * 8);
+}
+
+// k-contiguous operand (X[row * ld + k]).  One CTA per row: row maximum over the valid k range, then the digits,
+// 16 consecutive k per thread (one 16-byte store per plane).
+__global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ X, int64_t ld, int K, int k_off,
+                                                         int rows, signed char* __restrict__ q,
+                                                         double* __restrict__ scale_out, double extra, int flags,
+                                                         int which) {
+    const int row = blockIdx.x, tid = threadIdx.x;
+    int k_lo, k_hi;
+    row_k_range(row, flags, which, k_off, K, k_lo, k_hi);
     const double* x = X + (int64_t)row * ld;
     double amax = 0.0;
     for (int k = k_lo + 2 * tid; k < k_hi; k += 512) {
         const double2 w = *reinterpret_cast<const double2*>(x + k);
-        const double ax = fabs(w.x), ay = fabs(w.y);
-        amax = (ax <= 1.7e308 && ay <= 1.7e308) ? fmax(amax, fmax(ax, ay)) : 1e300;  // NaN / Inf poison the row
+        amax = finite_abs_max(finite_abs_max(amax, w.x), w.y);
     }
     __shared__ double red[8];
     __shared__ double mult_s;
@@ -283,44 +319,91 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
         double m = red[0];
 #pragma unroll
         for (int i = 1; i < 8; ++i) m = fmax(m, red[i]);
-        if (m > 1e-280 && m < 1e280) {
-            const int e = ilogb(m * (128.0 / 127.0)) + 1;  // |x| 2^-e <= 127/128
-            mult_s = scalbn(1.0, 55 - e);
-            scale_out[row] = scalbn(extra, e);
-        } else {  // all-zero (padding) row, or values this scheme does not cover
-            mult_s = 0.0;
-            scale_out[row] = (m == 0.0) ? 0.0 : nan("");  // NaN marks an unusable row (propagates to D)
-        }
+        double mult, scale;
+        row_scale(m, extra, mult, scale);
+        mult_s = mult;
+        scale_out[row] = scale;
     }
     __syncthreads();
     const double mult = mult_s;
     signed char* qrow = q + (int64_t)row * K;
     const int64_t plane = (int64_t)rows * K;
     for (int k0 = tid * 16; k0 < K; k0 += 256 * 16) {
-        unsigned int packed[S][4];
+        unsigned packed[4][S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) packed[s][0] = packed[s][1] = packed[s][2] = packed[s][3] = 0u;
+        for (int wd = 0; wd < 4; ++wd)
+#pragma unroll
+            for (int s = 0; s < S; ++s) packed[wd][s] = 0u;
         if (k0 >= k_lo && k0 < k_hi) {
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
                 const double2 w = *reinterpret_cast<const double2*>(x + k0 + 2 * h);
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    long long m = __double2ll_rn((u ? w.y : w.x) * mult);
-                    const int e = 2 * h + u;
-#pragma unroll
-                    for (int s = S - 1; s >= 1; --s) {
-                        const int d = (int)(signed char)(m & 0xFF);
-                        m = (m - d) >> 8;
-                        packed[s][e >> 2] |= ((unsigned)d & 0xFFu) << ((e & 3) * 8);
-                    }
-                    packed[0][e >> 2] |= ((unsigned)(int)m & 0xFFu) << ((e & 3) * 8);
-                }
+                put_digits(__double2ll_rn(w.x * mult), (2 * h) & 3, packed[h >> 1]);
+                put_digits(__double2ll_rn(w.y * mult), (2 * h + 1) & 3, packed[h >> 1]);
             }
         }
 #pragma unroll
         for (int s = 0; s < S; ++s)
-            *reinterpret_cast<uint4*>(qrow + s * plane + k0) = make_uint4(packed[s][0], packed[s][1], packed[s][2], packed[s][3]);
+            *reinterpret_cast<uint4*>(qrow + s * plane + k0) = make_uint4(packed[0][s], packed[1][s], packed[2][s], packed[3][s]);
+    }
+}
+
+// Operand stored with the row index contiguous (X[k * ld + row]: GEMM_A_MMAJOR / GEMM_B_NMAJOR).
+// Pass 1: maxima of 64 rows per CTA, reads coalesced along the rows.
+__global__ void __launch_bounds__(256) split_cols_max_kernel(const double* __restrict__ X, int64_t ld, int K, int k_off,
+                                                             double* __restrict__ scale_out, double* __restrict__ mult_out,
+                                                             double extra, int flags, int which) {
+    const int r = blockIdx.x * 64 + (threadIdx.x & 63), kg = threadIdx.x >> 6;
+    int k_lo, k_hi;
+    row_k_range(blockIdx.x * 64, flags, which, k_off, K, k_lo, k_hi);
+    double amax = 0.0;
+    for (int k = k_lo + kg; k < k_hi; k += 4) amax = finite_abs_max(amax, X[(int64_t)k * ld + r]);
+    __shared__ double red[4][64];
+    red[kg][threadIdx.x & 63] = amax;
+    __syncthreads();
+    if (kg == 0) {
+        const int c = threadIdx.x & 63;
+        const double m = fmax(fmax(red[0][c], red[1][c]), fmax(red[2][c], red[3][c]));
+        double mult, scale;
+        row_scale(m, extra, mult, scale);
+        mult_out[r] = mult;
+        scale_out[r] = scale;
+    }
+}
+// Pass 2: a 64 (rows) x 64 (k) tile per CTA, transposed through shared memory: global reads coalesced along the rows,
+// digit planes written as 64-byte k-contiguous row segments.
+__global__ void __launch_bounds__(256) split_cols_digits_kernel(const double* __restrict__ X, int64_t ld, int K,
+                                                                int k_off, int rows, signed char* __restrict__ q,
+                                                                const double* __restrict__ mult_in, int flags,
+                                                                int which) {
+    __shared__ unsigned dig[S][64][17];  // [plane][row][k / 4], padded against bank conflicts
+    const int r0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const int rl = threadIdx.x & 63, kq0 = threadIdx.x >> 6;
+    int k_lo, k_hi;
+    row_k_range(r0, flags, which, k_off, K, k_lo, k_hi);
+    const bool live = k0 >= k_lo && k0 < k_hi;  // ranges are multiples of 64
+    const double mult = mult_in[r0 + rl];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int kq = kq0 + 4 * i;
+        unsigned word[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) word[s] = 0u;
+        if (live) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                put_digits(__double2ll_rn(X[(int64_t)(k0 + 4 * kq + u) * ld + r0 + rl] * mult), u, word);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) dig[s][rl][kq] = word[s];
+    }
+    __syncthreads();
+    const int64_t plane = (int64_t)rows * K;
+    for (int t = threadIdx.x; t < S * 64 * 4; t += 256) {
+        const int s = t / 256, rr = (t >> 2) & 63, quarter = t & 3;
+        const unsigned* src = &dig[s][rr][quarter * 4];
+        *reinterpret_cast<uint4*>(q + s * plane + (int64_t)(r0 + rr) * K + k0 + quarter * 16) =
+            make_uint4(src[0], src[1], src[2], src[3]);
     }
 }
 
@@ -395,12 +478,13 @@ void gemm_i8_release(cudaStream_t s) {
 
 // Returns 0 when launched, 1 when this path does not apply (caller falls back to the DMMA kernels), < 0 on error.
 int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
-    if (a.flags & (GEMM_A_MMAJOR | GEMM_B_NMAJOR)) return 1;
-    if (a.K % KB || a.K > MAX_K || a.K <= 0 || (a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
-        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.ldd & 1) || (reinterpret_cast<uintptr_t>(a.D) & 15))
+    const bool a_t = a.flags & GEMM_A_MMAJOR, b_t = a.flags & GEMM_B_NMAJOR;
+    auto misaligned = [](const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) || (ld & 1); };
+    if (a.K % KB || a.K <= 0 || (!a_t && misaligned(a.A, a.lda)) || (!b_t && misaligned(a.B, a.ldb)) ||
+        misaligned(a.D, a.ldd))
         return 1;
-    if (a.beta != 0.0 && ((a.ldc & 1) || (reinterpret_cast<uintptr_t>(a.C) & 15))) return 1;
-    if (a.D2 && ((a.ldd2 & 1) || (reinterpret_cast<uintptr_t>(a.D2) & 15))) return 1;
+    if (a.beta != 0.0 && misaligned(a.C, a.ldc)) return 1;
+    if (a.D2 && misaligned(a.D2, a.ldd2)) return 1;
     if (!get_encode()) return 1;
     int dev = 0;
     GPB_CUDA(cudaGetDevice(&dev));
@@ -409,30 +493,50 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
         std::lock_guard<std::mutex> lock(g_ws_mutex);
         w = &g_ws[{dev, s}];
     }
-    GPB_TRY(grow(w->qa, w->qa_cap, (size_t)S * a.M * a.K, w->retired));
-    GPB_TRY(grow(w->qb, w->qb_cap, (size_t)S * a.N * a.K, w->retired));
-    GPB_TRY(grow(w->sa, w->sa_cap, sizeof(double) * a.M, w->retired));
-    GPB_TRY(grow(w->sb, w->sb_cap, sizeof(double) * a.N, w->retired));
+    const int chunks = (a.K + MAX_K - 1) / MAX_K;
+    const int Kc_max = ((a.K / KB + chunks - 1) / chunks) * KB;  // balanced chunks, multiples of 64
+    GPB_TRY(grow(w->qa, w->qa_cap, (size_t)S * a.M * Kc_max, w->retired));
+    GPB_TRY(grow(w->qb, w->qb_cap, (size_t)S * a.N * Kc_max, w->retired));
+    GPB_TRY(grow(w->sa, w->sa_cap, sizeof(double) * 2 * a.M, w->retired));  // scales, then the 2^(55-e) multipliers
+    GPB_TRY(grow(w->sb, w->sb_cap, sizeof(double) * 2 * a.N, w->retired));
     static bool configured_dev[64] = {};
     if (!configured_dev[dev & 63]) {
         GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured_dev[dev & 63] = true;
     }
-    split_rows_kernel<<<a.M, 256, 0, s>>>(a.A, a.lda, a.K, a.M, w->qa, w->sa, 1.0 / 16384.0, a.flags, 0);
-    GPB_CUDA(cudaGetLastError());
-    split_rows_kernel<<<a.N, 256, 0, s>>>(a.B, a.ldb, a.K, a.N, w->qb, w->sb, 1.0, a.flags, 1);
-    GPB_CUDA(cudaGetLastError());
-    CUtensorMap tmA, tmB;
-    if (make_plane_map(&tmA, w->qa, a.M, a.K, BM) || make_plane_map(&tmB, w->qb, a.N, a.K, BN)) {
-        set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
-        return -3;
-    }
     const int tm = a.M / BM, tn = a.N / BN;
     const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) : (int64_t)tm * tn;
-    I8Args p{a.M, a.N, a.K, w->sa, w->sb, a.C, a.ldc, a.D, a.ldd, a.D2, a.ldd2, a.alpha, a.beta, a.flags, tm, tn};
-    gemm_i8_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
-    GPB_CUDA(cudaGetLastError());
-    count_launch(3);
+    for (int k0 = 0, c = 0; k0 < a.K; k0 += Kc_max, ++c) {
+        const int Kc = std::min(Kc_max, a.K - k0);
+        if (a_t) {
+            const double* X = a.A + (int64_t)k0 * a.lda;
+            split_cols_max_kernel<<<a.M / 64, 256, 0, s>>>(X, a.lda, Kc, k0, w->sa, w->sa + a.M, 1.0 / 16384.0, a.flags, 0);
+            split_cols_digits_kernel<<<dim3(a.M / 64, Kc / 64), 256, 0, s>>>(X, a.lda, Kc, k0, a.M, w->qa, w->sa + a.M,
+                                                                             a.flags, 0);
+        } else {
+            split_rows_kernel<<<a.M, 256, 0, s>>>(a.A + k0, a.lda, Kc, k0, a.M, w->qa, w->sa, 1.0 / 16384.0, a.flags, 0);
+        }
+        GPB_CUDA(cudaGetLastError());
+        if (b_t) {
+            const double* X = a.B + (int64_t)k0 * a.ldb;
+            split_cols_max_kernel<<<a.N / 64, 256, 0, s>>>(X, a.ldb, Kc, k0, w->sb, w->sb + a.N, 1.0, a.flags, 1);
+            split_cols_digits_kernel<<<dim3(a.N / 64, Kc / 64), 256, 0, s>>>(X, a.ldb, Kc, k0, a.N, w->qb, w->sb + a.N,
+                                                                             a.flags, 1);
+        } else {
+            split_rows_kernel<<<a.N, 256, 0, s>>>(a.B + k0, a.ldb, Kc, k0, a.N, w->qb, w->sb, 1.0, a.flags, 1);
+        }
+        GPB_CUDA(cudaGetLastError());
+        CUtensorMap tmA, tmB;
+        if (make_plane_map(&tmA, w->qa, a.M, Kc, BM) || make_plane_map(&tmB, w->qb, a.N, Kc, BN)) {
+            set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
+            return -3;
+        }
+        I8Args p{a.M, a.N, Kc, w->sa, w->sb, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2,
+                 a.alpha, c == 0 ? a.beta : 1.0, a.flags, tm, tn, k0, a.K};
+        gemm_i8_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
+        GPB_CUDA(cudaGetLastError());
+        count_launch(3 + (a_t ? 1 : 0) + (b_t ? 1 : 0));
+    }
     if (flops_out) {
         if (!(a.flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) {
             *flops_out = (double)tiles * 2.0 * BM * BN * a.K;
