@@ -40,6 +40,7 @@ constexpr int THREADS = 192;                  // warp 0: TMA, warp 1: TMEM alloc
 constexpr int TMEM_COLS = 512;
 constexpr int RASTER = 8;                     // row-blocks per rasterisation group (B planes stay in L2 across them)
 constexpr int MAX_K = 16384;
+constexpr int DEBUG_NO_MMA = 1 << 20, DEBUG_NO_LOAD = 1 << 21;  // timing probes (results are meaningless)
 
 struct I8Args {
     int M, N, K;
@@ -100,6 +101,34 @@ __device__ __forceinline__ void mma_i8(unsigned tmem_d, uint64_t adesc, uint64_t
         "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
         : "memory");
 }
+// A operand from tensor memory (128 lanes x 8 columns = 128 rows x 32 int8), B from shared memory
+__device__ __forceinline__ void mma_i8_ts(unsigned tmem_d, unsigned tmem_a, uint64_t bdesc, unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// shared memory -> tensor memory: 128 rows x 256 bits described by a matrix descriptor
+__device__ __forceinline__ void tmem_cp_128x256b(unsigned tmem_dst, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+// one lane of a converged warp (the compiler keeps tcgen05 instructions under this predicate branch-free)
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, px;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
@@ -112,6 +141,7 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int (&r)[16]) {
         : "memory");
 }
 
+template <bool TS>
 __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, const I8Args p) {
     extern __shared__ unsigned char smem_raw[];
@@ -162,40 +192,62 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer
-            for (int kb = 0; kb < NKB; ++kb) {
-                const int stage = kb & 1;
-                if (kb >= STAGES) mbar_wait(smem_u32(&bars[2 + stage]), ((kb >> 1) - 1) & 1);
+    if (warp == 0) {  // ---- TMA producer: converged warp, one elected lane issues
+        for (int kb = 0; kb < NKB; ++kb) {
+            const int stage = kb & 1;
+            if (kb >= STAGES) mbar_wait(smem_u32(&bars[2 + stage]), ((kb >> 1) - 1) & 1);
+            if (elect_one()) {
                 const unsigned bar = smem_u32(&bars[stage]);
                 const unsigned dst = smem_u32(tiles + stage * STAGE_BYTES);
-                mbar_expect_tx(bar, STAGE_BYTES);
-                tma_load_3d(dst, &tmA, k_begin + kb * KB, row0, 0, bar);
-                tma_load_3d(dst + A_BYTES, &tmB, k_begin + kb * KB, col0, 0, bar);
+                if ((p.flags & DEBUG_NO_LOAD) && kb >= STAGES) {  // timing probe: MMA rate without the loads
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+                } else {
+                    mbar_expect_tx(bar, STAGE_BYTES);
+                    tma_load_3d(dst, &tmA, k_begin + kb * KB, row0, 0, bar);
+                    tma_load_3d(dst + A_BYTES, &tmB, k_begin + kb * KB, col0, 0, bar);
+                }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer
+        {  // ---- MMA issuer: the whole warp walks the pipeline, one elected lane issues
             for (int kb = 0; kb < NKB; ++kb) {
                 const int stage = kb & 1;
                 mbar_wait(smem_u32(&bars[stage]), (kb >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned a_base = smem_u32(tiles + stage * STAGE_BYTES), b_base = a_base + A_BYTES;
+                if (p.flags & DEBUG_NO_MMA) {  // timing probe: load rate without the MMAs
+                    if (elect_one()) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 + stage])) : "memory");
+                        if (kb == NKB - 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[4])) : "memory");
+                    }
+                } else if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < KB / 32; ++ks) {
+                    if (TS) {  // stage the 7 A planes of this k-step in TMEM columns 448..503: each then feeds up to 7 MMAs
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+                            tmem_cp_128x256b(tmem_base + (unsigned)(S * BN + 8 * s), smem_desc(a_base + s * A_PLANE + ks * 32));
+                    }
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         const uint64_t adesc = smem_desc(a_base + s * A_PLANE + ks * 32);
 #pragma unroll
                         for (int t = 0; t < S - s; ++t) {
                             const uint64_t bdesc = smem_desc(b_base + t * B_PLANE + ks * 32);
-                            mma_i8(tmem_base + (unsigned)((s + t) * BN), adesc, bdesc, (unsigned)((kb | ks | s) != 0));
+                            if (TS)
+                                mma_i8_ts(tmem_base + (unsigned)((s + t) * BN), tmem_base + (unsigned)(S * BN + 8 * s), bdesc,
+                                          (unsigned)((kb | ks | s) != 0));
+                            else
+                                mma_i8(tmem_base + (unsigned)((s + t) * BN), adesc, bdesc, (unsigned)((kb | ks | s) != 0));
                         }
                     }
                 }
                 mma_commit(smem_u32(&bars[2 + stage]));  // frees the stage when these MMAs have read it
+                if (kb == NKB - 1) mma_commit(smem_u32(&bars[4]));
+                }
+                __syncwarp();
             }
-            if (NKB > 0) mma_commit(smem_u32(&bars[4]));
         }
     } else {  // ---- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31
         const int q = warp & 3;
@@ -501,7 +553,8 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     GPB_TRY(grow(w->sb, w->sb_cap, sizeof(double) * 2 * a.N, w->retired));
     static bool configured_dev[64] = {};
     if (!configured_dev[dev & 63]) {
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured_dev[dev & 63] = true;
     }
     const int tm = a.M / BM, tn = a.N / BN;
@@ -531,9 +584,14 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
             set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
             return -3;
         }
+        static const int debug = getenv("GPB200_GEMM_I8_DEBUG") ? atoi(getenv("GPB200_GEMM_I8_DEBUG")) : 0;
         I8Args p{a.M, a.N, Kc, w->sa, w->sb, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2,
-                 a.alpha, c == 0 ? a.beta : 1.0, a.flags, tm, tn, k0, a.K};
-        gemm_i8_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
+                 a.alpha, c == 0 ? a.beta : 1.0, a.flags | (debug << 20), tm, tn, k0, a.K};
+        static const int use_ts = getenv("GPB200_GEMM_I8_TS") ? atoi(getenv("GPB200_GEMM_I8_TS")) : 0;
+        if (use_ts)
+            gemm_i8_kernel<true><<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
+        else
+            gemm_i8_kernel<false><<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
         GPB_CUDA(cudaGetLastError());
         count_launch(3 + (a_t ? 1 : 0) + (b_t ? 1 : 0));
     }
