@@ -7,17 +7,20 @@
 //   1. split_rows_kernel: every row of A (and of B) is scaled by a power of two 2^-e so that |x| <= 127/128, rounded
 //      to a 55-bit integer and written as S = 7 balanced base-256 digits d_0..d_6 (d_0 in [-127,127], the others in
 //      [-128,127]):  x = 2^e sum_s d_s 2^-(7+8s)  up to 2^(e-55).  Seven int8 planes per operand.
-//   2. gemm_i8_kernel: the 28 digit products with s + t <= 6 are exact int32 GEMMs.  A CTA owns a 128 x 64 tile of
-//      D and keeps all seven anti-diagonal sums  P_g = sum_{s+t=g} A_s B_t^T  live in TMEM (7 x 64 columns of 512),
-//      so every k-block of the 7 + 7 digit planes is brought in ONCE (one 3-D TMA box per operand) and feeds 28
-//      MMAs -- 4x less shared-memory fill per MMA than a plain int8 GEMM, which is what keeps this off the L2 limit.
-//      One thread issues the MMAs; a TMA thread runs two 84 KB stages ahead; four epilogue warps read the seven
-//      accumulators back (tcgen05.ld), combine them smallest-first in FP64 (Horner in 2^-8) and apply the row /
-//      column scales, alpha, beta.
+//   2. gemm_i8_kernel: the 28 digit products with s + t <= 6 are exact int32 GEMMs, grouped by anti-diagonal
+//      P_g = sum_{s+t=g} A_s B_t^T.  A persistent CTA owns 128 x 128 tiles of D; one tcgen05.mma is 128 x 128 x 32,
+//      the smallest shape that runs at the full 8192 MAC/clk/SM from shared memory (N = 64 is limited to 2/3 of it by
+//      shared-memory bandwidth: tools/umma_probe.cu).  TMEM holds four 128-column int32 accumulators, so a tile takes
+//      two sweeps over k: first P_4..P_6 (18 products, all 7 + 7 planes per k-block), then P_0..P_3 (10 products,
+//      planes 0..3).  Every k-block of planes is fetched by ONE 3-D TMA box per operand and feeds 18 (10) MMA pairs:
+//      ~50 bytes of L2->shared traffic per MMA clock instead of ~190 for a plain int8 GEMM of this tile.
+//      Warp 0 is the TMA producer (two 112 KB stages), warp 1 issues the MMAs (one elected lane), warps 2-5 drain
+//      the accumulators (tcgen05.ld), combine them smallest-first in FP64 (Horner in 2^-8; the first sweep's
+//      partial sum waits in a per-CTA scratch row) and apply the row / column scales, alpha and beta.
 //
 // Dropped terms (s + t >= 7) are below 2^-53 of rowmax(A) * rowmax(B) per product -- the same normwise bound as an
-// FP64 dot product; the int32 sums are exact for K <= 16384 (7 * K * 2^14 < 2^31).  Operands with the k index
-// contiguous only; the caller (gemm_nt) falls back to the DMMA kernels otherwise.
+// FP64 dot product; the int32 sums are exact for k extents <= 16384 (7 * K * 2^14 < 2^31), longer ones are chunked.
+// M and N must be multiples of 128; the caller (gemm_nt) falls back to the DMMA kernels otherwise.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -29,14 +32,25 @@
 namespace gpb {
 namespace {
 
+#ifndef I8_KB
+#define I8_KB 64
+#endif
 constexpr int S = 7;                          // digit planes per operand
-constexpr int BM = 128, BN = 64, KB = 64;     // tile of D; k-block in int8 elements (= bytes, one 64-byte swizzle row)
-constexpr int A_PLANE = BM * KB, B_PLANE = BN * KB;       // 8192, 4096
-constexpr int A_BYTES = S * A_PLANE, B_BYTES = S * B_PLANE;  // 57344, 28672
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;            // 86016
-constexpr int STAGES = 2;
+constexpr int S_HI = 3;                       // second sweep: diagonals 0..2 need planes 0..2 only
+constexpr int BM = 128, BN = 128, KB = I8_KB;  // tile of D; k-block in int8 elements (= bytes, one swizzle row)
+constexpr int A_PLANE = BM * KB, B_PLANE = BN * KB;       // 8192, 8192
+constexpr int A_BYTES = S * A_PLANE, B_BYTES = S * B_PLANE;  // 57344, 57344
+// Shared memory is 4 slots of 56 KB, each with a full / empty barrier.  A k-block of the first sweep takes two
+// consecutive slots (7 A planes | 7 B planes); a k-block of the second sweep takes one (3 A planes, 3 B planes at
+// +28 KB), so the short second-sweep stages run four deep.
+constexpr int SLOT_BYTES = A_BYTES;                        // 57344
+constexpr int SLOT_B_OFF = SLOT_BYTES / 2;                 // 28672
+constexpr int HI_BYTES = S_HI * A_PLANE;                   // 24576 per operand in the second sweep
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = SLOT_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers, tmem slot*/;
-constexpr int THREADS = 192;                  // warp 0: TMA, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
+constexpr int EPI_WARPS = 8;                   // two per TMEM lane quarter, 64 columns each
+constexpr int THREADS = 64 + 32 * EPI_WARPS;   // warp 0: TMA, warp 1: TMEM alloc + MMA issue, warps 2-9: epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int RASTER = 8;                     // row-blocks per rasterisation group (B planes stay in L2 across them)
 constexpr int MAX_K = 16384;
@@ -53,6 +67,7 @@ struct I8Args {
     int64_t ldd2;
     double alpha, beta;
     int flags, tiles_m, tiles_n;
+    double* scratch;     // gridDim.x * 128 * 128 doubles: first-sweep partial sums, private to each thread
     int k_off, k_total;  // this launch covers [k_off, k_off + K) of the full k extent (int32 sums stay exact)
 };
 
@@ -86,7 +101,9 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
 }
 // shared-memory matrix descriptor: k-major tile of 64-byte rows, 64-byte swizzle (8-row atoms of 512 bytes)
 __device__ __forceinline__ uint64_t smem_desc(unsigned addr) {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+    // stride between 8-row atoms = 8 * KB bytes; layout type 4 = 64-byte swizzle, 6 = 32-byte swizzle
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((8 * KB) >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)(KB == 64 ? 4 : 6) << 61);
 }
 // instruction descriptor: D = s32, A = B = signed 8-bit, both k-major, N = 64, M = 128
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -100,21 +117,6 @@ __device__ __forceinline__ void mma_i8(unsigned tmem_d, uint64_t adesc, uint64_t
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
         : "memory");
-}
-// A operand from tensor memory (128 lanes x 8 columns = 128 rows x 32 int8), B from shared memory
-__device__ __forceinline__ void mma_i8_ts(unsigned tmem_d, unsigned tmem_a, uint64_t bdesc, unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-// shared memory -> tensor memory: 128 rows x 256 bits described by a matrix descriptor
-__device__ __forceinline__ void tmem_cp_128x256b(unsigned tmem_dst, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(sdesc) : "memory");
 }
 // one lane of a converged warp (the compiler keeps tcgen05 instructions under this predicate branch-free)
 __device__ __forceinline__ bool elect_one() {
@@ -141,44 +143,74 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int (&r)[16]) {
         : "memory");
 }
 
-template <bool TS>
-__global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, const I8Args p) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + STAGES * STAGE_BYTES);
-    // bars[0..1] full, bars[2..3] empty, bars[4] accumulators ready; then the TMEM base address slot
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+struct TileRange {
+    int row0, col0, k_begin, nkb;
+};
+__device__ __forceinline__ TileRange tile_range(const I8Args& p, int t) {
     int bi, bj;
-    if (p.flags & GEMM_LOWER) {
-        const int t = blockIdx.x;
-        int r = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while (r * (r + 1) > t) --r;
-        while ((r + 1) * (r + 2) <= t) ++r;
+    if (p.flags & GEMM_LOWER) {  // tiles with bj <= bi, row-block major
+        int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (r * (r + 1) / 2 > t) --r;
+        while ((r + 1) * (r + 2) / 2 <= t) ++r;
         bi = r;
-        bj = t - r * (r + 1);
-    } else {  // groups of RASTER row-blocks sweep the columns together
+        bj = t - r * (r + 1) / 2;
+    } else {  // groups of RASTER row-blocks sweep the columns together (their B planes stay in L2)
         const int per_group = RASTER * p.tiles_n;
-        const int grp = blockIdx.x / per_group, r = blockIdx.x - grp * per_group;
+        const int grp = t / per_group, r = t - grp * per_group;
         const int rows_in = min(RASTER, p.tiles_m - grp * RASTER);
         bj = r / rows_in;
         bi = grp * RASTER + (r - bj * rows_in);
     }
-    const int row0 = bi * BM, col0 = bj * BN;
+    TileRange tr;
+    tr.row0 = bi * BM;
+    tr.col0 = bj * BN;
     int k_begin = 0, k_end = p.k_total;  // in the full k extent, then clipped to this launch's chunk
-    if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, row0);
-    if (p.flags & GEMM_TRIK_B) k_begin = max(k_begin, col0);
-    if (p.flags & GEMM_TRIL_B) k_end = min(k_end, col0 + BN);
-    if (p.flags & GEMM_TRIL_A) k_end = min(k_end, row0 + BM);
+    if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, tr.row0);
+    if (p.flags & GEMM_TRIK_B) k_begin = max(k_begin, tr.col0);
+    if (p.flags & GEMM_TRIL_B) k_end = min(k_end, tr.col0 + BN);
+    if (p.flags & GEMM_TRIL_A) k_end = min(k_end, tr.row0 + BM);
     k_begin = max(k_begin, p.k_off) - p.k_off;
     k_end = min(k_end, p.k_off + p.K) - p.k_off;
-    const int NKB = max(0, k_end - k_begin) / KB;
+    tr.k_begin = k_begin;
+    tr.nkb = max(0, k_end - k_begin) / KB;
+    return tr;
+}
 
+// issue the MMAs of one k-block for the diagonals [G0, G1]: accumulator g - G0 lives at TMEM columns (g - G0) * BN
+template <int G0, int G1>
+__device__ __forceinline__ void issue_kblock(unsigned tmem_base, unsigned a_base, unsigned b_base, int kb) {
+#pragma unroll
+    for (int ks = 0; ks < KB / 32; ++ks) {
+#pragma unroll
+        for (int s = 0; s <= G1; ++s) {
+            const uint64_t adesc = smem_desc(a_base + s * A_PLANE + ks * 32);
+#pragma unroll
+            for (int t = 0; t <= G1 - s; ++t) {
+                if (s + t < G0) continue;
+                const uint64_t bdesc = smem_desc(b_base + t * B_PLANE + ks * 32);
+                // the first product into each accumulator (s = 0 of the first k-step) overwrites it
+                mma_i8(tmem_base + (unsigned)((s + t - G0) * BN), adesc, bdesc, (unsigned)((kb | ks | s) != 0));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ CUtensorMap tmA_hi,
+                                                             const __grid_constant__ CUtensorMap tmB_hi, const I8Args p,
+                                                             const int n_tiles) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + STAGES * STAGE_BYTES);
+    // bars[0..STAGES) stage full, [STAGES..2 STAGES) stage empty, then accumulators ready, accumulators drained
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 12);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < 2 * STAGES + 1; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_init(smem_u32(&bars[2 * STAGES + 1]), EPI_WARPS);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -193,108 +225,199 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
     const unsigned tmem_base = *tmem_slot;
 
     if (warp == 0) {  // ---- TMA producer: converged warp, one elected lane issues
-        for (int kb = 0; kb < NKB; ++kb) {
-            const int stage = kb & 1;
-            if (kb >= STAGES) mbar_wait(smem_u32(&bars[2 + stage]), ((kb >> 1) - 1) & 1);
-            if (elect_one()) {
-                const unsigned bar = smem_u32(&bars[stage]);
-                const unsigned dst = smem_u32(tiles + stage * STAGE_BYTES);
-                if ((p.flags & DEBUG_NO_LOAD) && kb >= STAGES) {  // timing probe: MMA rate without the loads
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-                } else {
-                    mbar_expect_tx(bar, STAGE_BYTES);
-                    tma_load_3d(dst, &tmA, k_begin + kb * KB, row0, 0, bar);
-                    tma_load_3d(dst + A_BYTES, &tmB, k_begin + kb * KB, col0, 0, bar);
+        int it = 0;  // slots handed out so far
+        auto acquire = [&](int i) {  // wait until the MMAs that read slot use i - STAGES have completed
+            if (i >= STAGES) mbar_wait(smem_u32(&bars[STAGES + i % STAGES]), ((i / STAGES) - 1) & 1);
+        };
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const TileRange tr = tile_range(p, t);
+            for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: A planes -> slot it, B planes -> slot it + 1
+                acquire(it);
+                acquire(it + 1);
+                if (elect_one()) {
+                    const int k = tr.k_begin + kb * KB;
+                    const unsigned bar_a = smem_u32(&bars[it % STAGES]), bar_b = smem_u32(&bars[(it + 1) % STAGES]);
+                    if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {  // timing probe: MMA rate without the loads
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_a) : "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_b) : "memory");
+                    } else {
+                        mbar_expect_tx(bar_a, A_BYTES);
+                        tma_load_3d(smem_u32(tiles + (it % STAGES) * SLOT_BYTES), &tmA, k, tr.row0, 0, bar_a);
+                        mbar_expect_tx(bar_b, B_BYTES);
+                        tma_load_3d(smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), &tmB, k, tr.col0, 0, bar_b);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        {  // ---- MMA issuer: the whole warp walks the pipeline, one elected lane issues
-            for (int kb = 0; kb < NKB; ++kb) {
-                const int stage = kb & 1;
-                mbar_wait(smem_u32(&bars[stage]), (kb >> 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const unsigned a_base = smem_u32(tiles + stage * STAGE_BYTES), b_base = a_base + A_BYTES;
-                if (p.flags & DEBUG_NO_MMA) {  // timing probe: load rate without the MMAs
-                    if (elect_one()) {
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 + stage])) : "memory");
-                        if (kb == NKB - 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[4])) : "memory");
+            for (int kb = 0; kb < tr.nkb; ++kb, ++it) {  // second sweep: one slot per k-block
+                acquire(it);
+                if (elect_one()) {
+                    const int k = tr.k_begin + kb * KB;
+                    const unsigned bar = smem_u32(&bars[it % STAGES]);
+                    if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+                    } else {
+                        const unsigned dst = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
+                        mbar_expect_tx(bar, 2 * HI_BYTES);
+                        tma_load_3d(dst, &tmA_hi, k, tr.row0, 0, bar);
+                        tma_load_3d(dst + SLOT_B_OFF, &tmB_hi, k, tr.col0, 0, bar);
                     }
-                } else if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < KB / 32; ++ks) {
-                    if (TS) {  // stage the 7 A planes of this k-step in TMEM columns 448..503: each then feeds up to 7 MMAs
-#pragma unroll
-                        for (int s = 0; s < S; ++s)
-                            tmem_cp_128x256b(tmem_base + (unsigned)(S * BN + 8 * s), smem_desc(a_base + s * A_PLANE + ks * 32));
-                    }
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        const uint64_t adesc = smem_desc(a_base + s * A_PLANE + ks * 32);
-#pragma unroll
-                        for (int t = 0; t < S - s; ++t) {
-                            const uint64_t bdesc = smem_desc(b_base + t * B_PLANE + ks * 32);
-                            if (TS)
-                                mma_i8_ts(tmem_base + (unsigned)((s + t) * BN), tmem_base + (unsigned)(S * BN + 8 * s), bdesc,
-                                          (unsigned)((kb | ks | s) != 0));
-                            else
-                                mma_i8(tmem_base + (unsigned)((s + t) * BN), adesc, bdesc, (unsigned)((kb | ks | s) != 0));
-                        }
-                    }
-                }
-                mma_commit(smem_u32(&bars[2 + stage]));  // frees the stage when these MMAs have read it
-                if (kb == NKB - 1) mma_commit(smem_u32(&bars[4]));
                 }
                 __syncwarp();
             }
         }
-    } else {  // ---- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31
-        const int q = warp & 3;
-        const int row = row0 + q * 32 + lane;
-        const double sa = p.sa[row] * p.alpha;
-        const double beta = p.beta;
-        if (NKB > 0) {
-            mbar_wait(smem_u32(&bars[4]), 0);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    } else if (warp == 1) {  // ---- MMA issuer: the whole warp walks the pipeline, one elected lane issues
+        int it = 0, uses = 0;
+        auto filled = [&](int i) { mbar_wait(smem_u32(&bars[i % STAGES]), (i / STAGES) & 1); };
+        auto drained = [&]() {  // the epilogue has read the previous sweep's accumulators
+            if (uses >= 1) {
+                mbar_wait(smem_u32(&bars[2 * STAGES + 1]), (uses - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            }
+            ++uses;
+        };
+        const bool no_mma = p.flags & DEBUG_NO_MMA;  // timing probe: load rate without the MMAs
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const TileRange tr = tile_range(p, t);
+            if (tr.nkb == 0) continue;
+            drained();
+            for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: diagonals S_HI..6, accumulator g - S_HI
+                filled(it);
+                filled(it + 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const unsigned bar_a = smem_u32(&bars[STAGES + it % STAGES]), bar_b = smem_u32(&bars[STAGES + (it + 1) % STAGES]);
+                if (elect_one()) {
+                    if (no_mma) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_a) : "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_b) : "memory");
+                        if (kb == tr.nkb - 1)
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES])) : "memory");
+                    } else {
+                        issue_kblock<S_HI, S - 1>(tmem_base, smem_u32(tiles + (it % STAGES) * SLOT_BYTES),
+                                                  smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), kb);
+                        mma_commit(bar_a);  // both slots are free once these MMAs have read them
+                        mma_commit(bar_b);
+                        if (kb == tr.nkb - 1) mma_commit(smem_u32(&bars[2 * STAGES]));
+                    }
+                }
+                __syncwarp();
+            }
+            drained();
+            for (int kb = 0; kb < tr.nkb; ++kb, ++it) {  // second sweep: diagonals 0..S_HI-1
+                filled(it);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const unsigned bar = smem_u32(&bars[STAGES + it % STAGES]);
+                if (elect_one()) {
+                    if (no_mma) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+                        if (kb == tr.nkb - 1)
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES])) : "memory");
+                    } else {
+                        const unsigned base = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
+                        issue_kblock<0, S_HI - 1>(tmem_base, base, base + SLOT_B_OFF, kb);
+                        mma_commit(bar);
+                        if (kb == tr.nkb - 1) mma_commit(smem_u32(&bars[2 * STAGES]));
+                    }
+                }
+                __syncwarp();
+            }
         }
+    } else {  // ---- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; two warps per quarter split the columns
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        constexpr int COLS = BN / (EPI_WARPS / 4);  // columns per warp
+        const int cbase = half * COLS;
+        const unsigned lane_base = (unsigned)(q * 32) << 16;
+        double* scr = p.scratch + ((size_t)blockIdx.x * BM + q * 32 + lane) * BN + cbase;
+        const double beta = p.beta;
+        int uses = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const TileRange tr = tile_range(p, t);
+            const int row = tr.row0 + q * 32 + lane;
+            if (beta != 0.0) {  // pull this thread's part of the C row towards L2 while the MMAs run
+                const double* crow = p.C + (int64_t)row * p.ldc + tr.col0 + cbase;
+#pragma unroll
+                for (int j = 0; j < COLS; j += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + j));
+            }
+            if (tr.nkb > 0) {  // first sweep: H = ((P_6 2^-8 + P_5) 2^-8 + P_4) 2^-8 + P_3 -> scratch
+                mbar_wait(smem_u32(&bars[2 * STAGES]), uses & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-            double v[16];
-            if (NKB > 0) {
-                int r[S][16];
+                for (int c = 0; c < COLS / 16; ++c) {
+                    int r[S - S_HI][16];
 #pragma unroll
-                for (int g = 0; g < S; ++g)
-                    tmem_ld16(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(g * BN + c * 16), r[g]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    for (int g = 0; g < S - S_HI; ++g)
+                        tmem_ld16(tmem_base + lane_base + (unsigned)(g * BN + cbase + c * 16), r[g]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    double acc = (double)r[S - 1][j];
+                    for (int j = 0; j < 16; j += 2) {
+                        double h0 = (double)r[S - S_HI - 1][j], h1 = (double)r[S - S_HI - 1][j + 1];
 #pragma unroll
-                    for (int g = S - 2; g >= 0; --g) acc = fma(acc, 0.00390625, (double)r[g][j]);
-                    v[j] = acc * sa * __ldg(p.sb + col0 + c * 16 + j);
+                        for (int g = S - S_HI - 2; g >= 0; --g) {
+                            h0 = fma(h0, 0.00390625, (double)r[g][j]);
+                            h1 = fma(h1, 0.00390625, (double)r[g][j + 1]);
+                        }
+                        *reinterpret_cast<double2*>(scr + c * 16 + j) = make_double2(h0, h1);
+                    }
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.0;
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES + 1])) : "memory");
+                ++uses;
+                mbar_wait(smem_u32(&bars[2 * STAGES]), uses & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
-            const int64_t cc = col0 + c * 16;
-            if (beta != 0.0) {
-                const double2* src = reinterpret_cast<const double2*>(p.C + (int64_t)row * p.ldc + cc);
+            const double sa = p.sa[row] * p.alpha;
+#pragma unroll 1
+            for (int c = 0; c < COLS / 16; ++c) {  // second sweep: continue the Horner sum through P_2..P_0, scale, store
+                double v[16];
+                const int col = tr.col0 + cbase + c * 16;
+                if (tr.nkb > 0) {
+                    int r[S_HI][16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const double2 w = src[j];
-                    v[2 * j] = fma(beta, w.x, v[2 * j]);
-                    v[2 * j + 1] = fma(beta, w.y, v[2 * j + 1]);
+                    for (int g = 0; g < S_HI; ++g)
+                        tmem_ld16(tmem_base + lane_base + (unsigned)(g * BN + cbase + c * 16), r[g]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    if (c == COLS / 16 - 1) {  // every accumulator column of this warp is in registers: release TMEM now
+                        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0)
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES + 1])) : "memory");
+                        ++uses;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const double2 h = *reinterpret_cast<const double2*>(scr + c * 16 + j);
+                        double h0 = h.x, h1 = h.y;
+#pragma unroll
+                        for (int g = S_HI - 1; g >= 0; --g) {
+                            h0 = fma(h0, 0.00390625, (double)r[g][j]);
+                            h1 = fma(h1, 0.00390625, (double)r[g][j + 1]);
+                        }
+                        v[j] = h0 * sa * __ldg(p.sb + col + j);
+                        v[j + 1] = h1 * sa * __ldg(p.sb + col + j + 1);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.0;
                 }
-            }
-            double2* dst = reinterpret_cast<double2*>(p.D + (int64_t)row * p.ldd + cc);
+                if (beta != 0.0) {
+                    const double2* src = reinterpret_cast<const double2*>(p.C + (int64_t)row * p.ldc + col);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_double2(v[2 * j], v[2 * j + 1]);
-            if (p.D2 != nullptr) {
-                double2* dst2 = reinterpret_cast<double2*>(p.D2 + (int64_t)row * p.ldd2 + cc);
+                    for (int j = 0; j < 8; ++j) {
+                        const double2 w = src[j];
+                        v[2 * j] = fma(beta, w.x, v[2 * j]);
+                        v[2 * j + 1] = fma(beta, w.y, v[2 * j + 1]);
+                    }
+                }
+                double2* dst = reinterpret_cast<double2*>(p.D + (int64_t)row * p.ldd + col);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst2[j] = make_double2(v[2 * j], v[2 * j + 1]);
+                for (int j = 0; j < 8; ++j) dst[j] = make_double2(v[2 * j], v[2 * j + 1]);
+                if (p.D2 != nullptr) {
+                    double2* dst2 = reinterpret_cast<double2*>(p.D2 + (int64_t)row * p.ldd2 + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst2[j] = make_double2(v[2 * j], v[2 * j + 1]);
+                }
             }
         }
     }
@@ -476,16 +599,17 @@ EncodeFn get_encode() {
     return fn;
 }
 
-// planes[S][rows][K] int8: dims (k, row, plane), box (64, box_rows, S)
-int make_plane_map(CUtensorMap* m, const signed char* base, int64_t rows, int64_t K, int box_rows) {
+// planes[S][rows][K] int8: dims (k, row, plane), box (64, box_rows, box_planes)
+int make_plane_map(CUtensorMap* m, const signed char* base, int64_t rows, int64_t K, int box_rows, int box_planes) {
     EncodeFn enc = get_encode();
     if (!enc) return 1;
     const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)S};
     const cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)rows * (cuuint64_t)K};
-    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)box_rows, (cuuint32_t)S};
+    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<signed char*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 1;
 }
@@ -494,8 +618,8 @@ int make_plane_map(CUtensorMap* m, const signed char* base, int64_t rows, int64_
 // gemm_i8_release(): CUDA graphs captured by the callers keep the addresses they were recorded with.
 struct Workspace {
     signed char *qa = nullptr, *qb = nullptr;
-    double *sa = nullptr, *sb = nullptr;
-    size_t qa_cap = 0, qb_cap = 0, sa_cap = 0, sb_cap = 0;
+    double *sa = nullptr, *sb = nullptr, *scratch = nullptr;
+    size_t qa_cap = 0, qb_cap = 0, sa_cap = 0, sb_cap = 0, scratch_cap = 0;
     std::vector<void*> retired;
 };
 std::mutex g_ws_mutex;
@@ -522,7 +646,7 @@ void gemm_i8_release(cudaStream_t s) {
     auto it = g_ws.find({dev, s});
     if (it == g_ws.end()) return;
     Workspace& w = it->second;
-    for (void* p : {(void*)w.qa, (void*)w.qb, (void*)w.sa, (void*)w.sb})
+    for (void* p : {(void*)w.qa, (void*)w.qb, (void*)w.sa, (void*)w.sb, (void*)w.scratch})
         if (p) cudaFree(p);
     for (void* p : w.retired) cudaFree(p);
     g_ws.erase(it);
@@ -532,7 +656,7 @@ void gemm_i8_release(cudaStream_t s) {
 int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     const bool a_t = a.flags & GEMM_A_MMAJOR, b_t = a.flags & GEMM_B_NMAJOR;
     auto misaligned = [](const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) || (ld & 1); };
-    if (a.K % KB || a.K <= 0 || (!a_t && misaligned(a.A, a.lda)) || (!b_t && misaligned(a.B, a.ldb)) ||
+    if (a.M % BM || a.N % BN || a.K % 64 || a.K <= 0 || (!a_t && misaligned(a.A, a.lda)) || (!b_t && misaligned(a.B, a.ldb)) ||
         misaligned(a.D, a.ldd))
         return 1;
     if (a.beta != 0.0 && misaligned(a.C, a.ldc)) return 1;
@@ -546,19 +670,22 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
         w = &g_ws[{dev, s}];
     }
     const int chunks = (a.K + MAX_K - 1) / MAX_K;
-    const int Kc_max = ((a.K / KB + chunks - 1) / chunks) * KB;  // balanced chunks, multiples of 64
+    const int Kc_max = ((a.K / 64 + chunks - 1) / chunks) * 64;  // balanced chunks, multiples of 64
     GPB_TRY(grow(w->qa, w->qa_cap, (size_t)S * a.M * Kc_max, w->retired));
     GPB_TRY(grow(w->qb, w->qb_cap, (size_t)S * a.N * Kc_max, w->retired));
     GPB_TRY(grow(w->sa, w->sa_cap, sizeof(double) * 2 * a.M, w->retired));  // scales, then the 2^(55-e) multipliers
     GPB_TRY(grow(w->sb, w->sb_cap, sizeof(double) * 2 * a.N, w->retired));
     static bool configured_dev[64] = {};
+    static int sm_count[64] = {};
     if (!configured_dev[dev & 63]) {
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
         configured_dev[dev & 63] = true;
     }
     const int tm = a.M / BM, tn = a.N / BN;
-    const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) : (int64_t)tm * tn;
+    const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) / 2 : (int64_t)tm * tn;
+    const int grid = (int)std::min<int64_t>(tiles, sm_count[dev & 63]);
+    GPB_TRY(grow(w->scratch, w->scratch_cap, sizeof(double) * (size_t)grid * BM * BN, w->retired));
     for (int k0 = 0, c = 0; k0 < a.K; k0 += Kc_max, ++c) {
         const int Kc = std::min(Kc_max, a.K - k0);
         if (a_t) {
@@ -579,19 +706,16 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
             split_rows_kernel<<<a.N, 256, 0, s>>>(a.B + k0, a.ldb, Kc, k0, a.N, w->qb, w->sb, 1.0, a.flags, 1);
         }
         GPB_CUDA(cudaGetLastError());
-        CUtensorMap tmA, tmB;
-        if (make_plane_map(&tmA, w->qa, a.M, Kc, BM) || make_plane_map(&tmB, w->qb, a.N, Kc, BN)) {
+        CUtensorMap tmA, tmB, tmA_hi, tmB_hi;
+        if (make_plane_map(&tmA, w->qa, a.M, Kc, BM, S) || make_plane_map(&tmB, w->qb, a.N, Kc, BN, S) ||
+            make_plane_map(&tmA_hi, w->qa, a.M, Kc, BM, S_HI) || make_plane_map(&tmB_hi, w->qb, a.N, Kc, BN, S_HI)) {
             set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
             return -3;
         }
         static const int debug = getenv("GPB200_GEMM_I8_DEBUG") ? atoi(getenv("GPB200_GEMM_I8_DEBUG")) : 0;
         I8Args p{a.M, a.N, Kc, w->sa, w->sb, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2,
-                 a.alpha, c == 0 ? a.beta : 1.0, a.flags | (debug << 20), tm, tn, k0, a.K};
-        static const int use_ts = getenv("GPB200_GEMM_I8_TS") ? atoi(getenv("GPB200_GEMM_I8_TS")) : 0;
-        if (use_ts)
-            gemm_i8_kernel<true><<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
-        else
-            gemm_i8_kernel<false><<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
+                 a.alpha, c == 0 ? a.beta : 1.0, a.flags | (debug << 20), tm, tn, w->scratch, k0, a.K};
+        gemm_i8_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
         GPB_CUDA(cudaGetLastError());
         count_launch(3 + (a_t ? 1 : 0) + (b_t ? 1 : 0));
     }
@@ -601,7 +725,7 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
         } else {
             double kext = 0.0;
             for (int bi = 0; bi < tm; ++bi) {
-                const int ntile = (a.flags & GEMM_LOWER) ? 2 * (bi + 1) : tn;
+                const int ntile = (a.flags & GEMM_LOWER) ? bi + 1 : tn;
                 for (int bj = 0; bj < ntile; ++bj) {
                     int kb = 0, ke = a.K;
                     if (a.flags & GEMM_TRIK_A) kb = std::max(kb, bi * BM);
