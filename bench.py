@@ -216,7 +216,7 @@ def main():
         step_resident()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0, flops0 = eng.launch_count(), eng.gemm_flops()
+    launches0, flops0, flops_i8_0 = eng.launch_count(), eng.gemm_flops(), eng.gemm_flops_int8()
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -226,6 +226,7 @@ def main():
     wall_s = time.perf_counter() - t0
     launches = eng.launch_count() - launches0
     flops = eng.gemm_flops() - flops0
+    flops_i8 = eng.gemm_flops_int8() - flops_i8_0
     clocks = sampler.stop() if sampler else None
     dev_s = max_over_ranks(dev_ms * 1e-3)
     wall_s = max_over_ranks(wall_s)
@@ -254,13 +255,23 @@ def main():
     potrf_ms = 0.5 * (ph.get("grad.potrf", 0) + ph.get("fit.potrf", 0))
     chol_tf = (N_TRAIN**3 / 3) / (potrf_ms * 1e-3) / 1e12 if potrf_ms else None
     npad = (N_TRAIN + 127) // 128 * 128
-    # dominant kernel = dgemm_kernel (DMMA GEMM): algorithmic flops issued / time of the GEMM-only phases
+    # dominant kernel = gemm_i8_kernel: FP64 GEMMs executed as 28 exact int8 tensor-core products (csrc/gemm_i8.cu).
+    # Roofline: int8 operations executed on the tcgen05 pipe / CUDA-event time of the GEMM-only phases, against twice
+    # the MEASURED sustained bf16 rate (kind::i8 issues at twice the kind::f16 rate; MEASURED_PEAKS.json has no int8 entry).
     gemm_phase_ms = sum(ph.get(k, 0) for k in ("grad.potrf", "fit.potrf", "grad.trtri", "grad.lauum", "predict.trsm"))
     gemm_tf = (flops / args.steps) / (gemm_phase_ms * 1e-3) / 1e12 if gemm_phase_ms else None
+    int8_tops = 28.0 * (flops_i8 / args.steps) / (gemm_phase_ms * 1e-3) / 1e12 if gemm_phase_ms else None
     pred_tf = (m_loc * float(npad) ** 2) / (ph.get("predict.trsm", 1e30) * 1e-3) / 1e12
+    int8_peak, int8_src = 2 * 1397.2, "fallback: 2 x 1397.2 (bf16 sustained of this pool when MEASURED_PEAKS.json was written)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        int8_peak = 2.0 * float(mp["bf16_tflops_sustained"])
+        int8_src = "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 runs at twice the bf16 rate on tcgen05; sustained figure: timed inside a long step)"
+    except Exception:
+        pass
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r1.json"))).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_i8_traffic_r1.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
     line = {
@@ -271,9 +282,12 @@ def main():
         "e2e": {"value": m_total / e2e_s, "unit": UNIT, "step_s": e2e_s,
                 "h2d_bytes_per_step": int(m_loc * DIM * 8 + 3 * THETA.size * 8), "d2h_bytes_per_step": int(2 * m_loc * 8 + (THETA.size + 1) * 8)},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "dgemm_kernel (mma.sync m8n8k4 f64 -> DMMA.8x8x4)", "bound": "tensor", "achieved": gemm_tf, "peak": peak,
-                     "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": traffic, "peak_source": peak_src,
-                     "how": "algorithmic GEMM flops issued in the step / CUDA-event time of the GEMM-only phases (potrf x2, trtri, lauum, predict trsm) on the library stream"},
+        "roofline": {"kernel": "gemm_i8_kernel (tcgen05.mma kind::i8 -> UTCIMMA; 28 exact int8 products per FP64 product)",
+                     "bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TFLOP/s",
+                     "frac": (int8_tops / int8_peak) if int8_tops else None, "traffic": traffic, "peak_source": int8_src,
+                     "how": "28 x algorithmic FP64 GEMM flops issued on the INT8 path in the step / CUDA-event time of the GEMM-only phases (potrf x2, trtri, lauum, predict trsm; these also hold the short-k DMMA GEMMs and the diagonal-block kernels) on the library stream; traffic = ncu dram bytes of one 8192^3 launch",
+                     "fp64_equivalent": {"achieved": gemm_tf, "fp64_dmma_peak": peak, "ratio": (gemm_tf / peak) if gemm_tf else None,
+                                         "int8_share_of_gemm_flops": (flops_i8 / flops) if flops else None, "fp64_peak_source": peak_src}},
         "cholesky": {"seconds": potrf_ms * 1e-3, "tflops": chol_tf, "frac_of_fp64_peak": chol_tf / peak if chol_tf else None, "flops": "N^3/3"},
         "predict": {"tflops": pred_tf, "frac_of_fp64_peak": pred_tf / peak, "flops": "M N^2"},
         "phases_ms": {k: round(v, 3) for k, v in sorted(ph.items())},

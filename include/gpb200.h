@@ -44,7 +44,8 @@ enum { GPB_EI_VALUE = 0, GPB_EI_NEG_LOG = 1, GPB_EI_NEG_LOG_GRAD = 2 };
 const char* gpb_last_error(void);
 int gpb_device_count(int* count);
 int64_t gpb_launch_count(void);           /* kernels launched by this library so far (process-wide) */
-double gpb_gemm_flops(void);              /* algorithmic flops issued through the DMMA GEMM so far */
+double gpb_gemm_flops(void);              /* algorithmic FP64 flops issued through the GEMM kernels so far */
+double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-core path (each costs 28 int8 products) */
 
 int gpb_ctx_create(int device, gpb_ctx** out);
 void gpb_ctx_destroy(gpb_ctx* ctx);

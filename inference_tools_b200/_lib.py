@@ -25,6 +25,7 @@ SIGNATURES = {
     "gpb_device_count": (C.c_int, [_ip]),
     "gpb_launch_count": (C.c_int64, []),
     "gpb_gemm_flops": (C.c_double, []),
+    "gpb_gemm_flops_int8": (C.c_double, []),
     "gpb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_ctx_p)]),
     "gpb_ctx_destroy": (None, [_ctx_p]),
     "gpb_set_data": (C.c_int, [_ctx_p, _dp, C.c_int64, C.c_int, _dp, _dp, _dp]),
@@ -336,6 +337,9 @@ class Engine:
 
     def gemm_flops(self):
         return float(self.lib.gpb_gemm_flops())
+
+    def gemm_flops_int8(self):
+        return float(self.lib.gpb_gemm_flops_int8())
 
 
 def device_count() -> int:

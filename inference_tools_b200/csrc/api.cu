@@ -10,7 +10,8 @@ static int64_t g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 int64_t launch_count() { return g_launches; }
 double gemm_flops_issued();  // gemm_dmma.cu
-void credit_gemm_flops(double f);
+double gemm_flops_issued_i8();
+void credit_gemm_flops(double f, double f_i8);
 
 }  // namespace gpb
 
@@ -148,12 +149,12 @@ int run_graphed(gpb_ctx* c, const std::string& key, F&& body) {
     if (e.exec) {
         GPB_CUDA(cudaGraphLaunch(e.exec, c->s));
         count_launch((int)e.launches);
-        credit_gemm_flops(e.flops);
+        credit_gemm_flops(e.flops, e.flops_i8);
         return 0;
     }
     if (e.uses++ == 0) return body();
     const int64_t l0 = launch_count();
-    const double f0 = gemm_flops_issued();
+    const double f0 = gemm_flops_issued(), g0 = gemm_flops_issued_i8();
     GPB_CUDA(cudaStreamBeginCapture(c->s, cudaStreamCaptureModeThreadLocal));
     const int rc = body();
     cudaGraph_t g = nullptr;
@@ -167,6 +168,7 @@ int run_graphed(gpb_ctx* c, const std::string& key, F&& body) {
     }
     e.launches = launch_count() - l0;
     e.flops = gemm_flops_issued() - f0;
+    e.flops_i8 = gemm_flops_issued_i8() - g0;
     const cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
     cudaGraphDestroy(g);
     if (ie != cudaSuccess) {
@@ -233,6 +235,7 @@ int gpb_device_count(int* count) {
 
 int64_t gpb_launch_count(void) { return launch_count(); }
 double gpb_gemm_flops(void) { return gemm_flops_issued(); }
+double gpb_gemm_flops_int8(void) { return gemm_flops_issued_i8(); }
 
 int gpb_ctx_create(int device, gpb_ctx** out) {
     int count = 0;

@@ -90,7 +90,7 @@ struct gpb_ctx {
         cudaGraphExec_t exec = nullptr;
         int uses = 0;
         int64_t launches = 0;
-        double flops = 0.0;
+        double flops = 0.0, flops_i8 = 0.0;
     };
     std::map<std::string, GraphEntry> graphs;
     bool use_graphs = true;

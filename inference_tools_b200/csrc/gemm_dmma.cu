@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) dgemm_kernel(const Ge
 int gemm_nt_tma(const GemmArgs& a, cudaStream_t s, double* flops_out);  // gemm_tma.cu
 int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out);   // gemm_i8.cu
 
-static double g_gemm_flops = 0.0;
+static double g_gemm_flops = 0.0, g_gemm_flops_i8 = 0.0;  // all GEMM launches; the share issued on the INT8 path
 
 template <class C>
 int launch_cfg(const GemmArgs& a, cudaStream_t s) {
@@ -300,6 +300,7 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
         if (rc < 0) return rc;
         if (rc == 0) {
             g_gemm_flops += fl;
+            g_gemm_flops_i8 += fl;
             return 0;
         }
     }
@@ -326,6 +327,10 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
 }
 
 double gemm_flops_issued() { return g_gemm_flops; }
-void credit_gemm_flops(double f) { g_gemm_flops += f; }
+double gemm_flops_issued_i8() { return g_gemm_flops_i8; }
+void credit_gemm_flops(double f, double f_i8) {
+    g_gemm_flops += f;
+    g_gemm_flops_i8 += f_i8;
+}
 
 }  // namespace gpb

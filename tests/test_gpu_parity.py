@@ -661,3 +661,83 @@ def test_linear_inverter_argument_checks_and_failures():
     clone = pickle.loads(pickle.dumps(inv))
     th = np.full(inv.n_hyperpars, 0.3)
     assert clone.marginal_likelihood(th) == inv.marginal_likelihood(th)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FP64 GEMM on the INT8 tensor cores (csrc/gemm_i8.cu): the primitive under potrf / trsm / trtri / lauum for k >= 512
+def _gemm_impl(impl, A, B, C, alpha, beta, flags, M, N, K):
+    import ctypes
+    lib = _lib.load_library()
+    dp = ctypes.POINTER(ctypes.c_double)
+    ptr = lambda a: None if a is None else np.ascontiguousarray(a).ctypes.data_as(dp)
+    A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
+    D = np.zeros((M, N))
+    lib.gpb_test_gemm_impl.restype = ctypes.c_int
+    rc = lib.gpb_test_gemm_impl(impl, M, N, K, ptr(A), ptr(B), ptr(C), ctypes.c_double(alpha), ctypes.c_double(beta),
+                                flags, D.ctypes.data_as(dp), 0, None)
+    if rc:
+        raise RuntimeError(lib.gpb_last_error().decode())
+    return D
+
+
+@pytest.mark.parametrize("flags,name", [(0, "nt"), (32, "a_t"), (64, "b_t"), (96, "ab_t")])
+def test_int8_tensor_core_gemm_is_fp64_accurate(flags, name):
+    """D = C - A B^T for every operand layout; the error is measured against |A||B| + |C| like an FP64 dot product."""
+    rng = np.random.default_rng(7)
+    M, N, K = 384, 256, 704
+    A, B, C = rng.standard_normal((M, K)), rng.standard_normal((N, K)), rng.standard_normal((M, N))
+    ref = C - A @ B.T
+    den = np.abs(A) @ np.abs(B).T + np.abs(C)
+    D = _gemm_impl(1, A.T if flags & 32 else A, B.T if flags & 64 else B, C, -1.0, 1.0, flags, M, N, K)
+    # numpy's own FP64 result carries rounding of the same order, so the bound is a few ulp of |A||B| + |C|
+    assert (np.abs(D - ref) / den).max() < 1e-15
+    D0 = _gemm_impl(0, A.T if flags & 32 else A, B.T if flags & 64 else B, C, -1.0, 1.0, flags, M, N, K)
+    assert (np.abs(D0 - ref) / den).max() < 1e-15  # the dispatcher (DMMA at this size) meets the same bound
+    assert (np.abs(D - D0) / den).max() < 1e-15
+
+
+def test_int8_tensor_core_gemm_scaling_ranges_and_chunks():
+    rng = np.random.default_rng(8)
+    M, N, K = 256, 256, 1024
+    # rows of wildly different magnitude, zero rows, and a k extent beyond one int32-exact chunk
+    A = rng.standard_normal((M, K)) * np.exp(25 * rng.standard_normal((M, 1)))
+    B = rng.standard_normal((N, K)) * np.exp(25 * rng.standard_normal((N, 1)))
+    A[3] = 0.0
+    B[200] = 0.0
+    D = _gemm_impl(1, A, B, None, 1.0, 0.0, 0, M, N, K)
+    den = np.abs(A) @ np.abs(B).T
+    assert (np.abs(D - A @ B.T)[den > 0] / den[den > 0]).max() < 1e-15 and np.all(D[3] == 0) and np.all(D[:, 200] == 0)
+    K2 = 16384 + 2048
+    A, B = rng.standard_normal((128, K2)), rng.standard_normal((256, K2))
+    D = _gemm_impl(1, A, B, None, 2.0, 0.0, 0, 128, 256, K2)
+    assert (np.abs(D - 2 * A @ B.T) / (np.abs(A) @ np.abs(B).T)).max() < 1e-15
+    # elements far below their row maximum keep only the bits above 2^-55 of it: normwise, not componentwise, accuracy
+    A = rng.standard_normal((128, 512)) * np.exp(4 * rng.standard_normal((128, 512)))
+    B = rng.standard_normal((128, 512)) * np.exp(4 * rng.standard_normal((128, 512)))
+    D = _gemm_impl(1, A, B, None, 1.0, 0.0, 0, 128, 128, 512)
+    bound = 512 * np.abs(A).max(1)[:, None] * np.abs(B).max(1)[None, :]
+    assert (np.abs(D - A @ B.T) / bound).max() < 2e-16
+    # non-finite input poisons its row of the result instead of producing garbage digits
+    A = rng.standard_normal((128, 512))
+    A[5, 17] = np.nan
+    D = _gemm_impl(1, A, rng.standard_normal((128, 512)), None, 1.0, 0.0, 0, 128, 128, 512)
+    assert np.all(np.isnan(D[5])) and np.all(np.isfinite(np.delete(D, 5, axis=0)))
+
+
+def test_int8_tensor_core_gemm_triangular_ranges():
+    """The k ranges used by trtri (B stored K x N, zero for k < n; A lower triangular) and lauum (both transposed, lower
+    tiles only), with poison outside the ranges the kernels may read."""
+    rng = np.random.default_rng(9)
+    n = 640
+    W = np.tril(rng.standard_normal((n, n)))
+    L = rng.standard_normal((n, n))
+    D = _gemm_impl(1, L, W, None, 1.0, 0.0, 64 | 4, n, n, n)
+    assert np.abs(D - L @ W).max() < 1e-12
+    T = rng.standard_normal((n, n))
+    Wp = W.copy()
+    for i in range(n):
+        Wp[i, (i // 128 + 1) * 128:] = 1e30  # beyond the row's 128-block: must never be read with GEMM_TRIL_A
+    D = _gemm_impl(1, Wp, T, None, -1.0, 0.0, 64 | 16, n, n, n)
+    assert np.abs(D + W @ T).max() < 1e-12
+    D = _gemm_impl(1, W, W, None, 1.0, 0.0, 32 | 64 | 2 | 4 | 1, n, n, n)
+    assert np.abs(np.tril(D - W.T @ W)).max() < 1e-12
