@@ -11,10 +11,10 @@
 //      P_g = sum_{s+t=g} A_s B_t^T.  A persistent CTA owns 128 x 128 tiles of D; one tcgen05.mma is 128 x 128 x 32,
 //      the smallest shape that runs at the full 8192 MAC/clk/SM from shared memory (N = 64 is limited to 2/3 of it by
 //      shared-memory bandwidth: tools/umma_probe.cu).  TMEM holds four 128-column int32 accumulators, so a tile takes
-//      two sweeps over k: first P_4..P_6 (18 products, all 7 + 7 planes per k-block), then P_0..P_3 (10 products,
-//      planes 0..3).  Every k-block of planes is fetched by ONE 3-D TMA box per operand and feeds 18 (10) MMA pairs:
-//      ~50 bytes of L2->shared traffic per MMA clock instead of ~190 for a plain int8 GEMM of this tile.
-//      Warp 0 is the TMA producer (two 112 KB stages), warp 1 issues the MMAs (one elected lane), warps 2-5 drain
+//      two sweeps over k: first P_3..P_6 (22 products, all 7 + 7 planes per k-block), then P_0..P_2 (6 products,
+//      planes 0..2).  Every k-block of planes is fetched by ONE 3-D TMA box per operand and feeds 22 (6) MMA pairs:
+//      ~45 bytes of L2->shared traffic per MMA clock instead of ~190 for a plain int8 GEMM of this tile.
+//      Warp 0 is the TMA producer (four 56 KB slots), warp 1 issues the MMAs (one elected lane), warps 2-9 drain
 //      the accumulators (tcgen05.ld), combine them smallest-first in FP64 (Horner in 2^-8; the first sweep's
 //      partial sum waits in a per-CTA scratch row) and apply the row / column scales, alpha and beta.
 //
