@@ -583,10 +583,6 @@ int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int
 int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* info) {
     GPB_TRY(use(c));
     GPB_TRY(need_model(c));
-    if (c->n_regions && grad) {
-        set_error("gpb_loo: the leave-one-out gradient is not implemented for ChangePoint kernels");
-        return -3;
-    }
     c->timer.reset();
     const size_t np = (size_t)c->npad;
     const int npad = (int)c->npad, n = (int)c->n, nt = c->n_mean + c->n_cov;
@@ -612,8 +608,15 @@ int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* inf
     c->timer.mark("loo");
     // the factor (Kwork) and W are dead from here on: reuse them as the dK plane and the product buffer
     GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2), c->s));
+    const double* dK_all = nullptr;
+    if (c->n_regions && grad) {  // ChangePoint models: dense gradient planes from the generic kernel (small N by nature)
+        const size_t plane = (size_t)n * n;
+        GPB_TRY(ensure(c->S, c->S_cap, sizeof(double) * plane * (c->n_cov + 1)));
+        GPB_TRY(launch_assemble_grads(cp, c->x, n, c->S, c->S + plane, c->s));
+        dK_all = c->S + plane;
+    }
     GPB_TRY(launch_loo(cp, mp, c->n_mean, c->x, n, npad, c->alpha_work, c->Kinv, npad, c->partials, c->Kwork, c->W,
-                       c->scal, grad ? c->grad_dev : nullptr, c->s));
+                       c->scal, grad ? c->grad_dev : nullptr, dK_all, c->n_cov, c->s));
     double val = 0.0;
     GPB_CUDA(cudaMemcpyAsync(&val, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->s));
     if (grad) GPB_CUDA(cudaMemcpyAsync(grad, c->grad_dev, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->s));

@@ -85,6 +85,6 @@ int launch_loo_predictions(const double* Kinv, int64_t ld, const double* alpha, 
                            double* sigma, cudaStream_t s);
 int launch_loo(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad,
                const double* alpha, double* Kinv, int64_t ld, double* ws, double* Dk, double* T, double* val_dev,
-               double* grad_dev, cudaStream_t s);
+               double* grad_dev, const double* dK_all, int n_cov, cudaStream_t s);
 
 }  // namespace gpb

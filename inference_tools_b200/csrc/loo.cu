@@ -188,10 +188,12 @@ int launch_loo_predictions(const double* Kinv, int64_t ld, const double* alpha, 
     return 0;
 }
 
-// ws: 5 vectors of npad doubles (var, c1, c2, t1, t2); Dk, T: npad x npad scratch (only when grad_dev != nullptr)
+// ws: 5 vectors of npad doubles (var, c1, c2, t1, t2); Dk, T: npad x npad scratch (only when grad_dev != nullptr).
+// dK_all (n_cov dense n x n planes from launch_assemble_grads) is only used for models with a ChangePoint: there the
+// per-parameter planes come from the generic gradient kernel instead of dk_plane_kernel.
 int launch_loo(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad,
                const double* alpha, double* Kinv, int64_t ld, double* ws, double* Dk, double* T, double* val_dev,
-               double* grad_dev, cudaStream_t s) {
+               double* grad_dev, const double* dK_all, int n_cov, cudaStream_t s) {
     double *var = ws, *c1 = ws + npad, *c2 = ws + 2 * (size_t)npad, *t1 = ws + 3 * (size_t)npad, *t2 = ws + 4 * (size_t)npad;
     loo_terms_kernel<<<1, 1024, 0, s>>>(Kinv, ld, alpha, n, npad, var, c1, c2, val_dev);
     GPB_LAUNCH_OK();
@@ -205,6 +207,21 @@ int launch_loo(const CovParams& cp, const MeanParams& mp, int n_theta_mean, cons
         GPB_TRY(launch_row_dot(Kinv, ld, n, npad, t1, t2, s));
         loo_grad_reduce_kernel<<<1, 1024, 0, s>>>(c1, c2, t2, nullptr, n, 1.0, grad_dev + p);
         GPB_LAUNCH_OK();
+    }
+    if (cp.n_regions) {  // regression.py:497-523 with dK_p = covariance_and_gradients planes, one GEMM Kinv dK_p each
+        for (int p = 0; p < n_cov; ++p) {
+            GPB_CUDA(cudaMemsetAsync(Dk, 0, sizeof(double) * (size_t)npad * ld, s));
+            GPB_CUDA(cudaMemcpy2DAsync(Dk, sizeof(double) * ld, dK_all + (size_t)p * n * n, sizeof(double) * n,
+                                       sizeof(double) * n, n, cudaMemcpyDeviceToDevice, s));
+            GemmArgs gm{npad, npad, npad, Kinv, ld, Dk, ld, nullptr, 0, T, ld, nullptr, 0, 1.0, 0.0, GEMM_FULL};
+            GPB_TRY(gemm_nt(gm, s));
+            GPB_TRY(launch_row_dot(T, ld, n, npad, alpha, t1, s));
+            rowdot2_kernel<<<(n + 7) / 8, 256, 0, s>>>(T, Kinv, ld, n, npad, nullptr, t2);
+            GPB_LAUNCH_OK();
+            loo_grad_reduce_kernel<<<1, 1024, 0, s>>>(c1, c2, t1, t2, n, 1.0, grad_dev + n_theta_mean + p);
+            GPB_LAUNCH_OK();
+        }
+        return 0;
     }
     for (int c = 0; c < cp.ncomp; ++c) {
         double* g = grad_dev + n_theta_mean + cp.theta_off[c];

@@ -254,8 +254,8 @@ def main():
     case(gp, "rqwhite_d5_n1024_const", 26, 1024, 5, ("RQ", "WHITE"), "const", m_query=256)
     case(gp, "se_d2_n700_linear", 27, 700, 2, ("SE",), "linear", m_query=128)
     # ChangePoint kernels (covariance.py:371-605)
-    case(gp, "cp_sese_d1_n40_const", 41, 40, 1, (("CP", 0, (("SE",), ("SE",))),), "const", store_k=True)
-    case(gp, "cp_serq_white_d2_n36_linear", 42, 36, 2, (("CP", 1, (("SE",), ("RQ",))), "WHITE"), "linear", store_k=True)
+    case(gp, "cp_sese_d1_n40_const", 41, 40, 1, (("CP", 0, (("SE",), ("SE",))),), "const", store_k=True, loo=True)
+    case(gp, "cp_serq_white_d2_n36_linear", 42, 36, 2, (("CP", 1, (("SE",), ("RQ",))), "WHITE"), "linear", store_k=True, loo=True)
     case(gp, "cp_sesese_d1_n48_const", 43, 48, 1, (("CP", 0, (("SE",), ("SE",), ("SE",))),), "const", store_k=True)
     case(gp, "cp_sese_d3_n300_const", 44, 300, 3, (("CP", 2, (("SE",), ("SE",))),), "const")
     # GpLinearInverter (inversion.py)
