@@ -92,12 +92,21 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
             : "memory");
     } while (!done);
 }
+template <int CTAS>
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
-            "r"(dst),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-        : "memory");
+    if (CTAS == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+                "r"(dst),
+            "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+            : "memory");
+    } else {  // executed by both CTAs of the pair; the transaction bytes are credited to the leader's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+                "r"(dst),
+            "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar & 0xFEFFFFFFu)
+            : "memory");
+    }
 }
 // shared-memory matrix descriptor: k-major tile of 64-byte rows, 64-byte swizzle (8-row atoms of 512 bytes)
 __device__ __forceinline__ uint64_t smem_desc(unsigned addr) {
@@ -105,18 +114,30 @@ __device__ __forceinline__ uint64_t smem_desc(unsigned addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((8 * KB) >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)(KB == 64 ? 4 : 6) << 61);
 }
-// instruction descriptor: D = s32, A = B = signed 8-bit, both k-major, N = 64, M = 128
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
+// instruction descriptor: D = s32, A = B = signed 8-bit, both k-major, N = 128, M = 128 per CTA of the group
+template <int CTAS>
 __device__ __forceinline__ void mma_i8(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
-        : "memory");
+    constexpr uint32_t idesc =
+        (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
+    if (CTAS == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+            : "memory");
+    }
 }
 // one lane of a converged warp (the compiler keeps tcgen05 instructions under this predicate branch-free)
 __device__ __forceinline__ bool elect_one() {
@@ -131,8 +152,37 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// arrives on `bar` when every MMA issued so far has completed; with a CTA pair, on the same barrier of both CTAs
+template <int CTAS>
 __device__ __forceinline__ void mma_commit(unsigned bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+    if (CTAS == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .b16 m;\n"
+            "mov.b16 m, 3;\n"
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+            "}\n" ::"r"(bar)
+            : "memory");
+    }
+}
+// plain arrival on a barrier of CTA `cta` of the cluster (same shared-memory offset)
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned bar, unsigned cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, int (&r)[16]) {
     asm volatile(
@@ -146,14 +196,25 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int (&r)[16]) {
 struct TileRange {
     int row0, col0, k_begin, nkb;
 };
+// tile t of the launch: CTAS * 128 rows x 128 columns
+template <int CTAS>
 __device__ __forceinline__ TileRange tile_range(const I8Args& p, int t) {
+    constexpr int BMT = BM * CTAS;
     int bi, bj;
-    if (p.flags & GEMM_LOWER) {  // tiles with bj <= bi, row-block major
-        int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while (r * (r + 1) / 2 > t) --r;
-        while ((r + 1) * (r + 2) / 2 <= t) ++r;
-        bi = r;
-        bj = t - r * (r + 1) / 2;
+    if (p.flags & GEMM_LOWER) {  // tiles that touch the lower triangle, row-block major
+        if (CTAS == 1) {         // bj <= bi
+            int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+            while (r * (r + 1) / 2 > t) --r;
+            while ((r + 1) * (r + 2) / 2 <= t) ++r;
+            bi = r;
+            bj = t - r * (r + 1) / 2;
+        } else {                 // 256-row blocks: bj <= 2 bi + 1
+            int r = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
+            while (r * (r + 1) > t) --r;
+            while ((r + 1) * (r + 2) <= t) ++r;
+            bi = r;
+            bj = t - r * (r + 1);
+        }
     } else {  // groups of RASTER row-blocks sweep the columns together (their B planes stay in L2)
         const int per_group = RASTER * p.tiles_n;
         const int grp = t / per_group, r = t - grp * per_group;
@@ -162,13 +223,13 @@ __device__ __forceinline__ TileRange tile_range(const I8Args& p, int t) {
         bi = grp * RASTER + (r - bj * rows_in);
     }
     TileRange tr;
-    tr.row0 = bi * BM;
+    tr.row0 = bi * BMT;
     tr.col0 = bj * BN;
     int k_begin = 0, k_end = p.k_total;  // in the full k extent, then clipped to this launch's chunk
     if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, tr.row0);
     if (p.flags & GEMM_TRIK_B) k_begin = max(k_begin, tr.col0);
     if (p.flags & GEMM_TRIL_B) k_end = min(k_end, tr.col0 + BN);
-    if (p.flags & GEMM_TRIL_A) k_end = min(k_end, tr.row0 + BM);
+    if (p.flags & GEMM_TRIL_A) k_end = min(k_end, tr.row0 + BMT);
     k_begin = max(k_begin, p.k_off) - p.k_off;
     k_end = min(k_end, p.k_off + p.K) - p.k_off;
     tr.k_begin = k_begin;
@@ -176,8 +237,9 @@ __device__ __forceinline__ TileRange tile_range(const I8Args& p, int t) {
     return tr;
 }
 
-// issue the MMAs of one k-block for the diagonals [G0, G1]: accumulator g - G0 lives at TMEM columns (g - G0) * BN
-template <int G0, int G1>
+// issue the MMAs of one k-block for the diagonals [G0, G1]: accumulator g - G0 lives at TMEM columns (g - G0) * BN.
+// B planes are BN / CTAS rows each in this CTA's shared memory (a CTA pair splits the columns of the tile).
+template <int CTAS, int G0, int G1>
 __device__ __forceinline__ void issue_kblock(unsigned tmem_base, unsigned a_base, unsigned b_base, int kb) {
 #pragma unroll
     for (int ks = 0; ks < KB / 32; ++ks) {
@@ -187,14 +249,19 @@ __device__ __forceinline__ void issue_kblock(unsigned tmem_base, unsigned a_base
 #pragma unroll
             for (int t = 0; t <= G1 - s; ++t) {
                 if (s + t < G0) continue;
-                const uint64_t bdesc = smem_desc(b_base + t * B_PLANE + ks * 32);
+                const uint64_t bdesc = smem_desc(b_base + t * (B_PLANE / CTAS) + ks * 32);
                 // the first product into each accumulator (s = 0 of the first k-step) overwrites it
-                mma_i8(tmem_base + (unsigned)((s + t - G0) * BN), adesc, bdesc, (unsigned)((kb | ks | s) != 0));
+                mma_i8<CTAS>(tmem_base + (unsigned)((s + t - G0) * BN), adesc, bdesc, (unsigned)((kb | ks | s) != 0));
             }
         }
     }
 }
 
+// CTAS = 1: one CTA per 128 x 128 tile.  CTAS = 2: a cluster of two CTAs (cta_group::2) per 256 x 128 tile -- each CTA
+// stages its own 128 rows of A and HALF of the B planes, the leader issues M = 256 MMAs that read both halves, and each
+// CTA's TMEM receives its 128 rows of the accumulators: per MMA a CTA reads 6 KB of shared memory instead of 8 KB and
+// fills 25 % less of it, which takes the kernel off the shared-memory bandwidth limit.
+template <int CTAS>
 __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmA_hi,
@@ -203,34 +270,56 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
     extern __shared__ unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + STAGES * STAGE_BYTES);
-    // bars[0..STAGES) stage full, [STAGES..2 STAGES) stage empty, then accumulators ready, accumulators drained
+    // bars[0..STAGES) slot full, [STAGES..2 STAGES) slot empty, then accumulators ready, accumulators drained
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 12);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned rank = 0;  // CTA within the pair; the leader (0) owns the full / drained barriers and issues the MMAs
+    if (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+    const int unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;  // CTA (pair) index: the tile scheduler's lane
+    constexpr int B_ROWS = BN / CTAS;                                 // B rows staged by this CTA
+    constexpr int B_BYTES_CTA = B_BYTES / CTAS, HI_B_BYTES = HI_BYTES / CTAS;
+
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 2 * STAGES + 1; ++i) mbar_init(smem_u32(&bars[i]), 1);
-        mbar_init(smem_u32(&bars[2 * STAGES + 1]), EPI_WARPS);  // one arrival per epilogue warp
+        for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(&bars[i]), CTAS);  // one arrival per producer of the pair
+#pragma unroll
+        for (int i = STAGES; i < 2 * STAGES + 1; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_init(smem_u32(&bars[2 * STAGES + 1]), CTAS * EPI_WARPS);  // one arrival per epilogue warp of the pair
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    if (CTAS == 2) cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        if (CTAS == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
 
-    if (warp == 0) {  // ---- TMA producer: converged warp, one elected lane issues
+    if (warp == 0) {  // ---- TMA producer (both CTAs of a pair): converged warp, one elected lane issues
         int it = 0;  // slots handed out so far
         auto acquire = [&](int i) {  // wait until the MMAs that read slot use i - STAGES have completed
             if (i >= STAGES) mbar_wait(smem_u32(&bars[STAGES + i % STAGES]), ((i / STAGES) - 1) & 1);
         };
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const TileRange tr = tile_range(p, t);
+        // the leader announces the bytes of the whole pair; the other CTA only arrives (on the leader's barrier)
+        auto announce = [&](unsigned bar, unsigned bytes) {
+            if (rank == 0) mbar_expect_tx(bar, bytes * CTAS);
+            else mbar_arrive_cluster(bar, 0);
+        };
+        for (int t = unit; t < n_tiles; t += n_units) {
+            const TileRange tr = tile_range<CTAS>(p, t);
+            const int arow = tr.row0 + (int)rank * BM, brow = tr.col0 + (int)rank * B_ROWS;
             for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: A planes -> slot it, B planes -> slot it + 1
                 acquire(it);
                 acquire(it + 1);
@@ -238,13 +327,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                     const int k = tr.k_begin + kb * KB;
                     const unsigned bar_a = smem_u32(&bars[it % STAGES]), bar_b = smem_u32(&bars[(it + 1) % STAGES]);
                     if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {  // timing probe: MMA rate without the loads
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_a) : "memory");
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_b) : "memory");
+                        if (rank == 0) { mbar_arrive(bar_a); mbar_arrive(bar_b); }
+                        else { mbar_arrive_cluster(bar_a, 0); mbar_arrive_cluster(bar_b, 0); }
                     } else {
-                        mbar_expect_tx(bar_a, A_BYTES);
-                        tma_load_3d(smem_u32(tiles + (it % STAGES) * SLOT_BYTES), &tmA, k, tr.row0, 0, bar_a);
-                        mbar_expect_tx(bar_b, B_BYTES);
-                        tma_load_3d(smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), &tmB, k, tr.col0, 0, bar_b);
+                        announce(bar_a, A_BYTES);
+                        tma_load_3d<CTAS>(smem_u32(tiles + (it % STAGES) * SLOT_BYTES), &tmA, k, arow, 0, bar_a);
+                        announce(bar_b, B_BYTES_CTA);
+                        tma_load_3d<CTAS>(smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), &tmB, k, brow, 0, bar_b);
                     }
                 }
                 __syncwarp();
@@ -255,71 +344,76 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                     const int k = tr.k_begin + kb * KB;
                     const unsigned bar = smem_u32(&bars[it % STAGES]);
                     if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+                        if (rank == 0) mbar_arrive(bar);
+                        else mbar_arrive_cluster(bar, 0);
                     } else {
                         const unsigned dst = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
-                        mbar_expect_tx(bar, 2 * HI_BYTES);
-                        tma_load_3d(dst, &tmA_hi, k, tr.row0, 0, bar);
-                        tma_load_3d(dst + SLOT_B_OFF, &tmB_hi, k, tr.col0, 0, bar);
+                        announce(bar, HI_BYTES + HI_B_BYTES);
+                        tma_load_3d<CTAS>(dst, &tmA_hi, k, arow, 0, bar);
+                        tma_load_3d<CTAS>(dst + SLOT_B_OFF, &tmB_hi, k, brow, 0, bar);
                     }
                 }
                 __syncwarp();
             }
         }
-    } else if (warp == 1) {  // ---- MMA issuer: the whole warp walks the pipeline, one elected lane issues
-        int it = 0, uses = 0;
-        auto filled = [&](int i) { mbar_wait(smem_u32(&bars[i % STAGES]), (i / STAGES) & 1); };
-        auto drained = [&]() {  // the epilogue has read the previous sweep's accumulators
-            if (uses >= 1) {
-                mbar_wait(smem_u32(&bars[2 * STAGES + 1]), (uses - 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            }
-            ++uses;
-        };
-        const bool no_mma = p.flags & DEBUG_NO_MMA;  // timing probe: load rate without the MMAs
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const TileRange tr = tile_range(p, t);
-            if (tr.nkb == 0) continue;
-            drained();
-            for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: diagonals S_HI..6, accumulator g - S_HI
-                filled(it);
-                filled(it + 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const unsigned bar_a = smem_u32(&bars[STAGES + it % STAGES]), bar_b = smem_u32(&bars[STAGES + (it + 1) % STAGES]);
-                if (elect_one()) {
-                    if (no_mma) {
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_a) : "memory");
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_b) : "memory");
-                        if (kb == tr.nkb - 1)
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES])) : "memory");
-                    } else {
-                        issue_kblock<S_HI, S - 1>(tmem_base, smem_u32(tiles + (it % STAGES) * SLOT_BYTES),
-                                                  smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), kb);
-                        mma_commit(bar_a);  // both slots are free once these MMAs have read them
-                        mma_commit(bar_b);
-                        if (kb == tr.nkb - 1) mma_commit(smem_u32(&bars[2 * STAGES]));
-                    }
+    } else if (warp == 1) {  // ---- MMA issuer (leader CTA): the whole warp walks the pipeline, one elected lane issues
+        if (rank == 0) {
+            int it = 0, uses = 0;
+            auto filled = [&](int i) { mbar_wait(smem_u32(&bars[i % STAGES]), (i / STAGES) & 1); };
+            auto drained = [&]() {  // the epilogue warps (of both CTAs) have read the previous sweep's accumulators
+                if (uses >= 1) {
+                    mbar_wait(smem_u32(&bars[2 * STAGES + 1]), (uses - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
-                __syncwarp();
-            }
-            drained();
-            for (int kb = 0; kb < tr.nkb; ++kb, ++it) {  // second sweep: diagonals 0..S_HI-1
-                filled(it);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const unsigned bar = smem_u32(&bars[STAGES + it % STAGES]);
-                if (elect_one()) {
-                    if (no_mma) {
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-                        if (kb == tr.nkb - 1)
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES])) : "memory");
-                    } else {
-                        const unsigned base = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
-                        issue_kblock<0, S_HI - 1>(tmem_base, base, base + SLOT_B_OFF, kb);
-                        mma_commit(bar);
-                        if (kb == tr.nkb - 1) mma_commit(smem_u32(&bars[2 * STAGES]));
+                ++uses;
+            };
+            const bool no_mma = p.flags & DEBUG_NO_MMA;  // timing probe: load rate without the MMAs
+            auto release = [&](unsigned bar) {           // no-MMA probe: free a barrier in every CTA of the pair
+                mbar_arrive(bar);
+                if (CTAS == 2) mbar_arrive_cluster(bar, 1);
+            };
+            for (int t = unit; t < n_tiles; t += n_units) {
+                const TileRange tr = tile_range<CTAS>(p, t);
+                if (tr.nkb == 0) continue;
+                drained();
+                for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: diagonals S_HI..6, accumulator g - S_HI
+                    filled(it);
+                    filled(it + 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const unsigned bar_a = smem_u32(&bars[STAGES + it % STAGES]), bar_b = smem_u32(&bars[STAGES + (it + 1) % STAGES]);
+                    if (elect_one()) {
+                        if (no_mma) {
+                            release(bar_a);
+                            release(bar_b);
+                            if (kb == tr.nkb - 1) release(smem_u32(&bars[2 * STAGES]));
+                        } else {
+                            issue_kblock<CTAS, S_HI, S - 1>(tmem_base, smem_u32(tiles + (it % STAGES) * SLOT_BYTES),
+                                                            smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), kb);
+                            mma_commit<CTAS>(bar_a);  // both slots are free once these MMAs have read them
+                            mma_commit<CTAS>(bar_b);
+                            if (kb == tr.nkb - 1) mma_commit<CTAS>(smem_u32(&bars[2 * STAGES]));
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
+                drained();
+                for (int kb = 0; kb < tr.nkb; ++kb, ++it) {  // second sweep: diagonals 0..S_HI-1
+                    filled(it);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const unsigned bar = smem_u32(&bars[STAGES + it % STAGES]);
+                    if (elect_one()) {
+                        if (no_mma) {
+                            release(bar);
+                            if (kb == tr.nkb - 1) release(smem_u32(&bars[2 * STAGES]));
+                        } else {
+                            const unsigned base = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
+                            issue_kblock<CTAS, 0, S_HI - 1>(tmem_base, base, base + SLOT_B_OFF, kb);
+                            mma_commit<CTAS>(bar);
+                            if (kb == tr.nkb - 1) mma_commit<CTAS>(smem_u32(&bars[2 * STAGES]));
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else {  // ---- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; two warps per quarter split the columns
@@ -329,17 +423,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
         const unsigned lane_base = (unsigned)(q * 32) << 16;
         double* scr = p.scratch + ((size_t)blockIdx.x * BM + q * 32 + lane) * BN + cbase;
         const double beta = p.beta;
+        const unsigned bar_ready = smem_u32(&bars[2 * STAGES]), bar_drained = smem_u32(&bars[2 * STAGES + 1]);
+        auto release_tmem = [&]() {  // this warp's accumulator columns are in registers
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (CTAS == 1) mbar_arrive(bar_drained);
+                else mbar_arrive_cluster(bar_drained, 0);
+            }
+        };
         int uses = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const TileRange tr = tile_range(p, t);
-            const int row = tr.row0 + q * 32 + lane;
+        for (int t = unit; t < n_tiles; t += n_units) {
+            const TileRange tr = tile_range<CTAS>(p, t);
+            const int row = tr.row0 + (int)rank * BM + q * 32 + lane;
             if (beta != 0.0) {  // pull this thread's part of the C row towards L2 while the MMAs run
                 const double* crow = p.C + (int64_t)row * p.ldc + tr.col0 + cbase;
 #pragma unroll
                 for (int j = 0; j < COLS; j += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + j));
             }
             if (tr.nkb > 0) {  // first sweep: H = ((P_6 2^-8 + P_5) 2^-8 + P_4) 2^-8 + P_3 -> scratch
-                mbar_wait(smem_u32(&bars[2 * STAGES]), uses & 1);
+                mbar_wait(bar_ready, uses & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
                 for (int c = 0; c < COLS / 16; ++c) {
@@ -348,6 +451,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                     for (int g = 0; g < S - S_HI; ++g)
                         tmem_ld16(tmem_base + lane_base + (unsigned)(g * BN + cbase + c * 16), r[g]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    if (c == COLS / 16 - 1) release_tmem();
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
                         double h0 = (double)r[S - S_HI - 1][j], h1 = (double)r[S - S_HI - 1][j + 1];
@@ -359,12 +463,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                         *reinterpret_cast<double2*>(scr + c * 16 + j) = make_double2(h0, h1);
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                __syncwarp();
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES + 1])) : "memory");
                 ++uses;
-                mbar_wait(smem_u32(&bars[2 * STAGES]), uses & 1);
+                mbar_wait(bar_ready, uses & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
             const double sa = p.sa[row] * p.alpha;
@@ -378,11 +478,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                     for (int g = 0; g < S_HI; ++g)
                         tmem_ld16(tmem_base + lane_base + (unsigned)(g * BN + cbase + c * 16), r[g]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                    if (c == COLS / 16 - 1) {  // every accumulator column of this warp is in registers: release TMEM now
-                        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0)
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bars[2 * STAGES + 1])) : "memory");
+                    if (c == COLS / 16 - 1) {
+                        release_tmem();
                         ++uses;
                     }
 #pragma unroll
@@ -422,20 +519,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();  // nobody leaves while its peer may still signal it
     if (warp == 1) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (CTAS == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
 // valid k range [k_lo, k_hi) of an operand row, local to the chunk [k_off, k_off + K) of the full k extent.
-// which = 0: rows of A (tile height 128), 1: rows of B (tile height 64) -- the triangular flags are per tile.
+// which = 0: rows of B (tile width 128); otherwise rows of A and `which` is the tile height (128, or 256 for a CTA
+// pair) -- the triangular flags are per tile.
 __device__ __forceinline__ void row_k_range(int row, int flags, int which, int k_off, int K, int& k_lo, int& k_hi) {
     int lo = 0, hi = k_off + K;
-    if (which == 0) {
-        if (flags & GEMM_TRIK_A) lo = (row / BM) * BM;
-        if (flags & GEMM_TRIL_A) hi = min(hi, (row / BM + 1) * BM);
+    if (which != 0) {
+        if (flags & GEMM_TRIK_A) lo = (row / which) * which;
+        if (flags & GEMM_TRIL_A) hi = min(hi, (row / which + 1) * which);
     } else {
         if (flags & GEMM_TRIK_B) lo = (row / BN) * BN;
         if (flags & GEMM_TRIL_B) hi = min(hi, (row / BN + 1) * BN);
@@ -678,64 +779,91 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     static bool configured_dev[64] = {};
     static int sm_count[64] = {};
     if (!configured_dev[dev & 63]) {
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         GPB_CUDA(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
         configured_dev[dev & 63] = true;
     }
-    const int tm = a.M / BM, tn = a.N / BN;
-    const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) / 2 : (int64_t)tm * tn;
-    const int grid = (int)std::min<int64_t>(tiles, sm_count[dev & 63]);
+    // CTA pairs (256 x 128 tiles, GPB200_GEMM_I8_PAIR=1): measured on B200 at 8192^3 the pair kernel's MMA side is
+    // faster (8.1 ms vs 9.2 ms with the loads switched off: the shared-memory relief works) but its load side is twice
+    // as slow (11.5 ms vs 5.9 ms with the MMAs switched off: the slot hand-shake through the leader's barrier has
+    // ~4 us of latency and only 2-4 k-blocks fit in flight), so the whole kernel loses: 89 vs 105 TF/s.  Off by default.
+    static const int pair_env = getenv("GPB200_GEMM_I8_PAIR") ? atoi(getenv("GPB200_GEMM_I8_PAIR")) : 0;
+    const int ctas = (pair_env && a.M % (2 * BM) == 0) ? 2 : 1;
+    const int bmt = BM * ctas;
+    const int tm = a.M / bmt, tn = a.N / BN;
+    const int64_t tiles = (a.flags & GEMM_LOWER) ? (ctas == 2 ? (int64_t)tm * (tm + 1) : (int64_t)tm * (tm + 1) / 2)
+                                                 : (int64_t)tm * tn;
+    const int units = (int)std::min<int64_t>(tiles, sm_count[dev & 63] / ctas);
+    const int grid = units * ctas;
     GPB_TRY(grow(w->scratch, w->scratch_cap, sizeof(double) * (size_t)grid * BM * BN, w->retired));
     for (int k0 = 0, c = 0; k0 < a.K; k0 += Kc_max, ++c) {
         const int Kc = std::min(Kc_max, a.K - k0);
         if (a_t) {
             const double* X = a.A + (int64_t)k0 * a.lda;
-            split_cols_max_kernel<<<a.M / 64, 256, 0, s>>>(X, a.lda, Kc, k0, w->sa, w->sa + a.M, 1.0 / 16384.0, a.flags, 0);
+            split_cols_max_kernel<<<a.M / 64, 256, 0, s>>>(X, a.lda, Kc, k0, w->sa, w->sa + a.M, 1.0 / 16384.0, a.flags, bmt);
             split_cols_digits_kernel<<<dim3(a.M / 64, Kc / 64), 256, 0, s>>>(X, a.lda, Kc, k0, a.M, w->qa, w->sa + a.M,
-                                                                             a.flags, 0);
+                                                                             a.flags, bmt);
         } else {
-            split_rows_kernel<<<a.M, 256, 0, s>>>(a.A + k0, a.lda, Kc, k0, a.M, w->qa, w->sa, 1.0 / 16384.0, a.flags, 0);
+            split_rows_kernel<<<a.M, 256, 0, s>>>(a.A + k0, a.lda, Kc, k0, a.M, w->qa, w->sa, 1.0 / 16384.0, a.flags, bmt);
         }
         GPB_CUDA(cudaGetLastError());
         if (b_t) {
             const double* X = a.B + (int64_t)k0 * a.ldb;
-            split_cols_max_kernel<<<a.N / 64, 256, 0, s>>>(X, a.ldb, Kc, k0, w->sb, w->sb + a.N, 1.0, a.flags, 1);
+            split_cols_max_kernel<<<a.N / 64, 256, 0, s>>>(X, a.ldb, Kc, k0, w->sb, w->sb + a.N, 1.0, a.flags, 0);
             split_cols_digits_kernel<<<dim3(a.N / 64, Kc / 64), 256, 0, s>>>(X, a.ldb, Kc, k0, a.N, w->qb, w->sb + a.N,
-                                                                             a.flags, 1);
+                                                                             a.flags, 0);
         } else {
-            split_rows_kernel<<<a.N, 256, 0, s>>>(a.B + k0, a.ldb, Kc, k0, a.N, w->qb, w->sb, 1.0, a.flags, 1);
+            split_rows_kernel<<<a.N, 256, 0, s>>>(a.B + k0, a.ldb, Kc, k0, a.N, w->qb, w->sb, 1.0, a.flags, 0);
         }
         GPB_CUDA(cudaGetLastError());
         CUtensorMap tmA, tmB, tmA_hi, tmB_hi;
-        if (make_plane_map(&tmA, w->qa, a.M, Kc, BM, S) || make_plane_map(&tmB, w->qb, a.N, Kc, BN, S) ||
-            make_plane_map(&tmA_hi, w->qa, a.M, Kc, BM, S_HI) || make_plane_map(&tmB_hi, w->qb, a.N, Kc, BN, S_HI)) {
+        if (make_plane_map(&tmA, w->qa, a.M, Kc, BM, S) || make_plane_map(&tmB, w->qb, a.N, Kc, BN / ctas, S) ||
+            make_plane_map(&tmA_hi, w->qa, a.M, Kc, BM, S_HI) || make_plane_map(&tmB_hi, w->qb, a.N, Kc, BN / ctas, S_HI)) {
             set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
             return -3;
         }
         static const int debug = getenv("GPB200_GEMM_I8_DEBUG") ? atoi(getenv("GPB200_GEMM_I8_DEBUG")) : 0;
         I8Args p{a.M, a.N, Kc, w->sa, w->sb, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2,
                  a.alpha, c == 0 ? a.beta : 1.0, a.flags | (debug << 20), tm, tn, w->scratch, k0, a.K};
-        gemm_i8_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
+        if (ctas == 1) {
+            gemm_i8_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
+        } else {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(THREADS);
+            cfg.dynamicSmemBytes = SMEM_BYTES;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const int nt = (int)tiles;
+            GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+        }
         GPB_CUDA(cudaGetLastError());
         count_launch(3 + (a_t ? 1 : 0) + (b_t ? 1 : 0));
     }
     if (flops_out) {
         if (!(a.flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) {
-            *flops_out = (double)tiles * 2.0 * BM * BN * a.K;
+            *flops_out = (double)tiles * 2.0 * bmt * BN * a.K;
         } else {
             double kext = 0.0;
             for (int bi = 0; bi < tm; ++bi) {
-                const int ntile = (a.flags & GEMM_LOWER) ? bi + 1 : tn;
+                const int ntile = (a.flags & GEMM_LOWER) ? (ctas == 2 ? 2 * bi + 2 : bi + 1) : tn;
                 for (int bj = 0; bj < ntile; ++bj) {
                     int kb = 0, ke = a.K;
-                    if (a.flags & GEMM_TRIK_A) kb = std::max(kb, bi * BM);
+                    if (a.flags & GEMM_TRIK_A) kb = std::max(kb, bi * bmt);
                     if (a.flags & GEMM_TRIK_B) kb = std::max(kb, bj * BN);
                     if (a.flags & GEMM_TRIL_B) ke = std::min(ke, bj * BN + BN);
-                    if (a.flags & GEMM_TRIL_A) ke = std::min(ke, bi * BM + BM);
+                    if (a.flags & GEMM_TRIL_A) ke = std::min(ke, bi * bmt + bmt);
                     kext += std::max(0, ke - kb);
                 }
             }
-            *flops_out = kext * 2.0 * BM * BN;
+            *flops_out = kext * 2.0 * bmt * BN;
         }
     }
     return 0;
