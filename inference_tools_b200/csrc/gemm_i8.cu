@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(&bars[i]), CTAS);  // one arrival per producer of the pair
+        for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);  // the leader's arrive.expect_tx
 #pragma unroll
         for (int i = STAGES; i < 2 * STAGES + 1; ++i) mbar_init(smem_u32(&bars[i]), 1);
         mbar_init(smem_u32(&bars[2 * STAGES + 1]), CTAS * EPI_WARPS);  // one arrival per epilogue warp of the pair
@@ -312,10 +312,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
         auto acquire = [&](int i) {  // wait until the MMAs that read slot use i - STAGES have completed
             if (i >= STAGES) mbar_wait(smem_u32(&bars[STAGES + i % STAGES]), ((i / STAGES) - 1) & 1);
         };
-        // the leader announces the bytes of the whole pair; the other CTA only arrives (on the leader's barrier)
+        // The leader announces the bytes of the whole pair on its barrier; the other CTA's TMA is credited to the same
+        // barrier and needs no arrival of its own (a remote mbarrier.arrive costs more than the load it would announce).
+        // Early bytes are harmless: the phase cannot complete before the leader's arrival, and the other CTA cannot be a
+        // whole phase ahead because it waits for the MMAs that read the slot (its local `empty` barrier) first.
         auto announce = [&](unsigned bar, unsigned bytes) {
             if (rank == 0) mbar_expect_tx(bar, bytes * CTAS);
-            else mbar_arrive_cluster(bar, 0);
         };
         for (int t = unit; t < n_tiles; t += n_units) {
             const TileRange tr = tile_range<CTAS>(p, t);
@@ -328,7 +330,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                     const unsigned bar_a = smem_u32(&bars[it % STAGES]), bar_b = smem_u32(&bars[(it + 1) % STAGES]);
                     if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {  // timing probe: MMA rate without the loads
                         if (rank == 0) { mbar_arrive(bar_a); mbar_arrive(bar_b); }
-                        else { mbar_arrive_cluster(bar_a, 0); mbar_arrive_cluster(bar_b, 0); }
                     } else {
                         announce(bar_a, A_BYTES);
                         tma_load_3d<CTAS>(smem_u32(tiles + (it % STAGES) * SLOT_BYTES), &tmA, k, arow, 0, bar_a);
@@ -345,7 +346,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                     const unsigned bar = smem_u32(&bars[it % STAGES]);
                     if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {
                         if (rank == 0) mbar_arrive(bar);
-                        else mbar_arrive_cluster(bar, 0);
                     } else {
                         const unsigned dst = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
                         announce(bar, HI_BYTES + HI_B_BYTES);
@@ -784,11 +784,10 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
         GPB_CUDA(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
         configured_dev[dev & 63] = true;
     }
-    // CTA pairs (256 x 128 tiles, GPB200_GEMM_I8_PAIR=1): measured on B200 at 8192^3 the pair kernel's MMA side is
-    // faster (8.1 ms vs 9.2 ms with the loads switched off: the shared-memory relief works) but its load side is twice
-    // as slow (11.5 ms vs 5.9 ms with the MMAs switched off: the slot hand-shake through the leader's barrier has
-    // ~4 us of latency and only 2-4 k-blocks fit in flight), so the whole kernel loses: 89 vs 105 TF/s.  Off by default.
-    static const int pair_env = getenv("GPB200_GEMM_I8_PAIR") ? atoi(getenv("GPB200_GEMM_I8_PAIR")) : 0;
+    // CTA pairs (256 x 128 tiles) whenever the rows allow it; GPB200_GEMM_I8_PAIR=0 forces single-CTA tiles.
+    // Measured on B200 at 8192^3: 9.65 ms against 10.44 ms -- the pair reads 6 KB instead of 8 KB of shared memory per
+    // MMA; its loads have a longer round trip (credited to the leader's barrier) and now set the pace.
+    static const int pair_env = getenv("GPB200_GEMM_I8_PAIR") ? atoi(getenv("GPB200_GEMM_I8_PAIR")) : 1;
     const int ctas = (pair_env && a.M % (2 * BM) == 0) ? 2 : 1;
     const int bmt = BM * ctas;
     const int tm = a.M / bmt, tn = a.N / BN;
