@@ -138,3 +138,30 @@ def test_mean_function_host_helpers():
     lin.pass_spatial_data(x)
     assert np.allclose(lin.build_mean(th[:3]), th[0] + dx @ th[1:3])
     assert gp.ConstantMean()(x[0], th) == th[0]
+
+
+def test_linear_inverter_host_side():
+    """GpLinearInverter (reference inversion.py:55-136): argument checks in the reference's order, hyper-parameter
+    bookkeeping, and no engine (hence no GPU) before the first evaluation."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "linv_rq_linear.npz"))
+    y, y_err, A, x = g["y"], g["y_err"], g["A"], g["x"]
+    with pytest.raises(ValueError, match="'model_matrix' argument must be a 2D"):
+        gp.GpLinearInverter(y, y_err, A.ravel(), x)
+    with pytest.raises(ValueError, match="of equal size"):
+        gp.GpLinearInverter(y, y_err[:-1], A, x)
+    with pytest.raises(ValueError, match="first dimension of 'model_matrix'"):
+        gp.GpLinearInverter(y[:-1], y_err[:-1], A, x)
+    with pytest.raises(ValueError, match="'parameter_spatial_positions' must be a 2D"):
+        gp.GpLinearInverter(y, y_err, A, x.ravel())
+    with pytest.raises(ValueError, match="second dimension of 'model_matrix'"):
+        gp.GpLinearInverter(y, y_err, A, x[:-1])
+    with pytest.raises(TypeError):
+        gp.GpLinearInverter(y, y_err, A, x, prior_covariance_function=object())
+    inv = gp.GpLinearInverter(y, y_err, A, x, prior_covariance_function=gp.RationalQuadratic, prior_mean_function=gp.LinearMean)
+    assert inv._engine is None
+    assert inv.hyperpar_labels == [str(s) for s in g["labels"]]
+    assert inv.n_hyperpars == len(g["thetas"][0]) == inv.mean.n_params + inv.cov.n_params
+    assert inv.mean_slice == slice(0, inv.mean.n_params) and inv.cov_slice == slice(inv.mean.n_params, inv.n_hyperpars)
+    assert inv.cov.bounds == [(None, None)] * inv.cov.n_params and inv.mean.bounds == [(None, None)] * inv.mean.n_params
+    with pytest.raises(ValueError, match="hyper-parameters"):
+        inv.optimize_hyperparameters(np.ones(inv.n_hyperpars + 1))
