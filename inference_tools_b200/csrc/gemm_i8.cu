@@ -550,9 +550,11 @@ __device__ __forceinline__ void row_scale(double m, double extra, double& mult, 
         const int e = ilogb(m * (128.0 / 127.0)) + 1;
         mult = scalbn(1.0, 55 - e);
         scale = scalbn(extra, e);
-    } else {  // all-zero (padding) row, or non-finite / out-of-range values: NaN propagates to the row of D
+    } else {
+        // all-zero (padding) rows and rows whose largest entry is below 1e-280 (underflowing covariance tails)
+        // contribute nothing; non-finite or absurdly large input poisons its row of D with NaN
         mult = 0.0;
-        scale = (m == 0.0) ? 0.0 : nan("");
+        scale = (m < 1e280) ? 0.0 : nan("");
     }
 }
 __device__ __forceinline__ double finite_abs_max(double amax, double v) {

@@ -717,6 +717,11 @@ def test_int8_tensor_core_gemm_scaling_ranges_and_chunks():
     D = _gemm_impl(1, A, B, None, 1.0, 0.0, 0, 128, 128, 512)
     bound = 512 * np.abs(A).max(1)[:, None] * np.abs(B).max(1)[None, :]
     assert (np.abs(D - A @ B.T) / bound).max() < 2e-16
+    # a row of underflowing values (covariance tails) counts as zero instead of poisoning anything
+    A = rng.standard_normal((128, 512))
+    A[9] = 1e-300 * rng.standard_normal(512)
+    D = _gemm_impl(1, A, rng.standard_normal((128, 512)), None, 1.0, 0.0, 0, 128, 128, 512)
+    assert np.all(D[9] == 0.0) and np.all(np.isfinite(D))
     # non-finite input poisons its row of the result instead of producing garbage digits
     A = rng.standard_normal((128, 512))
     A[5, 17] = np.nan
