@@ -18,8 +18,10 @@
 //      the accumulators (tcgen05.ld), combine them smallest-first in FP64 (Horner in 2^-8; the first sweep's
 //      partial sum waits in a per-CTA scratch row) and apply the row / column scales, alpha and beta.
 //
-// Dropped terms (s + t >= 7) are below 2^-53 of rowmax(A) * rowmax(B) per product -- the same normwise bound as an
-// FP64 dot product; the int32 sums are exact for k extents <= 16384 (7 * K * 2^14 < 2^31), longer ones are chunked.
+// Error per product: the two splitting errors (2^-55 of the row maxima) plus the dropped terms (s + t >= 7), at most
+// 2^-51 of rowmax(A) * rowmax(B) with worst-case digits and ~2^-56 with real ones (tests/test_int8_split_model.py) -- a
+// normwise bound of the size of an FP64 dot product's; the int32 sums are exact for k extents <= 16384
+// (7 * K * 2^14 < 2^31), longer ones are chunked.
 // M and N must be multiples of 128; the caller (gemm_nt) falls back to the DMMA kernels otherwise.
 #include "common.cuh"
 
