@@ -726,6 +726,7 @@ struct Workspace {
     double *sa = nullptr, *sb = nullptr, *scratch = nullptr;
     size_t qa_cap = 0, qb_cap = 0, sa_cap = 0, sb_cap = 0, scratch_cap = 0;
     std::vector<void*> retired;
+    int sm_count = 0;  // 0 until the kernels have been configured on this workspace's device
 };
 std::mutex g_ws_mutex;
 std::map<std::pair<int, cudaStream_t>, Workspace> g_ws;
@@ -773,6 +774,13 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     {
         std::lock_guard<std::mutex> lock(g_ws_mutex);
         w = &g_ws[{dev, s}];
+        if (w->sm_count == 0) {  // once per (device, stream), under the lock: worker threads share nothing else here
+            GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            int sms = 0;
+            GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            w->sm_count = sms;
+        }
     }
     const int chunks = (a.K + MAX_K - 1) / MAX_K;
     const int Kc_max = ((a.K / 64 + chunks - 1) / chunks) * 64;  // balanced chunks, multiples of 64
@@ -780,14 +788,6 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     GPB_TRY(grow(w->qb, w->qb_cap, (size_t)S * a.N * Kc_max, w->retired));
     GPB_TRY(grow(w->sa, w->sa_cap, sizeof(double) * 2 * a.M, w->retired));  // scales, then the 2^(55-e) multipliers
     GPB_TRY(grow(w->sb, w->sb_cap, sizeof(double) * 2 * a.N, w->retired));
-    static bool configured_dev[64] = {};
-    static int sm_count[64] = {};
-    if (!configured_dev[dev & 63]) {
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-        configured_dev[dev & 63] = true;
-    }
     // CTA pairs (256 x 128 tiles) whenever the rows allow it; GPB200_GEMM_I8_PAIR=0 forces single-CTA tiles.
     // Measured on B200 at 8192^3: 9.65 ms against 10.44 ms -- the pair reads 6 KB instead of 8 KB of shared memory per
     // MMA; its loads have a longer round trip (credited to the leader's barrier) and now set the pace.
@@ -797,7 +797,7 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     const int tm = a.M / bmt, tn = a.N / BN;
     const int64_t tiles = (a.flags & GEMM_LOWER) ? (ctas == 2 ? (int64_t)tm * (tm + 1) : (int64_t)tm * (tm + 1) / 2)
                                                  : (int64_t)tm * tn;
-    const int units = (int)std::min<int64_t>(tiles, sm_count[dev & 63] / ctas);
+    const int units = (int)std::min<int64_t>(tiles, w->sm_count / ctas);
     const int grid = units * ctas;
     GPB_TRY(grow(w->scratch, w->scratch_cap, sizeof(double) * (size_t)grid * BM * BN, w->retired));
     for (int k0 = 0, c = 0; k0 < a.K; k0 += Kc_max, ++c) {
