@@ -20,6 +20,12 @@ from inference_tools_b200.gp.covariance import CovarianceFunction, SquaredExpone
 from inference_tools_b200.gp.mean import ConstantMean, MeanFunction, as_engine_mean
 
 
+def _error_text(lines) -> str:
+    """The reference's message layout: a blank line, the class tag, then the '>>' lines, all indented alike."""
+    pad = " " * 16
+    return "\n\n" + pad + "[ GpLinearInverter error ]\n" + "".join(pad + ln + "\n" for ln in lines) + pad
+
+
 class GpLinearInverter:
     """Gaussian-process linear inversion: posterior of ``y = A x + noise`` under a GP prior on ``x``.
 
@@ -38,57 +44,31 @@ class GpLinearInverter:
         prior_mean_function: MeanFunction = ConstantMean,
         device: int = 0,
     ):
-        # same checks, in the same order, as inversion.py:64-112
-        if model_matrix.ndim != 2:
-            raise ValueError(
-                """\n
-                [ GpLinearInverter error ]
-                >> 'model_matrix' argument must be a 2D numpy.ndarray
-                """
-            )
-        if y.ndim != y_err.ndim != 1 or y.size != y_err.size:
-            raise ValueError(
-                """\n
-                [ GpLinearInverter error ]
-                >> 'y' and 'y_err' arguments must be 1D numpy.ndarray
-                >> of equal size.
-                """
-            )
-        if model_matrix.shape[0] != y.size:
-            raise ValueError(
-                f"""\n
-                [ GpLinearInverter error ]
-                >> The size of the first dimension of 'model_matrix' must
-                >> equal the size of 'y', however they have shapes
-                >> {model_matrix.shape}, {y.shape}
-                >> respectively.
-                """
-            )
-        if parameter_spatial_positions.ndim != 2:
-            raise ValueError(
-                """\n
-                [ GpLinearInverter error ]
-                >> 'parameter_spatial_positions' must be a 2D numpy.ndarray, with the
-                >> size of first dimension being equal to the number of model parameters
-                >> and the size of the second dimension being equal to the number of
-                >> spatial dimensions.
-                """
-            )
-        if model_matrix.shape[1] != parameter_spatial_positions.shape[0]:
-            raise ValueError(
-                f"""\n
-                [ GpLinearInverter error ]
-                >> The size of the second dimension of 'model_matrix' must be equal
-                >> to the size of the first dimension of 'parameter_spatial_positions',
-                >> however they have shapes
-                >> {model_matrix.shape}, {parameter_spatial_positions.shape}
-                >> respectively.
-                """
-            )
-        if parameter_spatial_positions.shape[1] > _lib.MAX_DIM:
-            raise ValueError(
-                f"[ GpLinearInverter error ] the CUDA engine supports at most {_lib.MAX_DIM} spatial dimensions"
-            )
+        # the reference's checks, in its order and with its texts (inversion.py:64-112)
+        A, pos = model_matrix, parameter_spatial_positions
+        checks = (
+            (A.ndim != 2, [">> 'model_matrix' argument must be a 2D numpy.ndarray"]),
+            (y.ndim != y_err.ndim != 1 or y.size != y_err.size,
+             [">> 'y' and 'y_err' arguments must be 1D numpy.ndarray", ">> of equal size."]),
+            (A.ndim == 2 and A.shape[0] != y.size,
+             [">> The size of the first dimension of 'model_matrix' must",
+              ">> equal the size of 'y', however they have shapes",
+              f">> {A.shape}, {y.shape}", ">> respectively."]),
+            (pos.ndim != 2,
+             [">> 'parameter_spatial_positions' must be a 2D numpy.ndarray, with the",
+              ">> size of first dimension being equal to the number of model parameters",
+              ">> and the size of the second dimension being equal to the number of",
+              ">> spatial dimensions."]),
+            (A.ndim == 2 and pos.ndim == 2 and A.shape[1] != pos.shape[0],
+             [">> The size of the second dimension of 'model_matrix' must be equal",
+              ">> to the size of the first dimension of 'parameter_spatial_positions',",
+              ">> however they have shapes", f">> {A.shape}, {pos.shape}", ">> respectively."]),
+            (pos.ndim == 2 and pos.shape[1] > _lib.MAX_DIM,
+             [f">> the CUDA engine supports at most {_lib.MAX_DIM} spatial dimensions"]),
+        )
+        for failed, lines in checks:
+            if failed:
+                raise ValueError(_error_text(lines))
 
         self.A = np.ascontiguousarray(model_matrix, dtype=float)
         self.y = np.ascontiguousarray(y, dtype=float)
@@ -135,13 +115,8 @@ class GpLinearInverter:
     def _theta(self, theta) -> ndarray:
         theta = np.asarray(theta, dtype=float)
         if theta.size != self.n_hyperpars:
-            raise ValueError(
-                f"""\n
-                [ GpLinearInverter error ]
-                >> There are a total of {self.n_hyperpars} hyper-parameters,
-                >> but {theta.size} values were given.
-                """
-            )
+            raise ValueError(_error_text([f">> There are a total of {self.n_hyperpars} hyper-parameters,",
+                                          f">> but {theta.size} values were given."]))
         return theta
 
     # ------------------------------------------------------------------ reference API
@@ -178,13 +153,8 @@ class GpLinearInverter:
         evaluation is one engine call."""
         initial_guess = np.asarray(initial_guess, dtype=float)
         if initial_guess.size != self.n_hyperpars:
-            raise ValueError(
-                f"""\n
-                [ GpLinearInverter error ]
-                >> There are a total of {self.n_hyperpars} hyper-parameters,
-                >> but {initial_guess.size} values were given in 'initial_guess'.
-                """
-            )
+            raise ValueError(_error_text([f">> There are a total of {self.n_hyperpars} hyper-parameters,",
+                                          f">> but {initial_guess.size} values were given in 'initial_guess'."]))
         hp_bounds = [*self.mean.bounds, *self.cov.bounds]
         result = minimize(
             fun=lambda t: -self.marginal_likelihood(t),
