@@ -5,11 +5,14 @@ NCCL_INC := $(shell python -c "import os, nvidia; print(os.path.join(list(nvidia
 NVFLAGS := $(ARCH) $(if $(NCCL_INC),-I$(NCCL_INC),) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Wno-deprecated-gpu-targets
 SRC_DIR := inference_tools_b200/csrc
 BUILD := build/obj
-SRCS := $(wildcard $(SRC_DIR)/*.cu)
+# api_test.cu (host-buffer hooks onto internal primitives for tests/ and tools/) is NOT part of the product library:
+# it goes into libgpb200_test.so, which links against libgpb200.so.
+SRCS := $(filter-out $(SRC_DIR)/api_test.cu,$(wildcard $(SRC_DIR)/*.cu))
 OBJS := $(patsubst $(SRC_DIR)/%.cu,$(BUILD)/%.o,$(SRCS))
 LIB := inference_tools_b200/libgpb200.so
+TEST_LIB := inference_tools_b200/libgpb200_test.so
 
-all: $(LIB)
+all: $(LIB) $(TEST_LIB)
 
 $(BUILD)/%.o: $(SRC_DIR)/%.cu $(wildcard $(SRC_DIR)/*.cuh) include/gpb200.h
 	@mkdir -p $(BUILD)
@@ -18,6 +21,9 @@ $(BUILD)/%.o: $(SRC_DIR)/%.cu $(wildcard $(SRC_DIR)/*.cuh) include/gpb200.h
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 
+$(TEST_LIB): $(BUILD)/api_test.o $(LIB)
+	$(NVCC) $(ARCH) -shared -o $@ $(BUILD)/api_test.o -Linference_tools_b200 -lgpb200 -lcudart -Xlinker -rpath -Xlinker '$$ORIGIN'
+
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(TEST_LIB)
 .PHONY: all clean

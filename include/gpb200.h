@@ -40,12 +40,28 @@ enum { GPB_GET_K_XX = 0, GPB_GET_L = 1, GPB_GET_ALPHA = 2, GPB_GET_MU = 3 };
 /* gpb_expected_improvement modes: ExpectedImprovement.__call__ (acquisition.py:76-86), opt_func
  * (:88-97), opt_func_gradient (:99-125) */
 enum { GPB_EI_VALUE = 0, GPB_EI_NEG_LOG = 1, GPB_EI_NEG_LOG_GRAD = 2 };
+/* gpb_acquisition kinds: ExpectedImprovement (acquisition.py:44-140), UpperConfidenceBound (:143-192), MaxVariance
+ * (:195-232).  The modes above read, for every kind: the acquisition value (__call__), opt_func (the minimiser's
+ * objective: -ln EI, -UCB, -sigma^2), opt_func and its gradient (opt_func_gradient). */
+enum { GPB_ACQ_EI = 0, GPB_ACQ_UCB = 1, GPB_ACQ_MAXVAR = 2 };
 
 const char* gpb_last_error(void);
 int gpb_device_count(int* count);
 int64_t gpb_launch_count(void);           /* kernels launched by this library so far (process-wide) */
 double gpb_gemm_flops(void);              /* algorithmic FP64 flops issued through the GEMM kernels so far */
 double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-core path (each costs 28 int8 products) */
+
+/* Runtime options, process-wide (initial values come from the GPB200_* environment variables):
+ *   "gemm_i8"        0 = every FP64 GEMM on the FP64 tensor pipe (DMMA), 1 = INT8 tensor-core digit-split GEMM where
+ *                    it pays (k >= gemm_i8_min_k and >= 148 tiles; default), 2 = wherever it applies
+ *   "gemm_i8_min_k"  shortest k extent sent to the INT8 path (512)      "gemm_i8_pair"  CTA-pair tiles (1)
+ *   "gemm_tile", "gemm_tma", "gemm_i8_debug"  kernel-selection / probe switches of the GEMM dispatcher
+ *   "graphs"         CUDA-graph replay of launch sequences (1)
+ *   "i8_fallback"    repeat a factorisation on DMMA when the INT8 path reports a non-PD pivot (1)
+ *   "predict_block"  block width of the left-looking predict solve against cached digit planes (0 = recursion)
+ * Changing an option drops every context's captured graphs at its next call. */
+int gpb_set_option(const char* name, int64_t value);
+int gpb_get_option(const char* name, int64_t* value);
 
 int gpb_ctx_create(int device, gpb_ctx** out);
 void gpb_ctx_destroy(gpb_ctx* ctx);
@@ -102,6 +118,12 @@ int gpb_posterior(gpb_ctx* ctx, const double* q, int64_t m, double* mu, double* 
  * GPB_EI_NEG_LOG_GRAD (SquaredExponential only); argmax_or_null receives the index of the best value */
 int gpb_expected_improvement(gpb_ctx* ctx, const double* q, int64_t m, double y_max, int mode, double* out,
                              double* grad_or_null, int64_t* argmax_or_null);
+
+/* Any acquisition function over a batch of candidates: kind = GPB_ACQ_*, param = y_max (EI, acquisition.py:41) or
+ * kappa (UCB, :162); argbest_or_null receives the index of the best candidate (largest value = smallest opt_func; lowest
+ * index on ties), found by a device reduction. */
+int gpb_acquisition(gpb_ctx* ctx, int kind, double param, const double* q, int64_t m, int mode, double* out,
+                    double* grad_or_null, int64_t* argbest_or_null);
 
 /* Distributed (one process per GPU) block-column-cyclic Cholesky + log marginal likelihood for N beyond one GPU
  * (BASELINE.json config 5).  Replaces regression.py:534-539 (build_covariance + cholesky + solve_triangular) when

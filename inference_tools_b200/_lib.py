@@ -13,6 +13,8 @@ COV_SE, COV_RQ, COV_WHITE, COV_HETERO = 0, 1, 2, 3
 MEAN_CONST, MEAN_LINEAR, MEAN_QUADRATIC = 0, 1, 2
 GET_K_XX, GET_L, GET_ALPHA, GET_MU = 0, 1, 2, 3
 EI_VALUE, EI_NEG_LOG, EI_NEG_LOG_GRAD = 0, 1, 2
+ACQ_VALUE, ACQ_OPT, ACQ_OPT_GRAD = 0, 1, 2      # the same modes, read for any acquisition kind
+ACQ_EI, ACQ_UCB, ACQ_MAXVAR = 0, 1, 2
 MAX_DIM, MAX_COMP, MAX_REG = 8, 4, 4
 
 _dp = C.POINTER(C.c_double)
@@ -26,6 +28,8 @@ SIGNATURES = {
     "gpb_launch_count": (C.c_int64, []),
     "gpb_gemm_flops": (C.c_double, []),
     "gpb_gemm_flops_int8": (C.c_double, []),
+    "gpb_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "gpb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),
     "gpb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_ctx_p)]),
     "gpb_ctx_destroy": (None, [_ctx_p]),
     "gpb_set_data": (C.c_int, [_ctx_p, _dp, C.c_int64, C.c_int, _dp, _dp, _dp]),
@@ -47,6 +51,7 @@ SIGNATURES = {
     "gpb_spatial_derivatives": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_posterior": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_expected_improvement": (C.c_int, [_ctx_p, _dp, C.c_int64, C.c_double, C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
+    "gpb_acquisition": (C.c_int, [_ctx_p, C.c_int, C.c_double, _dp, C.c_int64, C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
     "gpb_dist_unique_id": (C.c_int, [C.c_char_p]),
     "gpb_dist_init": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_char_p]),
     "gpb_dist_lml": (C.c_int, [_ctx_p, _dp, C.c_int, _dp, _ip, _dp]),
@@ -88,6 +93,52 @@ def load_library():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+_test_lib = None
+
+
+def load_test_library():
+    """libgpb200_test.so: host-buffer hooks onto internal primitives (csrc/api_test.cu) for tests/ and tools/ only."""
+    global _test_lib
+    if _test_lib is None:
+        load_library()  # resolves its libgpb200.so dependency to the already loaded copy
+        _test_lib = C.CDLL(os.path.join(_HERE, "libgpb200_test.so"))
+    return _test_lib
+
+
+def set_option(name: str, value: int) -> None:
+    """Runtime switch of the library (process-wide): "gemm_i8" 0/1/2, "gemm_i8_min_k", "gemm_i8_pair", "gemm_tile",
+    "gemm_tma", "graphs", "i8_fallback", "predict_block" (include/gpb200.h)."""
+    lib = load_library()
+    if lib.gpb_set_option(name.encode(), int(value)) != 0:
+        raise EngineError(lib.gpb_last_error().decode())
+
+
+def get_option(name: str) -> int:
+    lib = load_library()
+    v = C.c_int64(0)
+    if lib.gpb_get_option(name.encode(), C.byref(v)) != 0:
+        raise EngineError(lib.gpb_last_error().decode())
+    return v.value
+
+
+class options:
+    """Context manager: ``with _lib.options(gemm_i8=0): ...`` sets options and restores the previous values."""
+
+    def __init__(self, **kw):
+        self.new, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.new.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
 
 
 def _ptr(a):
@@ -254,6 +305,16 @@ class Engine:
         grad = np.empty((m, self.d)) if mode == EI_NEG_LOG_GRAD else None
         best = C.c_int64(-1)
         self._check(self.lib.gpb_expected_improvement(self._ctx, _ptr(q), m, float(y_max), mode, _ptr(out), _ptr(grad), C.byref(best)))
+        return out, grad, best.value
+
+    def acquisition(self, kind, param, q, mode=ACQ_VALUE):
+        """(values, gradient or None, index of the best candidate) for ACQ_EI (param = y_max), ACQ_UCB (kappa), ACQ_MAXVAR"""
+        q = _f64(q)
+        m = q.shape[0]
+        out = np.empty(m)
+        grad = np.empty((m, self.d)) if mode == ACQ_OPT_GRAD else None
+        best = C.c_int64(-1)
+        self._check(self.lib.gpb_acquisition(self._ctx, kind, float(param), _ptr(q), m, mode, _ptr(out), _ptr(grad), C.byref(best)))
         return out, grad, best.value
 
     # ---------------------------------------------------------------- device-resident path + timers

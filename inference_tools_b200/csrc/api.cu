@@ -6,13 +6,6 @@
 namespace gpb {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
-static int64_t g_launches = 0;
-void count_launch(int n) { g_launches += n; }
-int64_t launch_count() { return g_launches; }
-double gemm_flops_issued();  // gemm_dmma.cu
-double gemm_flops_issued_i8();
-void credit_gemm_flops(double f, double f_i8);
-
 }  // namespace gpb
 
 using namespace gpb;
@@ -138,13 +131,26 @@ std::string pkey(const char* tag, std::initializer_list<const void*> ptrs, std::
     return k;
 }
 
+void clear_graphs(gpb_ctx* c) {
+    for (auto& kv : c->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c->graphs.clear();
+}
+
 // Run a launch sequence whose arguments are only device pointers and shapes.  First use: plain launches (also
 // performs the one-time kernel attribute setup).  Second use: the same sequence is captured into a CUDA graph;
 // from then on every call is one cudaGraphLaunch -- the recursion issues hundreds of short kernels whose host
 // launch cost otherwise dominates for N <= 8192.  GPB200_NO_GRAPHS=1 disables the cache.
 template <class F>
-int run_graphed(gpb_ctx* c, const std::string& key, F&& body) {
+int run_graphed(gpb_ctx* c, const std::string& key0, F&& body) {
+    if (c->opt_epoch != option_epoch()) {  // a runtime option changed: recorded sequences may pick other kernels now
+        clear_graphs(c);
+        c->opt_epoch = option_epoch();
+        c->use_graphs = option(OPT_GRAPHS) != 0;
+    }
     if (!c->use_graphs) return body();
+    // the per-thread DMMA override (retry after a failed INT8 factorisation) selects different kernels: separate graphs
+    const std::string key = key0 + "#" + std::to_string(gemm_i8_override());
     auto& e = c->graphs[key];
     if (e.exec) {
         GPB_CUDA(cudaGraphLaunch(e.exec, c->s));
@@ -153,8 +159,8 @@ int run_graphed(gpb_ctx* c, const std::string& key, F&& body) {
         return 0;
     }
     if (e.uses++ == 0) return body();
-    const int64_t l0 = launch_count();
-    const double f0 = gemm_flops_issued(), g0 = gemm_flops_issued_i8();
+    const int64_t l0 = thread_launch_count();
+    const double f0 = thread_gemm_flops(), g0 = thread_gemm_flops_i8();
     GPB_CUDA(cudaStreamBeginCapture(c->s, cudaStreamCaptureModeThreadLocal));
     const int rc = body();
     cudaGraph_t g = nullptr;
@@ -166,9 +172,9 @@ int run_graphed(gpb_ctx* c, const std::string& key, F&& body) {
         if (rc != 0) return rc;
         return body();
     }
-    e.launches = launch_count() - l0;
-    e.flops = gemm_flops_issued() - f0;
-    e.flops_i8 = gemm_flops_issued_i8() - g0;
+    e.launches = thread_launch_count() - l0;
+    e.flops = thread_gemm_flops() - f0;
+    e.flops_i8 = thread_gemm_flops_i8() - g0;
     const cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
     cudaGraphDestroy(g);
     if (ie != cudaSuccess) {
@@ -179,12 +185,6 @@ int run_graphed(gpb_ctx* c, const std::string& key, F&& body) {
     }
     GPB_CUDA(cudaGraphLaunch(e.exec, c->s));
     return 0;
-}
-
-void clear_graphs(gpb_ctx* c) {
-    for (auto& kv : c->graphs)
-        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    c->graphs.clear();
 }
 
 // assemble K(theta)+sig into `K` (lower tiles), factor in place, solve for alpha.
@@ -221,6 +221,22 @@ int assemble_and_factor(gpb_ctx* c, const CovParams& cp, const MeanParams& mp, d
     return 0;
 }
 
+// A non-positive pivot reported while GEMMs ran on the INT8 path is re-checked on the FP64 DMMA kernels before it is
+// believed: the digit splitting is accurate normwise (2^-55 of the row maxima), and a Schur complement that is positive
+// only by the 1e-12 a^2 jitter (near-noise-free SE / RQ data) can lose its sign to that.  "i8_fallback" = 0 disables.
+template <class F>
+int with_dmma_retry(gpb_ctx* c, int* info, F&& body) {
+    const double f0 = thread_gemm_flops_i8();
+    int rc = body();
+    if (rc == 0 && *info > 0 && option(OPT_I8_FALLBACK) && gemm_i8_override() < 0 && thread_gemm_flops_i8() > f0) {
+        set_gemm_i8_override(0);
+        rc = body();
+        set_gemm_i8_override(-1);
+        ++c->dmma_retries;
+    }
+    return rc;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -232,10 +248,6 @@ int gpb_device_count(int* count) {
     GPB_CUDA(cudaGetDeviceCount(count));
     return 0;
 }
-
-int64_t gpb_launch_count(void) { return launch_count(); }
-double gpb_gemm_flops(void) { return gemm_flops_issued(); }
-double gpb_gemm_flops_int8(void) { return gemm_flops_issued_i8(); }
 
 int gpb_ctx_create(int device, gpb_ctx** out) {
     int count = 0;
@@ -250,7 +262,8 @@ int gpb_ctx_create(int device, gpb_ctx** out) {
     c->device = device;
     GPB_CUDA(cudaStreamCreateWithFlags(&c->s, cudaStreamNonBlocking));
     c->timer.s = c->s;
-    c->use_graphs = getenv("GPB200_NO_GRAPHS") == nullptr;
+    c->use_graphs = option(OPT_GRAPHS) != 0;
+    c->opt_epoch = option_epoch();
     *out = c;
     return 0;
 }
@@ -261,7 +274,8 @@ void gpb_ctx_destroy(gpb_ctx* c) {
     cudaStreamSynchronize(c->s);
     double* ptrs[] = {c->x, c->y, c->noise, c->ycov, c->theta_dev, c->Lfit, c->dinv_fit, c->alpha, c->mu, c->Kwork,
                       c->dinv_work, c->W, c->Kinv, c->partials, c->grad_dev, c->vec, c->resid, c->alpha_work, c->scal,
-                      c->tmp, c->S, c->dots, c->G, c->qbuf, c->o1, c->o2, c->o3, c->R_dev};
+                      c->tmp, c->S, c->dots, c->G, c->qbuf, c->o1, c->o2, c->o3, c->R_dev,
+                      reinterpret_cast<double*>(c->argws)};
     for (double* p : ptrs)
         if (p) cudaFree(p);
     dist_destroy(c);
@@ -459,7 +473,7 @@ int gpb_cross_covariance(gpb_ctx* c, const double* u, int64_t m, const double* v
     return 0;
 }
 
-int gpb_factor(gpb_ctx* c, const double* theta, int* info) {
+static int factor_impl(gpb_ctx* c, const double* theta, int* info) {
     GPB_TRY(use(c));
     GPB_TRY(need_model(c));
     c->timer.reset();
@@ -510,7 +524,7 @@ int gpb_get(gpb_ctx* c, int which, double* out) {
     return -2;
 }
 
-int gpb_lml(gpb_ctx* c, const double* theta, double* lml, int* info) {
+static int lml_impl(gpb_ctx* c, const double* theta, double* lml, int* info) {
     GPB_TRY(use(c));
     GPB_TRY(need_model(c));
     c->timer.reset();
@@ -534,7 +548,7 @@ int gpb_lml(gpb_ctx* c, const double* theta, double* lml, int* info) {
     return 0;
 }
 
-int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int* info) {
+static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* grad, int* info) {
     GPB_TRY(use(c));
     GPB_TRY(need_model(c));
     c->timer.reset();
@@ -580,7 +594,7 @@ int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int
     return 0;
 }
 
-int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* info) {
+static int loo_impl(gpb_ctx* c, const double* theta, double* loo, double* grad, int* info) {
     GPB_TRY(use(c));
     GPB_TRY(need_model(c));
     c->timer.reset();
@@ -627,6 +641,19 @@ int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* inf
     return 0;
 }
 
+int gpb_factor(gpb_ctx* c, const double* theta, int* info) {
+    return with_dmma_retry(c, info, [&]() { return factor_impl(c, theta, info); });
+}
+int gpb_lml(gpb_ctx* c, const double* theta, double* lml, int* info) {
+    return with_dmma_retry(c, info, [&]() { return lml_impl(c, theta, lml, info); });
+}
+int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int* info) {
+    return with_dmma_retry(c, info, [&]() { return lml_grad_impl(c, theta, lml, grad, info); });
+}
+int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* info) {
+    return with_dmma_retry(c, info, [&]() { return loo_impl(c, theta, loo, grad, info); });
+}
+
 int gpb_loo_predictions(gpb_ctx* c, double* mu, double* sigma) {
     GPB_TRY(use(c));
     if (!c->fitted) {
@@ -671,9 +698,9 @@ int64_t chunk_rows(const gpb_ctx* c) {
 //   PM_PREDICT : o_a = mu (m), o_b = sig (m)
 //   PM_GRADIENT: o_a = mean (m x d), o_b = cov (m x d x d)
 //   PM_SPATIAL : o_a = dmu (m x d), o_b = dvar (m x d)
-//   PM_EI      : o_a = value (m), o_b = grad (m x d) or nullptr; ei_mode, y_max
+//   PM_EI      : o_a = acquisition value (m), o_b = grad (m x d) or nullptr; ei_mode = GPB_EI_* mode, acq_kind / acq_param
 int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, double* o_a, double* o_b, int ei_mode,
-                   double y_max) {
+                   double acq_param, int acq_kind = GPB_ACQ_EI) {
     const int npad = (int)c->npad, n = (int)c->n, d = c->d;
     const bool stacked = mode == PM_GRADIENT || mode == PM_SPATIAL || (mode == PM_EI && ei_mode == GPB_EI_NEG_LOG_GRAD);
     const int ns = stacked ? d + 1 : 1;
@@ -728,8 +755,9 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
                 GPB_TRY(launch_finalize_predict(c->cp_fit, c->mp_fit, qp, mq, ns, c->dots, c->G, c->o1, c->o2, c->s));
                 if (stacked)
                     GPB_TRY(launch_finalize_spatial(c->dots, c->G, mq, d, c->o3, c->o3 + (size_t)qmax * d, c->s));
-                GPB_TRY(launch_ei(c->o1, c->o2, stacked ? c->o3 : nullptr, stacked ? c->o3 + (size_t)qmax * d : nullptr,
-                                  mq, d, y_max, ei_mode, o_a + q0, stacked ? o_b + q0 * d : nullptr, c->s));
+                GPB_TRY(launch_acquisition(c->o1, c->o2, stacked ? c->o3 : nullptr,
+                                           stacked ? c->o3 + (size_t)qmax * d : nullptr, mq, d, acq_kind, acq_param,
+                                           ei_mode, o_a + q0, stacked ? o_b + q0 * d : nullptr, c->s));
                 break;
         }
     }
@@ -747,7 +775,7 @@ int need_fit(gpb_ctx* c) {
 
 // host-buffer wrapper: uploads q, runs the driver into device outputs, downloads na/nb doubles per query
 int predict_host(gpb_ctx* c, const double* q, int64_t m, PredMode mode, double* a, int64_t na, double* b, int64_t nb,
-                 int ei_mode = 0, double y_max = 0.0) {
+                 int ei_mode = 0, double y_max = 0.0, int acq_kind = GPB_ACQ_EI, int64_t* argbest = nullptr) {
     if (m == 0) return 0;
     c->timer.reset();
     c->timer.mark("h2d");
@@ -756,7 +784,16 @@ int predict_host(gpb_ctx* c, const double* q, int64_t m, PredMode mode, double* 
     double* ad = qd + (size_t)m * c->d;
     double* bd = ad + (size_t)m * na;
     GPB_CUDA(cudaMemcpyAsync(qd, q, sizeof(double) * m * c->d, cudaMemcpyHostToDevice, c->s));
-    GPB_TRY(predict_driver(c, qd, m, mode, ad, nb ? bd : nullptr, ei_mode, y_max));
+    GPB_TRY(predict_driver(c, qd, m, mode, ad, nb ? bd : nullptr, ei_mode, y_max, acq_kind));
+    if (argbest) {  // best candidate on the device: largest value, i.e. smallest opt_func
+        c->timer.marks.back().first = "argbest";
+        GPB_TRY(ensure(c->argws, c->argws_cap, (sizeof(double) + sizeof(int64_t)) * (ARGBEST_BLOCKS + 1)));
+        double* wv = reinterpret_cast<double*>(c->argws);
+        int64_t* wi = reinterpret_cast<int64_t*>(wv + ARGBEST_BLOCKS + 1);
+        GPB_TRY(launch_argbest(ad, m, ei_mode == GPB_EI_VALUE, wv, wi, c->s));
+        GPB_CUDA(cudaMemcpyAsync(argbest, wi, sizeof(int64_t), cudaMemcpyDeviceToHost, c->s));
+        c->timer.mark("end");
+    }
     c->timer.marks.back().first = "d2h";
     GPB_CUDA(cudaMemcpyAsync(a, ad, sizeof(double) * m * na, cudaMemcpyDeviceToHost, c->s));
     if (nb && b) GPB_CUDA(cudaMemcpyAsync(b, bd, sizeof(double) * m * nb, cudaMemcpyDeviceToHost, c->s));
@@ -804,24 +841,29 @@ int gpb_spatial_derivatives(gpb_ctx* c, const double* q, int64_t m, double* dmu,
     return predict_host(c, q, m, PM_SPATIAL, dmu, c->d, dvar, c->d);
 }
 
-int gpb_expected_improvement(gpb_ctx* c, const double* q, int64_t m, double y_max, int mode, double* out,
-                             double* grad_or_null, int64_t* argmax_or_null) {
+int gpb_acquisition(gpb_ctx* c, int kind, double param, const double* q, int64_t m, int mode, double* out,
+                    double* grad_or_null, int64_t* argbest_or_null) {
     GPB_TRY(use(c));
     GPB_TRY(need_fit(c));
+    if (kind < GPB_ACQ_EI || kind > GPB_ACQ_MAXVAR || mode < GPB_EI_VALUE || mode > GPB_EI_NEG_LOG_GRAD) {
+        set_error("gpb_acquisition: unknown acquisition kind or mode");
+        return -2;
+    }
     if (mode == GPB_EI_NEG_LOG_GRAD && !is_pure_se(c)) {
         set_error("gradient terms are only available for the SquaredExponential covariance (covariance.py:38-44)");
         return -3;
     }
     const bool g = mode == GPB_EI_NEG_LOG_GRAD;
-    GPB_TRY(predict_host(c, q, m, PM_EI, out, 1, g ? grad_or_null : nullptr, g ? c->d : 0, mode, y_max));
-    if (argmax_or_null && m > 0) {
-        // best candidate: largest EI, i.e. smallest -ln EI
-        int64_t best = 0;
-        for (int64_t i = 1; i < m; ++i)
-            if (mode == GPB_EI_VALUE ? out[i] > out[best] : out[i] < out[best]) best = i;
-        *argmax_or_null = best;
-    }
+    if (argbest_or_null) *argbest_or_null = -1;
+    GPB_TRY(predict_host(c, q, m, PM_EI, out, 1, g ? grad_or_null : nullptr, g ? c->d : 0, mode, param, kind,
+                         (argbest_or_null && m > 0) ? argbest_or_null : nullptr));
+    if (argbest_or_null && m > 0 && *argbest_or_null < 0) *argbest_or_null = 0;  // all NaN: the host scan's answer
     return 0;
+}
+
+int gpb_expected_improvement(gpb_ctx* c, const double* q, int64_t m, double y_max, int mode, double* out,
+                             double* grad_or_null, int64_t* argmax_or_null) {
+    return gpb_acquisition(c, GPB_ACQ_EI, y_max, q, m, mode, out, grad_or_null, argmax_or_null);
 }
 
 int gpb_posterior(gpb_ctx* c, const double* q, int64_t m, double* mu, double* sigma) {
@@ -833,7 +875,8 @@ int gpb_posterior(gpb_ctx* c, const double* q, int64_t m, double* mu, double* si
     const int mp = (int)round_up(m, 128);
     GPB_TRY(ensure(c->S, c->S_cap, sizeof(double) * (size_t)mp * npad));
     GPB_TRY(ensure(c->dots, c->dots_cap, sizeof(double) * (size_t)mp));
-    GPB_TRY(ensure(c->qbuf, c->qbuf_cap, sizeof(double) * ((size_t)m * (d + 1) + (size_t)mp * mp)));
+    // + 1: the covariance block is moved up by one double when m (d + 1) is odd (16-byte alignment below)
+    GPB_TRY(ensure(c->qbuf, c->qbuf_cap, sizeof(double) * ((size_t)m * (d + 1) + 1 + (size_t)mp * mp)));
     double* qd = c->qbuf;
     double* mud = qd + (size_t)m * d;
     double* sg = mud + m;

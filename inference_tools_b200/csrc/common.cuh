@@ -65,8 +65,37 @@ struct GemmArgs {
 };
 int gemm_nt(const GemmArgs& a, cudaStream_t s);
 void gemm_i8_release(cudaStream_t s);  // gemm_i8.cu: frees the digit-plane workspace tied to a stream
-void count_launch(int n = 1);  // every other kernel launch is counted through this
+
+// ---------------------------------------------------------------- process-wide counters and options (options.cu)
+// Counters are atomics (restarts run on worker threads, one context each); every thread also keeps private copies so
+// that a CUDA-graph capture can attribute launches / flops to the sequence it recorded.
+void count_launch(int n = 1);  // every kernel launch is counted through this
 int64_t launch_count();
+int64_t thread_launch_count();
+void credit_gemm_flops(double f, double f_i8);  // algorithmic FP64 flops of a GEMM launch (f_i8: issued on the INT8 path)
+double gemm_flops_issued();
+double gemm_flops_issued_i8();
+double thread_gemm_flops();
+double thread_gemm_flops_i8();
+
+// Runtime options (gpb_set_option / gpb_get_option; initial values from the GPB200_* environment variables).
+enum Option : int {
+    OPT_GEMM_I8 = 0,      // 0 = FP64 DMMA kernels only, 1 = INT8 tensor-core path where it pays (default), 2 = wherever it applies
+    OPT_GEMM_I8_MIN_K,    // shortest k extent sent to the INT8 path (default 512)
+    OPT_GEMM_I8_PAIR,     // CTA-pair (cta_group::2) tiles on the INT8 path (default 1)
+    OPT_GEMM_I8_DEBUG,    // timing probes of the INT8 kernel (results meaningless)
+    OPT_GEMM_TILE,        // DMMA tile override: 0 auto, 2 small, 3 wide, 6 previous default
+    OPT_GEMM_TMA,         // TMA-staged DMMA kernel for k-major operands (default 1)
+    OPT_GRAPHS,           // CUDA-graph replay of pointer/shape-only launch sequences (default 1)
+    OPT_I8_FALLBACK,      // re-run a factorisation on the DMMA kernels when the INT8 path reports a non-PD pivot (default 1)
+    OPT_PREDICT_BLOCK,    // block width of the left-looking predict solve against cached digit planes (0 = recursion)
+    OPT_COUNT
+};
+int64_t option(Option o);
+uint64_t option_epoch();  // bumped by every gpb_set_option: contexts drop their captured graphs when it changes
+// per-thread override of OPT_GEMM_I8 (-1 = none): the DMMA retry after a failed INT8 factorisation
+int gemm_i8_override();
+void set_gemm_i8_override(int v);
 
 // ---------------------------------------------------------------- model description (kernels.cu)
 enum CovKind : int { COV_SE = 0, COV_RQ = 1, COV_WHITE = 2, COV_HETERO = 3 };

@@ -84,6 +84,8 @@ struct gpb_ctx {
     double *S = nullptr, *dots = nullptr, *G = nullptr, *qbuf = nullptr, *o1 = nullptr, *o2 = nullptr, *o3 = nullptr,
            *R_dev = nullptr;
     size_t S_cap = 0, dots_cap = 0, G_cap = 0, qbuf_cap = 0, o1_cap = 0, o2_cap = 0, o3_cap = 0, R_cap = 0;
+    char* argws = nullptr;  // arg-best reduction workspace (values, then indices)
+    size_t argws_cap = 0;
     gpb::PhaseTimer timer;
     // CUDA-graph cache of the pointer/shape-only launch sequences (potrf, solves, inverse, predict solve)
     struct GraphEntry {
@@ -94,6 +96,8 @@ struct gpb_ctx {
     };
     std::map<std::string, GraphEntry> graphs;
     bool use_graphs = true;
+    uint64_t opt_epoch = 0;  // option_epoch() the graphs were recorded under
+    int64_t dmma_retries = 0;  // factorisations repeated on the DMMA kernels after the INT8 path reported info > 0
     gpb_dist* dist = nullptr;
     gpb_linv* linv = nullptr;
 };

@@ -140,8 +140,16 @@ void dist_destroy(gpb_ctx* c) {
         if (p) cudaFree(p);
     if (d->info) cudaFree(d->info);
     for (auto e : d->events) cudaEventDestroy(e);
-    if (d->s_panel) cudaStreamDestroy(d->s_panel);
-    if (d->s_comm) cudaStreamDestroy(d->s_comm);
+    // the INT8 GEMM keeps a digit-plane workspace per (device, stream): free it with the stream, or it leaks on every
+    // init / finalize cycle and a later stream that reuses the handle would inherit stale buffers
+    if (d->s_panel) {
+        gemm_i8_release(d->s_panel);
+        cudaStreamDestroy(d->s_panel);
+    }
+    if (d->s_comm) {
+        gemm_i8_release(d->s_comm);
+        cudaStreamDestroy(d->s_comm);
+    }
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     delete d;
     c->dist = nullptr;

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 namespace gpb {
 namespace {
@@ -231,8 +232,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) dgemm_kernel(const Ge
 int gemm_nt_tma(const GemmArgs& a, cudaStream_t s, double* flops_out);  // gemm_tma.cu
 int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out);   // gemm_i8.cu
 
-static double g_gemm_flops = 0.0, g_gemm_flops_i8 = 0.0;  // all GEMM launches; the share issued on the INT8 path
-
 template <class C>
 int launch_cfg(const GemmArgs& a, cudaStream_t s) {
     constexpr int THREADS = C::THREADS;
@@ -241,16 +240,16 @@ int launch_cfg(const GemmArgs& a, cudaStream_t s) {
     const bool akm = !(a.flags & GEMM_A_MMAJOR), bkm = !(a.flags & GEMM_B_NMAJOR);
     kern_t kern = akm ? (bkm ? dgemm_kernel<true, true, C> : dgemm_kernel<true, false, C>)
                       : (bkm ? dgemm_kernel<false, true, C> : dgemm_kernel<false, false, C>);
-    static bool configured_dev[64][4] = {};
+    static std::once_flag configured_dev[64][4];  // per device and operand layout; worker threads may race here
     int dev = 0;
     GPB_CUDA(cudaGetDevice(&dev));
-    bool* configured = configured_dev[dev & 63];
     const int ki = (akm ? 0 : 2) + (bkm ? 0 : 1);
-    if (!configured[ki]) {
-        GPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured[ki] = true;
-    }
+    cudaError_t cfg_err = cudaSuccess;
+    std::call_once(configured_dev[dev & 63][ki], [&]() {
+        cfg_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (cfg_err == cudaSuccess) cfg_err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    });
+    GPB_CUDA(cfg_err);
     const int tm = a.M / BM, tn = a.N / BN;
     const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) : (int64_t)tm * tn;
     kern<<<(unsigned)tiles, THREADS, C::SMEM_BYTES, s>>>(a, tn);
@@ -258,7 +257,7 @@ int launch_cfg(const GemmArgs& a, cudaStream_t s) {
     count_launch();
     // algorithmic flops of this launch (2 * BM * BN * k-extent per computed tile)
     if (!(a.flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) {
-        g_gemm_flops += (double)tiles * 2.0 * BM * BN * a.K;
+        credit_gemm_flops((double)tiles * 2.0 * BM * BN * a.K, 0.0);
     } else {
         double kext = 0.0;
         for (int bi = 0; bi < tm; ++bi) {
@@ -272,7 +271,7 @@ int launch_cfg(const GemmArgs& a, cudaStream_t s) {
                 kext += std::max(0, ke - kb);
             }
         }
-        g_gemm_flops += kext * 2.0 * BM * BN;
+        credit_gemm_flops(kext * 2.0 * BM * BN, 0.0);
     }
     return 0;
 }
@@ -292,15 +291,15 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     const int64_t tm = a.M / 128, tn = a.N / 64;
     const int64_t big_tiles = (a.flags & GEMM_LOWER) ? tm * (tm + 1) : tm * tn;
     // INT8 tensor-core path (gemm_i8.cu: exact digit splitting, 28 int8 GEMMs per FP64 GEMM) for long k extents
-    static const int use_i8 = getenv("GPB200_GEMM_I8") ? atoi(getenv("GPB200_GEMM_I8")) : 1;
-    static const int i8_min_k = getenv("GPB200_GEMM_I8_MINK") ? atoi(getenv("GPB200_GEMM_I8_MINK")) : 512;  // measured break-even ~K = 256-384 (profiles/gemm_i8_r1_ksweep.json)
+    // (gpb_set_option "gemm_i8": 0 off, 1 where it pays, 2 wherever it applies; a thread's DMMA retry overrides it)
+    const int use_i8 = gemm_i8_override() >= 0 ? gemm_i8_override() : (int)option(OPT_GEMM_I8);
+    const int i8_min_k = (int)option(OPT_GEMM_I8_MIN_K);  // measured break-even ~K = 256-384 (profiles/gemm_i8_r1_ksweep.json)
     if (use_i8 && a.K >= i8_min_k && (big_tiles >= 148 || use_i8 == 2)) {  // 2 = force (tests)
         double fl = 0.0;
         const int rc = gemm_nt_i8(a, s, &fl);
         if (rc < 0) return rc;
         if (rc == 0) {
-            g_gemm_flops += fl;
-            g_gemm_flops_i8 += fl;
+            credit_gemm_flops(fl, fl);
             return 0;
         }
     }
@@ -308,29 +307,22 @@ int gemm_nt(const GemmArgs& a, cudaStream_t s) {
     // (default: a third resident warp per scheduler covers the other two's barrier / fragment-load gaps); the same
     // tile with 3 stages and 2 CTAs/SM 34.7; 8 warps of 32 x 32 <4,4,4,2> 33.7; BK=32 x 2 stages 34.1;
     // supertile rasterisation: no change.
-    static const int force = getenv("GPB200_GEMM_TILE") ? atoi(getenv("GPB200_GEMM_TILE")) : 0;  // 2 = small, 3 = wide
+    const int force = (int)option(OPT_GEMM_TILE);  // 2 = small, 3 = wide
     const int pick = force ? force : (big_tiles < 296 ? 2 : 3);
     if (pick == 2) return launch_cfg<Cfg<4, 2, 2, 2>>(a, s);
     if (pick == 6) return launch_cfg<Cfg<8, 4, 2, 2>>(a, s);  // previous default: 3 stages, 2 CTAs/SM (34.7 TF/s)
-    static const int use_tma = getenv("GPB200_GEMM_TMA") ? atoi(getenv("GPB200_GEMM_TMA")) : 1;
+    const int use_tma = (int)option(OPT_GEMM_TMA);
     if (use_tma && pick == 3) {  // TMA-staged variant (gemm_tma.cu) for k-major operands
         double fl = 0.0;
         const int rc = gemm_nt_tma(a, s, &fl);
         if (rc < 0) return rc;
         if (rc == 0) {
             count_launch();
-            g_gemm_flops += fl;
+            credit_gemm_flops(fl, 0.0);
             return 0;
         }
     }
     return launch_cfg<Cfg<8, 4, 2, 2, 16, 2, 3>>(a, s);
-}
-
-double gemm_flops_issued() { return g_gemm_flops; }
-double gemm_flops_issued_i8() { return g_gemm_flops_i8; }
-void credit_gemm_flops(double f, double f_i8) {
-    g_gemm_flops += f;
-    g_gemm_flops_i8 += f_i8;
 }
 
 }  // namespace gpb

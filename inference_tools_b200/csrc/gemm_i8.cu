@@ -691,16 +691,14 @@ using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, voi
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeFn get_encode() {
-    static EncodeFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeFn fn = []() -> EncodeFn {  // function-local static: initialised once, thread-safe
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeFn>(p);
-    }
+            return reinterpret_cast<EncodeFn>(p);
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -791,7 +789,7 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     // CTA pairs (256 x 128 tiles) whenever the rows allow it; GPB200_GEMM_I8_PAIR=0 forces single-CTA tiles.
     // Measured on B200 at 8192^3: 9.65 ms against 10.44 ms -- the pair reads 6 KB instead of 8 KB of shared memory per
     // MMA; its loads have a longer round trip (credited to the leader's barrier) and now set the pace.
-    static const int pair_env = getenv("GPB200_GEMM_I8_PAIR") ? atoi(getenv("GPB200_GEMM_I8_PAIR")) : 1;
+    const int pair_env = (int)option(OPT_GEMM_I8_PAIR);
     const int ctas = (pair_env && a.M % (2 * BM) == 0) ? 2 : 1;
     const int bmt = BM * ctas;
     const int tm = a.M / bmt, tn = a.N / BN;
@@ -826,7 +824,7 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
             set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
             return -3;
         }
-        static const int debug = getenv("GPB200_GEMM_I8_DEBUG") ? atoi(getenv("GPB200_GEMM_I8_DEBUG")) : 0;
+        const int debug = (int)option(OPT_GEMM_I8_DEBUG);
         I8Args p{a.M, a.N, Kc, w->sa, w->sb, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2,
                  a.alpha, c == 0 ? a.beta : 1.0, a.flags | (debug << 20), tm, tn, w->scratch, k0, a.K};
         if (ctas == 1) {

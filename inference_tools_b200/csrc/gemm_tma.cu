@@ -12,6 +12,7 @@
 
 #include <cuda.h>
 #include <cstdlib>
+#include <mutex>
 
 namespace gpb {
 namespace {
@@ -175,16 +176,14 @@ using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, voi
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeFn get_encode() {
-    static EncodeFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeFn fn = []() -> EncodeFn {  // function-local static: initialised once, thread-safe
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeFn>(p);
-    }
+            return reinterpret_cast<EncodeFn>(p);
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -211,14 +210,16 @@ int gemm_nt_tma(const GemmArgs& a, cudaStream_t s, double* flops_out) {
         return 1;
     CUtensorMap tmA, tmB;
     if (make_map(&tmA, a.A, a.M, a.K, a.lda, BM) || make_map(&tmB, a.B, a.N, a.K, a.ldb, BN)) return 1;
-    static bool configured_dev[64] = {};
+    static std::once_flag configured_dev[64];
     int dev = 0;
     GPB_CUDA(cudaGetDevice(&dev));
-    if (!configured_dev[dev & 63]) {
-        GPB_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured_dev[dev & 63] = true;
-    }
+    cudaError_t cfg_err = cudaSuccess;
+    std::call_once(configured_dev[dev & 63], [&]() {
+        cfg_err = cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (cfg_err == cudaSuccess)
+            cfg_err = cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    });
+    GPB_CUDA(cfg_err);
     const int tm = a.M / BM, tn = a.N / BN;
     const int64_t tiles = (a.flags & GEMM_LOWER) ? (int64_t)tm * (tm + 1) : (int64_t)tm * tn;
     dgemm_tma_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(tmA, tmB, a, tn);

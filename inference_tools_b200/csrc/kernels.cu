@@ -448,15 +448,33 @@ __global__ void finalize_spatial_kernel(const double* __restrict__ dots, const d
     }
 }
 
-// acquisition.py:76-125.  Branch at Z < -3 exactly as the reference.
-__global__ void ei_kernel(const double* __restrict__ mu, const double* __restrict__ sig,
-                          const double* __restrict__ dmu, const double* __restrict__ dvar, int m, int d, double y_max,
-                          int mode, double* __restrict__ out, double* __restrict__ grad) {
+// Acquisition functions over a batch of candidates (acquisition.py:76-125 ExpectedImprovement, :169-189
+// UpperConfidenceBound, :213-229 MaxVariance).  mode 0: value, 1: opt_func (the minimiser's objective), 2: opt_func and its
+// gradient.  EI branches at Z < -3 exactly as the reference.
+__global__ void acquisition_kernel(const double* __restrict__ mu, const double* __restrict__ sig,
+                                   const double* __restrict__ dmu, const double* __restrict__ dvar, int m, int d, int kind,
+                                   double param, int mode, double* __restrict__ out, double* __restrict__ grad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
+    const double s = sig[i];
+    if (kind == 1) {  // UCB: param = kappa
+        const double ucb = mu[i] + param * s;
+        out[i] = mode == 0 ? ucb : -ucb;
+        if (mode == 2)
+            for (int a = 0; a < d; ++a)
+                grad[(int64_t)i * d + a] = -(dmu[(int64_t)i * d + a] + 0.5 * param * dvar[(int64_t)i * d + a] / s);
+        return;
+    }
+    if (kind == 2) {  // MaxVariance
+        const double v = s * s;
+        out[i] = mode == 0 ? v : -v;
+        if (mode == 2)
+            for (int a = 0; a < d; ++a) grad[(int64_t)i * d + a] = -dvar[(int64_t)i * d + a];
+        return;
+    }
+    const double y_max = param;
     const double ir2pi = 0.3989422804014327, ir2 = 0.7071067811865476, rpi2 = 1.2533141373155003,
                  ln2pi = 1.8378770664093453;
-    const double s = sig[i];
     const double Z = (mu[i] - y_max) / s;
     if (Z < -3.0) {
         const double R = rpi2 * erfcx(-Z * ir2);
@@ -477,6 +495,47 @@ __global__ void ei_kernel(const double* __restrict__ mu, const double* __restric
             for (int a = 0; a < d; ++a)
                 grad[(int64_t)i * d + a] =
                     -((0.5 * pdf * dvar[(int64_t)i * d + a] / s + dmu[(int64_t)i * d + a] * cdf) / ei);
+    }
+}
+
+// Index of the best entry of v[0..m): the largest (want_max) or the smallest; ties go to the lowest index and NaNs never
+// win, exactly like a left-to-right host scan with a strict comparison.  Stage 1: one (value, index) pair per CTA;
+// stage 2 (one CTA) reduces the pairs.  No atomics: fixed order, bit-reproducible.
+__device__ __forceinline__ bool better(double a, int64_t ia, double b, int64_t ib, bool want_max) {
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    const bool gt = want_max ? a > b : a < b;
+    return gt || (a == b && ia < ib);
+}
+__global__ void __launch_bounds__(256) argbest_kernel(const double* __restrict__ v, const int64_t* __restrict__ idx_in,
+                                                      int64_t m, int want_max, double* __restrict__ val_out,
+                                                      int64_t* __restrict__ idx_out) {
+    __shared__ double sv[256];
+    __shared__ int64_t si[256];
+    double bv = 0.0;
+    int64_t bi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (int64_t)gridDim.x * 256) {
+        const double x = v[i];
+        const int64_t ix = idx_in ? idx_in[i] : i;
+        if (x != x || ix < 0) continue;
+        if (better(x, ix, bv, bi, want_max != 0)) {
+            bv = x;
+            bi = ix;
+        }
+    }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o && better(sv[threadIdx.x + o], si[threadIdx.x + o], sv[threadIdx.x], si[threadIdx.x], want_max != 0)) {
+            sv[threadIdx.x] = sv[threadIdx.x + o];
+            si[threadIdx.x] = si[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        val_out[blockIdx.x] = sv[0];
+        idx_out[blockIdx.x] = si[0];
     }
 }
 
@@ -593,11 +652,21 @@ int launch_finalize_spatial(const double* dots, const double* G, int mq, int d, 
     GPB_LAUNCH_CHECK();
 }
 
-int launch_ei(const double* mu, const double* sig, const double* dmu, const double* dvar, int m, int d, double y_max,
-              int mode, double* out, double* grad, cudaStream_t s) {
+int launch_acquisition(const double* mu, const double* sig, const double* dmu, const double* dvar, int m, int d, int kind,
+                       double param, int mode, double* out, double* grad, cudaStream_t s) {
     if (m == 0) return 0;
-    ei_kernel<<<(m + 255) / 256, 256, 0, s>>>(mu, sig, dmu, dvar, m, d, y_max, mode, out, grad);
+    acquisition_kernel<<<(m + 255) / 256, 256, 0, s>>>(mu, sig, dmu, dvar, m, d, kind, param, mode, out, grad);
     GPB_LAUNCH_CHECK();
+}
+
+int launch_argbest(const double* v, int64_t m, int want_max, double* ws_val, int64_t* ws_idx, cudaStream_t s) {
+    const int blocks = (int)std::min<int64_t>(ARGBEST_BLOCKS, (m + 255) / 256);
+    argbest_kernel<<<blocks, 256, 0, s>>>(v, nullptr, m, want_max, ws_val + 1, ws_idx + 1);
+    GPB_CUDA(cudaGetLastError());
+    argbest_kernel<<<1, 256, 0, s>>>(ws_val + 1, ws_idx + 1, blocks, want_max, ws_val, ws_idx);
+    GPB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return 0;
 }
 
 int launch_residual(const MeanParams& mp, const double* x, const double* y, int n, int npad, double* resid,

@@ -38,9 +38,14 @@ int launch_finalize_gradient(const double* dots, const double* G, int mq, int d,
 // spatial_derivatives() outputs (regression.py:413-414): dmu = dots rows a>=1; dvar[q][a] = -2 G[q][0][a+1]
 int launch_finalize_spatial(const double* dots, const double* G, int mq, int d, double* dmu, double* dvar,
                             cudaStream_t s);
-// ExpectedImprovement (acquisition.py:76-125). mode 0: EI, 1: -ln EI, 2: -ln EI and its gradient
-int launch_ei(const double* mu, const double* sig, const double* dmu, const double* dvar, int m, int d, double y_max,
-              int mode, double* out, double* grad, cudaStream_t s);
+// Acquisition functions (acquisition.py:76-125 EI, :169-189 UCB, :213-229 MaxVariance): kind 0 EI (param = y_max),
+// 1 UCB (param = kappa), 2 MaxVariance.  mode 0: value, 1: opt_func, 2: opt_func and its gradient
+int launch_acquisition(const double* mu, const double* sig, const double* dmu, const double* dvar, int m, int d, int kind,
+                       double param, int mode, double* out, double* grad, cudaStream_t s);
+// index of the largest / smallest entry (lowest index on ties, NaNs ignored, -1 when there is none): result in
+// ws_val[0] / ws_idx[0]; both workspaces hold 1 + ARGBEST_BLOCKS entries
+constexpr int ARGBEST_BLOCKS = 592;
+int launch_argbest(const double* v, int64_t m, int want_max, double* ws_val, int64_t* ws_idx, cudaStream_t s);
 // resid = y - mean(x) (regression.py:243, 538); mu_out optional
 int launch_residual(const MeanParams& mp, const double* x, const double* y, int n, int npad, double* resid,
                     double* mu_out, cudaStream_t s);

@@ -12,6 +12,7 @@
 // Leaves are 128 x 128: one CTA factors the diagonal block in shared memory (warp-parallel
 // right-looking sweep) and also leaves its explicit inverse, so every leaf solve is a GEMM too.
 #include "kernels.cuh"
+#include <mutex>
 
 namespace gpb {
 namespace {
@@ -215,13 +216,14 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
 }
 
 int launch_diag(double* A, int64_t ld, int blk, const LinalgWs& ws, cudaStream_t s) {
-    static bool configured_dev[64] = {};
+    static std::once_flag configured_dev[64];
     int dev = 0;
     GPB_CUDA(cudaGetDevice(&dev));
-    if (!configured_dev[dev & 63]) {
-        GPB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-        configured_dev[dev & 63] = true;
-    }
+    cudaError_t cfg_err = cudaSuccess;
+    std::call_once(configured_dev[dev & 63], [&]() {
+        cfg_err = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
+    });
+    GPB_CUDA(cfg_err);
     potrf_diag_kernel<<<1, 256, DIAG_SMEM, s>>>(A, ld, ws.dinv + (int64_t)blk * NB * NB, ws.info, blk * NB);
     GPB_CUDA(cudaGetLastError());
     count_launch();

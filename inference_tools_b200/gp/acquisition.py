@@ -1,8 +1,9 @@
 """Acquisition functions with the interface of ``inference.gp.acquisition`` (reference
-acquisition.py:8-232).  ``ExpectedImprovement`` evaluates on the GPU: the predictive mean / sigma (and
-their spatial derivatives) come from the batched solve and the EI / log-EI formulae, including the
-``Z < -3`` log-space branch through ``erfcx`` (acquisition.py:79-81, 104-114), run in the ``ei_kernel``
-epilogue.  Besides the reference's one-point-per-call methods every class offers ``batch(points)``
+acquisition.py:8-232).  All three evaluate on the GPU: the predictive mean / sigma (and their spatial
+derivatives) come from the batched solve, and the acquisition formulae -- EI / log-EI including the
+``Z < -3`` log-space branch through ``erfcx`` (acquisition.py:79-81, 104-114), UCB (:169-189), MaxVariance
+(:213-229) -- run in the ``acquisition_kernel`` epilogue; the best candidate of a batch is found by a device
+reduction.  Besides the reference's one-point-per-call methods every class offers ``batch(points)``
 for millions of candidates in one call (BASELINE.json config 4).
 """
 from __future__ import annotations
@@ -89,36 +90,37 @@ class ExpectedImprovement(AcquisitionFunction):
 
 
 class UpperConfidenceBound(AcquisitionFunction):
-    r"""UCB(x) = mu(x) + kappa sigma(x)  (reference acquisition.py:143-192)."""
+    r"""UCB(x) = mu(x) + kappa sigma(x)  (reference acquisition.py:143-192); evaluated by the same fused kernel as EI."""
 
     def __init__(self, kappa: float = 2.0):
         self.kappa = kappa
         self.name = "Upper confidence bound"
         self.convergence_description = r"$\mathrm{UCB}_{\mathrm{max}} - y_{\mathrm{max}}$"
 
+    def _run(self, x, mode):
+        p = self.gp.process_points(x)
+        return self.gp.engine.acquisition(_lib.ACQ_UCB, self.kappa, p, mode)
+
     def __call__(self, x) -> float:
-        mu, sig = self.gp(x)
-        return mu[0] + self.kappa * sig[0]
+        return self._run(x, _lib.ACQ_VALUE)[0][0]
 
     def opt_func(self, x) -> float:
-        mu, sig = self.gp(x)
-        return -mu[0] - self.kappa * sig[0]
+        return self._run(x, _lib.ACQ_OPT)[0][0]
 
     def opt_func_gradient(self, x):
-        mu, sig = self.gp(x)
-        dmu, dvar = self.gp.spatial_derivatives(x)
-        ucb = mu[0] + self.kappa * sig[0]
-        grad = dmu + 0.5 * self.kappa * dvar / sig[0]
-        return -ucb, -np.atleast_1d(grad).squeeze()
+        val, grad, _ = self._run(x, _lib.ACQ_OPT_GRAD)
+        return np.array(val[0]), grad[0].squeeze()
 
     def batch(self, points):
-        mu, sig = self.gp(points)
-        val = mu + self.kappa * sig
-        return val, int(val.argmax())
+        val, _, best = self._run(points, _lib.ACQ_VALUE)
+        return val, best
 
     def opt_func_batch(self, points):
-        mu, sig = self.gp(points)
-        return -mu - self.kappa * sig
+        return self._run(points, _lib.ACQ_OPT)[0]
+
+    def opt_func_gradient_batch(self, points):
+        val, grad, _ = self._run(points, _lib.ACQ_OPT_GRAD)
+        return val, grad
 
     def convergence_metric(self, x):
         return self.__call__(x) - self.mu_max
@@ -131,26 +133,30 @@ class MaxVariance(AcquisitionFunction):
         self.name = "Max variance"
         self.convergence_description = r"$\sqrt{\mathrm{Var}\left[x\right]}$"
 
+    def _run(self, x, mode):
+        p = self.gp.process_points(x)
+        return self.gp.engine.acquisition(_lib.ACQ_MAXVAR, 0.0, p, mode)
+
     def __call__(self, x) -> float:
-        _, sig = self.gp(x)
-        return sig[0] ** 2
+        return self._run(x, _lib.ACQ_VALUE)[0][0]
 
     def opt_func(self, x) -> float:
-        _, sig = self.gp(x)
-        return -sig[0] ** 2
+        return self._run(x, _lib.ACQ_OPT)[0][0]
 
     def opt_func_gradient(self, x):
-        _, sig = self.gp(x)
-        _, dvar = self.gp.spatial_derivatives(x)
-        return -sig[0] ** 2, -np.atleast_1d(dvar).squeeze()
+        val, grad, _ = self._run(x, _lib.ACQ_OPT_GRAD)
+        return np.array(val[0]), grad[0].squeeze()
 
     def batch(self, points):
-        _, sig = self.gp(points)
-        return sig**2, int(sig.argmax())
+        val, _, best = self._run(points, _lib.ACQ_VALUE)
+        return val, best
 
     def opt_func_batch(self, points):
-        _, sig = self.gp(points)
-        return -(sig**2)
+        return self._run(points, _lib.ACQ_OPT)[0]
+
+    def opt_func_gradient_batch(self, points):
+        val, grad, _ = self._run(points, _lib.ACQ_OPT_GRAD)
+        return val, grad
 
     def convergence_metric(self, x):
         return np.sqrt(self.__call__(x))

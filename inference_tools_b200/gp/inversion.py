@@ -31,7 +31,12 @@ class GpLinearInverter:
 
     Arguments as the reference constructor (inversion.py:55-63): ``y``, ``y_err`` (1D, equal size), ``model_matrix``
     (2D, ``(y.size, n_parameters)``), ``parameter_spatial_positions`` (2D, ``(n_parameters, n_dimensions)``),
-    ``prior_covariance_function`` and ``prior_mean_function`` as a class or an instance.  ``device`` selects the GPU.
+    ``prior_covariance_function`` and ``prior_mean_function`` as a class or an instance.  ``device`` selects the GPU
+    (default ``$GPB200_DEVICE`` / ``$LOCAL_RANK`` / 0, as ``GpRegressor``).
+
+    Difference from the reference: ``calculate_posterior(_mean)`` factor ``A K A^T + Sigma`` (Woodbury form) and raise
+    ``numpy.linalg.LinAlgError`` when that matrix is not positive definite, where the reference's general
+    ``solve(I + K W, K)`` (inversion.py:150-153) would still return a (meaningless) result.
     """
 
     def __init__(
@@ -42,7 +47,7 @@ class GpLinearInverter:
         parameter_spatial_positions: ndarray,
         prior_covariance_function: CovarianceFunction = SquaredExponential,
         prior_mean_function: MeanFunction = ConstantMean,
-        device: int = 0,
+        device: int = None,
     ):
         # the reference's checks, in its order and with its texts (inversion.py:64-112)
         A, pos = model_matrix, parameter_spatial_positions

@@ -86,3 +86,52 @@ def extrapolate(t, n_s, n, m_total):
     fit_grad = (t["grad_assemble"] + t["grad_trace"] + t["fit_assemble"]) * r**2 + (t["grad_lapack"] + t["fit_lapack"]) * r**3
     predict = t["predict_per_point"] * r**2 * m_total
     return fit_grad + predict, fit_grad, predict
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The UNMODIFIED reference (baseline/_ref, loaded by oracle/ref_loader.py) on the same step, at sizes it can allocate.
+def reference_timed_step(n_s, d, theta, m_s, seed=0):
+    """marginal_likelihood_gradient + set_hyperparameters + __call__ at m_s points of the reference's own GpRegressor
+    (RationalQuadratic + WhiteNoise, the benchmark's model) at sample size n_s; wall seconds per call, or None when no copy
+    of the reference is present on this host.  Construction (pass_spatial_data, bounds) is outside the step, as it is for
+    the engine."""
+    from oracle.ref_loader import load_reference_gp
+
+    ref = load_reference_gp()
+    if ref is None:
+        return None
+    x, y, e = synth(seed, n_s, d)
+    q = np.random.default_rng(seed + 1).uniform(0, 1, (m_s, d))
+    t0 = time.perf_counter()
+    g = ref.GpRegressor(x, y, y_err=e, kernel=ref.RationalQuadratic() + ref.WhiteNoise(), hyperpars=theta)
+    t = {"construct": time.perf_counter() - t0}
+    t0 = time.perf_counter()
+    lml, grad = g.marginal_likelihood_gradient(theta)
+    t["grad"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g.set_hyperparameters(theta)
+    t["fit"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mu, sig = g(q)
+    t["predict_per_point"] = (time.perf_counter() - t0) / max(1, m_s)
+    t["_check"] = float(lml) + float(np.sum(grad)) + float(mu[-1])
+    return t
+
+
+def reference_extrapolate(t1, n1, t2, n2, n, m_total):
+    """Full-step seconds at (n, m_total) from two sample sizes: every call is modelled as a N^2 + b N^3 (assembly, traces
+    and per-point solves are N^2; dpotrf, the explicit inverse and iK.T @ iK are N^3) with a, b >= 0 fitted through the two
+    measurements; the per-point predict cost is pure N^2 (one dtrtrs against L per point, regression.py:213)."""
+    out = {}
+    for key in ("grad", "fit"):
+        a1, a2 = t1[key], t2[key]
+        # a n1^2 + b n1^3 = a1 ; a n2^2 + b n2^3 = a2
+        det = n1**2 * n2**3 - n2**2 * n1**3
+        a = (a1 * n2**3 - a2 * n1**3) / det
+        b = (n1**2 * a2 - n2**2 * a1) / det
+        if a < 0 or b < 0:       # degenerate fit: fall back to the pessimistic-for-us pure N^2 / optimistic pure N^3 mix
+            a, b = 0.0, a2 / n2**3
+        out[key] = a * n**2 + b * n**3
+    out["predict"] = t2["predict_per_point"] * (n / n2) ** 2 * m_total
+    out["step"] = out["grad"] + out["fit"] + out["predict"]
+    return out

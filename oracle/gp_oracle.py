@@ -421,6 +421,80 @@ def marginal_likelihood_gradient(x, y, comps, mean, theta, noise_var=None, y_cov
     return lml, grad
 
 
+def _leaf_rows_and_grads(kind, th, x, r0, r1):
+    """Rows [r0, r1) of one plain kernel on the training data and of its gradient planes: the same expressions as
+    _leaf_cov_and_grads (covariance.py:268-276, 350-365, 171-175), built for a row block only."""
+    n, d = x.shape
+    xr = x[r0:r1]
+    idx = np.arange(r0, r1)
+    grads = []
+    if kind == "SE":
+        a, ls = np.exp(th[0]), np.exp(th[1:])
+        e = np.exp(-_scaled_half_sqdist(xr, x, ls))
+        e[idx - r0, idx] += EPS_JITTER
+        k = a**2 * e
+        grads.append(2.0 * k)
+        for i in range(d):
+            grads.append(((xr[:, i, None] - x[None, :, i]) ** 2 / ls[i] ** 2) * k)
+    elif kind == "RQ":
+        a, q, ls = np.exp(th[0]), np.exp(th[1]), np.exp(th[2:])
+        z = _scaled_half_sqdist(xr, x, ls)
+        f = 1 + z / q
+        lnf = np.log(f)
+        e = np.exp(-q * lnf)
+        e[idx - r0, idx] += EPS_JITTER
+        k = a**2 * e
+        grads.append(2.0 * k)
+        grads.append(-k * (lnf * q - z / f))
+        g = 2 * k / f
+        for i in range(d):
+            grads.append(g * (0.5 * (xr[:, i, None] - x[None, :, i]) ** 2 / ls[i] ** 2))
+    elif kind == "WHITE":
+        k = np.zeros((r1 - r0, n))
+        k[idx - r0, idx] = np.exp(2 * th[0])
+        grads.append(2.0 * k)
+    else:
+        raise NotImplementedError("row-blocked gradients: SE / RQ / WHITE only")
+    return k, grads
+
+
+def marginal_likelihood_gradient_blocked(x, y, comps, mean, theta, noise_var=None, block=1024, want_parts=False):
+    """marginal_likelihood_gradient (regression.py:544-567) for sizes whose p dense gradient planes do not fit: the same
+    LAPACK / BLAS calls on K (cholesky, dtrtrs on the identity, iK.T @ iK, iK @ r), but K and the dK planes are built
+    one row block at a time and the traces 0.5 sum(Q * dK^T) are accumulated per block (dK is symmetric).  Plain SE / RQ /
+    WHITE sums only.  tests/test_oracle_golden.py pins it to marginal_likelihood_gradient and to the reference fixtures."""
+    x = np.asarray(x, dtype=float)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    n, d = x.shape
+    tm, parts = split_theta(theta, comps, mean, n, d)
+    assert parts.cp is None
+    xbar = x.mean(axis=0)
+    k = train_cov(comps, parts, x, noise_var)
+    mu = mean_vec(mean, tm, x, xbar)
+    L = cholesky(k)
+    del k
+    logdet = np.log(np.diagonal(L)).sum()
+    ik = solve_triangular(L, np.eye(n), lower=True, overwrite_b=True, check_finite=False)
+    del L
+    ik = ik.T @ ik
+    alpha = ik @ (y - mu)
+    lml = -0.5 * ((y - mu).T @ alpha) - logdet
+    grad = np.zeros(len(theta))
+    pm = len(tm)
+    grad[:pm] = [(alpha * g).sum() for g in mean_grads(mean, x, xbar)]
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        Q = alpha[r0:r1, None] * alpha[None, :] - ik[r0:r1]
+        for kind, th, _, off in parts:
+            _, gk = _leaf_rows_and_grads(kind, th, x, r0, r1)
+            for j, g in enumerate(gk):
+                grad[pm + off + j] += 0.5 * (Q * g).sum()
+    if want_parts:
+        return lml, grad, alpha
+    return lml, grad
+
+
 def loo_likelihood(x, y, comps, mean, theta, noise_var=None):
     """regression.py:468-487."""
     x = np.asarray(x, dtype=float)
@@ -525,6 +599,25 @@ def neg_log_ei_gradient(mu, sig, dmu, dvar, y_max):
             val[i] = np.log(ei)
             grad[i] = (0.5 * pdf * dvar[i] / s + dmu[i] * cdf) / ei
     return -val, -grad
+
+
+def upper_confidence_bound(mu, sig, kappa):
+    """UpperConfidenceBound.__call__ (acquisition.py:169-171): mu + kappa sigma; opt_func (:173-175) is its negative."""
+    return np.asarray(mu) + kappa * np.asarray(sig)
+
+
+def upper_confidence_bound_gradient(mu, sig, dmu, dvar, kappa):
+    """UpperConfidenceBound.opt_func_gradient (acquisition.py:177-189): (-(mu + kappa sigma), -(dmu + 0.5 kappa dvar / sigma))
+    for (M,) mu / sigma and (M, d) dmu / dvar."""
+    mu, sig = np.asarray(mu), np.asarray(sig)
+    dmu, dvar = np.asarray(dmu).reshape(mu.size, -1), np.asarray(dvar).reshape(mu.size, -1)
+    return -(mu + kappa * sig), -(dmu + 0.5 * kappa * dvar / sig[:, None])
+
+
+def max_variance(sig):
+    """MaxVariance.__call__ (acquisition.py:213-215): sigma^2; opt_func (:217-219) is its negative; opt_func_gradient
+    (:221-229) returns (-sigma^2, -dvar); convergence_metric (:231-232) is sigma."""
+    return np.asarray(sig) ** 2
 
 
 # ----------------------------------------------------------------------------- bounds

@@ -18,7 +18,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names(prefix_exclude=("fit_", "linv_")):
+def golden_names(prefix_exclude=("fit_", "linv_", "acq_")):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
     return [n for n in names if not n.startswith(prefix_exclude)]
 

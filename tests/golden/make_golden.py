@@ -234,9 +234,41 @@ def inverter_case(gp, name, comps, mean, seed):
     print(f"{name}: lml={out['lml']}")
 
 
+def acquisition_case(gp, name, seed, n, d, comps, kappa):
+    """UpperConfidenceBound / MaxVariance (acquisition.py:143-232), one point per call as the reference evaluates
+    them: __call__, opt_func, opt_func_gradient (SquaredExponential only) and convergence_metric."""
+    rng = np.random.default_rng(seed + 1000)
+    x, y, y_err = synth(seed, n, d)
+    theta = default_theta(comps, "const", n, d, rng)
+    g = gp.GpRegressor(x, y, y_err=y_err, kernel=make_kernel(gp, comps), hyperpars=theta)
+    q = np.concatenate([rng.uniform(-0.1, 1.1, (48, d)), rng.uniform(0.3, 0.7, (16, d))])
+    out = dict(x=x, y=y, y_err=y_err, theta=theta, q=q, comps=np.array(comps), mean=np.array("const"), kappa=np.float64(kappa))
+    ucb, mv = gp.UpperConfidenceBound(kappa=kappa), gp.MaxVariance()
+    for tag, acq in (("ucb", ucb), ("mv", mv)):
+        acq.update_gp(g)
+        out[tag] = np.array([acq(p) for p in q])
+        out[tag + "_optfunc"] = np.array([acq.opt_func(p) for p in q])
+        out[tag + "_metric"] = np.array([acq.convergence_metric(p) for p in q])
+        if comps == ("SE",):
+            vg = [acq.opt_func_gradient(p) for p in q]
+            out[tag + "_optfunc_g_val"] = np.array([float(np.squeeze(v[0])) for v in vg])
+            out[tag + "_optfunc_g_grad"] = np.array([np.atleast_1d(v[1]) for v in vg])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: N={n} d={d} comps={comps} ucb[0]={out['ucb'][0]:.6f} mv[0]={out['mv'][0]:.6e}")
+
+
+def acquisition_cases(gp):
+    acquisition_case(gp, "acq_se_d2_n60", 61, 60, 2, ("SE",), 2.0)
+    acquisition_case(gp, "acq_se_d1_n40", 62, 40, 1, ("SE",), 0.7)
+    acquisition_case(gp, "acq_rqwhite_d3_n80", 63, 80, 3, ("RQ", "WHITE"), 3.5)
+
+
 def main():
     warnings.simplefilter("ignore")
     gp = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "acq":   # only the acquisition fixtures (added in round 2)
+        return acquisition_cases(gp)
+    acquisition_cases(gp)
     demo_case(gp)
     # small dense cases: K, L, dK stored
     case(gp, "se_d2_n32_const", 11, 32, 2, ("SE",), "const", store_k=True, loo=True)

@@ -1,0 +1,94 @@
+"""GPU parity at the sizes where the default dispatch runs on the INT8 tensor-core GEMM (pytest -m gpu).
+
+BASELINE.json config 2 size (N = 8192): alpha, mu / sigma at 256 points, the log marginal likelihood AND its gradient
+against the CPU oracle at the north_star tolerance (1e-9 relative; the gradient norm-relative), with the default GEMM
+dispatch and an assertion that the INT8 path carried the flops -- so the path the headline benchmark runs on is the path
+that is checked.  The oracle side is the row-blocked restatement pinned in tests/test_oracle_golden.py.
+tools/parity_at_scale.py repeats this at N = 16384 and 32768 (minutes of CPU; results under profiles/)."""
+import numpy as np
+import pytest
+from numpy.linalg import LinAlgError
+
+from conftest import rel_err, synth
+import inference_tools_b200.gp as gp
+from inference_tools_b200 import _lib
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("d,comps", [(3, ("SE",)), (5, ("RQ", "WHITE"))])
+def test_config2_size_against_oracle_on_the_int8_path(d, comps):
+    n = 8192
+    x, y, e = synth(4242 + d, n, d)
+    if comps == ("SE",):
+        kernel, theta = gp.SquaredExponential(), np.array([0.3, 0.1] + [np.log(0.35)] * d)
+    else:
+        kernel, theta = gp.RationalQuadratic() + gp.WhiteNoise(), np.array([0.2, 0.1, 1.0] + [np.log(0.3)] * d + [np.log(0.05)])
+    q = np.random.default_rng(d).uniform(0, 1, (256, d))
+    lib = _lib.load_library()
+    f0, i0 = lib.gpb_gemm_flops(), lib.gpb_gemm_flops_int8()
+    m = gp.GpRegressor(x, y, y_err=e, kernel=kernel, hyperpars=theta)
+    mu, sig = m(q)
+    lml, grad = m.marginal_likelihood_gradient(theta)
+    lml_v = m.marginal_likelihood(theta)
+    share = (lib.gpb_gemm_flops_int8() - i0) / (lib.gpb_gemm_flops() - f0)
+    assert share > 0.9, f"INT8 path carried only {share:.2f} of the GEMM flops"
+
+    lml_o, grad_o = orc.marginal_likelihood_gradient_blocked(x, y, comps, "const", theta, e**2)
+    ref = orc.Fit(x, y, comps, "const", theta, e**2)
+    mu_o, sig_o = ref.predict(q)
+    assert rel_err(m.alpha, ref.alpha) < TOL
+    assert rel_err(mu, mu_o) < TOL and np.abs(sig / sig_o - 1).max() < TOL
+    assert abs(lml - lml_o) <= TOL * abs(lml_o) and abs(lml_v - lml_o) <= TOL * abs(lml_o)
+    assert np.abs(grad - grad_o).max() <= TOL * np.abs(grad_o).max()
+    # and the two GEMM implementations agree with each other far inside the tolerance
+    with _lib.options(gemm_i8=0):
+        lml_d, grad_d = m.marginal_likelihood_gradient(theta)
+    assert abs(lml - lml_d) <= 1e-11 * abs(lml_d) and np.abs(grad - grad_d).max() <= 1e-10 * np.abs(grad_d).max()
+
+
+@pytest.mark.parametrize("sigma_n,ls", [(0.003, 0.3), (0.0003, 1.0)])
+def test_ill_conditioned_kernels_int8_vs_dmma_vs_oracle(sigma_n, ls):
+    """cond(K) ~ 1e7 .. 1e11 (near-noise-free smooth kernel, SURVEY.md 8d parity floor): the INT8 path must not report a
+    spurious non-PD matrix, and must stay as close to the oracle as the DMMA path does (within a factor 10 or 1e-9)."""
+    n, d = 4096, 3
+    x, y, e = synth(7, n, d, sigma_n)
+    theta = np.array([0.3, 0.1] + [np.log(ls)] * d)
+    q = np.random.default_rng(1).uniform(0, 1, (128, d))
+    lml_o, grad_o = orc.marginal_likelihood_gradient_blocked(x, y, ("SE",), "const", theta, e**2)
+    ref = orc.Fit(x, y, ("SE",), "const", theta, e**2)
+    mu_o, sig_o = ref.predict(q)
+    err = {}
+    for mode, opts in (("int8", {"gemm_i8": 2, "gemm_i8_min_k": 64}), ("dmma", {"gemm_i8": 0})):
+        with _lib.options(**opts):
+            m = gp.GpRegressor(x, y, y_err=e, hyperpars=theta)       # LinAlgError here = spurious info > 0
+            lml, grad = m.marginal_likelihood_gradient(theta)
+            mu, sig = m(q)
+            err[mode] = {"lml": abs(lml - lml_o) / abs(lml_o), "grad": rel_err(grad, grad_o), "mu": rel_err(mu, mu_o),
+                         "alpha": rel_err(m.alpha, ref.alpha)}
+    for k in err["int8"]:
+        assert err["int8"][k] <= max(10 * err["dmma"][k], TOL), (k, err)
+
+
+def test_spurious_non_pd_on_the_int8_path_is_rechecked_on_dmma():
+    """gpb_factor / gpb_lml(_grad): info > 0 from a factorisation whose GEMMs ran on the INT8 path is confirmed on the
+    DMMA kernels before it is reported (option "i8_fallback"); a genuinely indefinite matrix still fails."""
+    n, d = 2048, 2
+    x, y, _ = synth(11, n, d, 0.01)
+    x[1] = x[0]                                                         # duplicate point, no noise: singular up to jitter
+    theta = np.array([0.0, 0.0, np.log(0.5), np.log(0.5)])
+    with _lib.options(gemm_i8=2, gemm_i8_min_k=64):
+        m_ok = None
+        try:
+            m_ok = gp.GpRegressor(x, y, hyperpars=theta)
+        except LinAlgError:
+            pass
+    with _lib.options(gemm_i8=0):
+        try:
+            gp.GpRegressor(x, y, hyperpars=theta)
+            dmma_ok = True
+        except LinAlgError:
+            dmma_ok = False
+    assert (m_ok is not None) == dmma_ok                                 # same verdict as the FP64 tensor path

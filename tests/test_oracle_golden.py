@@ -126,3 +126,36 @@ def test_linear_inverter_matches_reference(name):
         assert np.abs(grad - g["lml_grad"][i]).max() <= 1e-9 * np.abs(g["lml_grad"][i]).max()
         mu, cov = inv.calculate_posterior(th)
         assert rel_err(mu, g["post_mean"][i]) < 1e-9 and rel_err(cov, g["post_cov"][i]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["acq_se_d2_n60", "acq_se_d1_n40", "acq_rqwhite_d3_n80"])
+def test_ucb_and_max_variance_match_reference(name):
+    """UpperConfidenceBound / MaxVariance (acquisition.py:143-232) restated in the oracle against reference outputs."""
+    g = load_golden(name)
+    f = orc.Fit(g["x"], g["y"], g["comps"], g["mean"], g["theta"], g["noise_var"])
+    kappa = float(g["kappa"])
+    mu, sig = f.predict(g["q"])
+    assert rel_err(orc.upper_confidence_bound(mu, sig, kappa), g["ucb"]) < 1e-9
+    assert rel_err(-orc.upper_confidence_bound(mu, sig, kappa), g["ucb_optfunc"]) < 1e-9
+    assert rel_err(orc.upper_confidence_bound(mu, sig, kappa) - g["y"].max(), g["ucb_metric"]) < 1e-8
+    assert np.abs(orc.max_variance(sig) / g["mv"] - 1).max() < 1e-8
+    assert np.abs(np.sqrt(orc.max_variance(sig)) / g["mv_metric"] - 1).max() < 1e-8
+    if "ucb_optfunc_g_grad" in g:
+        dm, dv = f.spatial_derivatives(g["q"])
+        val, grad = orc.upper_confidence_bound_gradient(mu, sig, dm, dv, kappa)
+        assert rel_err(val, g["ucb_optfunc_g_val"]) < 1e-9
+        assert rel_err(grad, g["ucb_optfunc_g_grad"].reshape(grad.shape)) < 1e-8
+        assert rel_err(-np.asarray(dv).reshape(grad.shape), g["mv_optfunc_g_grad"].reshape(grad.shape)) < 1e-8
+        assert np.abs(-orc.max_variance(sig) / g["mv_optfunc_g_val"] - 1).max() < 1e-8
+
+
+@pytest.mark.parametrize("name", ["se_d3_n200_const", "rqwhite_d5_n257_const", "rqwhite_d3_n48_quadratic", "sewhite_d1_n40_const"])
+def test_row_blocked_gradient_matches_dense_oracle_and_reference(name):
+    """The memory-lean gradient used by tools/parity_at_scale.py (N = 16384 / 32768) is the same arithmetic."""
+    g = load_golden(name)
+    args = (g["x"], g["y"], g["comps"], g["mean"], g["theta"], g["noise_var"])
+    lml, grad = orc.marginal_likelihood_gradient_blocked(*args, block=37)
+    lml_d, grad_d = orc.marginal_likelihood_gradient(*args)
+    assert abs(lml - lml_d) <= 1e-13 * abs(lml_d) and np.abs(grad - grad_d).max() <= 1e-12 * np.abs(grad_d).max()
+    assert abs(lml - g["lml_from_grad"]) <= TOL * abs(g["lml_from_grad"])
+    assert np.abs(grad - g["lml_grad"]).max() <= 1e-9 * np.abs(g["lml_grad"]).max()

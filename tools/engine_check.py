@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from inference_tools_b200 import _lib
 from oracle import gp_oracle as orc
 
-lib = _lib.load_library()
+lib = _lib.load_test_library()
 dp = C.POINTER(C.c_double)
 lib.gpb_test_potrf.argtypes = [C.c_int, dp, dp, C.POINTER(C.c_int), C.c_int, dp]
 lib.gpb_test_inverse.argtypes = [C.c_int, dp, dp, dp, C.c_int, dp, dp]

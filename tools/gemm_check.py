@@ -1,7 +1,7 @@
 """GPU check of the DMMA GEMM primitive against numpy + timing (gpurun only)."""
 import ctypes, json, os, sys
 import numpy as np
-lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inference_tools_b200", "libgpb200.so"))
+lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inference_tools_b200", "libgpb200_test.so"))
 lib.gpb_last_error.restype = ctypes.c_char_p
 dp = ctypes.POINTER(ctypes.c_double)
 def P(a): return a.ctypes.data_as(dp) if a is not None else None

@@ -1,7 +1,7 @@
 """Large DMMA GEMM launches for ncu (never a bench number): 8192^3 NT, the SYRK shape, the predict shape."""
 import ctypes, os, sys
 import numpy as np
-lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inference_tools_b200", "libgpb200.so"))
+lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inference_tools_b200", "libgpb200_test.so"))
 dp = ctypes.POINTER(ctypes.c_double)
 P = lambda a: a.ctypes.data_as(dp) if a is not None else None
 rng = np.random.default_rng(0)

@@ -6,7 +6,7 @@ import numpy as np
 def run(mode):
     os.environ["GPB200_GEMM_I8"] = "2" if mode == "i8" else "0"
     os.environ["GPB200_GEMM_I8_MINK"] = "64"
-    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inference_tools_b200", "libgpb200.so"))
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inference_tools_b200", "libgpb200_test.so"))
     lib.gpb_last_error.restype = ctypes.c_char_p
     dp = ctypes.POINTER(ctypes.c_double)
     P = lambda a: a.ctypes.data_as(dp) if a is not None else None
