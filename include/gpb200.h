@@ -59,6 +59,8 @@ double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-cor
  *   "graphs"         CUDA-graph replay of launch sequences (1)
  *   "i8_fallback"    repeat a factorisation on DMMA when the INT8 path reports a non-PD pivot (1)
  *   "predict_block"  block width of the left-looking predict solve against cached digit planes (0 = recursion)
+ *   "i8_grad_guard"  a-posteriori error estimate of the INT8 inverse chain in gpb_lml_grad, DMMA repeat when it is too
+ *                    large relative to the gradient (1)
  * Changing an option drops every context's captured graphs at its next call. */
 int gpb_set_option(const char* name, int64_t value);
 int gpb_get_option(const char* name, int64_t* value);
@@ -100,6 +102,12 @@ int gpb_get(gpb_ctx* ctx, int which, double* out);
 int gpb_lml(gpb_ctx* ctx, const double* theta, double* lml, int* info);
 /* GpRegressor.marginal_likelihood_gradient (regression.py:544-567): grad has n_mean + n_cov entries */
 int gpb_lml_grad(gpb_ctx* ctx, const double* theta, double* lml, double* grad, int* info);
+/* The same for n_theta hyper-parameter vectors at once (thetas is n_theta x p row-major, p = n_mean + n_cov), sharded over
+ * nctx contexts that hold the same data and model on different GPUs: vector r runs on context r % nctx, each context on
+ * its own host thread.  Serves the multistart restarts (regression.py:585-605, the reference forks a process pool) and
+ * population-batched differential evolution (:569-574).  grad_or_null = NULL evaluates values only (gpb_lml). */
+int gpb_lml_grad_batch(gpb_ctx** ctxs, int nctx, const double* thetas, int n_theta, int p, double* lml,
+                       double* grad_or_null, int* info);
 /* GpRegressor.loo_likelihood / loo_likelihood_gradient / loo_predictions (regression.py:451-526) */
 int gpb_loo(gpb_ctx* ctx, const double* theta, double* loo, double* grad_or_null, int* info);
 int gpb_loo_predictions(gpb_ctx* ctx, double* mu, double* sigma);
@@ -125,13 +133,24 @@ int gpb_expected_improvement(gpb_ctx* ctx, const double* q, int64_t m, double y_
 int gpb_acquisition(gpb_ctx* ctx, int kind, double param, const double* q, int64_t m, int mode, double* out,
                     double* grad_or_null, int64_t* argbest_or_null);
 
-/* Distributed (one process per GPU) block-column-cyclic Cholesky + log marginal likelihood for N beyond one GPU
- * (BASELINE.json config 5).  Replaces regression.py:534-539 (build_covariance + cholesky + solve_triangular) when
- * the matrix is sharded; the only collective on the data path is the NCCL panel broadcast.  Rank 0 creates the
- * 128-byte NCCL unique id and shares it (torch.distributed / any channel); every rank then calls gpb_dist_init. */
+/* Distributed regressor (one process per GPU) for N beyond one GPU (BASELINE.json config 5): K(theta) + sig lives as
+ * block columns of width `block`, column j on rank j mod world; the only exchanges on the data path are NCCL broadcasts
+ * of column panels (and of solved nbd-vectors in the backward solve).  Rank 0 creates the 128-byte NCCL unique id and
+ * shares it (torch.distributed / any channel); every rank then calls gpb_dist_init.  All gpb_dist_* calls below are
+ * COLLECTIVE: every rank of the communicator must make them in the same order.
+ *   gpb_dist_factor   set_hyperparameters (regression.py:218-244): assemble own columns, right-looking blocked Cholesky
+ *                     with one-panel look-ahead; L stays sharded, v = L^-1 (y - mu) ends up on every rank
+ *   gpb_dist_lml      marginal_likelihood (regression.py:528-542) = gpb_dist_factor + -1/2 v.v - sum log L_ii
+ *   gpb_dist_alpha    alpha = L^-T v (regression.py:242-244), block back-substitution; alpha_out (n doubles, host) on
+ *                     every rank
+ *   gpb_dist_predict  __call__ (regression.py:188-216): each rank passes ITS OWN slab of query points (m may differ,
+ *                     may be 0); per chunk of queries the panels of L are streamed through all ranks */
 int gpb_dist_unique_id(char* out128);
 int gpb_dist_init(gpb_ctx* ctx, int rank, int world, const char* id128);
+int gpb_dist_factor(gpb_ctx* ctx, const double* theta, int block, int* info, double* seconds_out3);
 int gpb_dist_lml(gpb_ctx* ctx, const double* theta, int block, double* lml, int* info, double* seconds_out3);
+int gpb_dist_alpha(gpb_ctx* ctx, double* alpha_out);
+int gpb_dist_predict(gpb_ctx* ctx, const double* q, int64_t m, double* mu, double* sig);
 int gpb_dist_finalize(gpb_ctx* ctx);
 /* layout of the sweep for one rank (host-only, no GPU): block columns, owned ones, doubles of panel / staging storage */
 int gpb_dist_plan(int64_t n, int block, int world, int rank, int* n_blocks, int* n_owned, int64_t* panel_doubles,
@@ -149,6 +168,12 @@ int gpb_linv_set_problem(gpb_ctx* ctx, const double* A, int64_t m, const double*
 int gpb_linv_lml(gpb_ctx* ctx, const double* theta, double* lml, int* info);
 int gpb_linv_lml_grad(gpb_ctx* ctx, const double* theta, double* lml, double* grad, int* info);
 int gpb_linv_posterior(gpb_ctx* ctx, const double* theta, double* mean, double* cov_or_null, int* info);
+
+/* Counters of a context: "dmma_retries" (factorisations repeated on DMMA after the INT8 path reported a non-PD pivot),
+ * "grad_guard_retries" (gradient evaluations whose inverse chain was repeated on DMMA by the error guard),
+ * "grad_guard_est" (the guard's last estimate of the INT8 gradient error relative to max|grad|), "predict_block"
+ * (block width of the cached-plane predict solve, 0 = recursion). */
+int gpb_ctx_stat(gpb_ctx* ctx, const char* name, double* out);
 
 /* CUDA-event phase timings (milliseconds) of the most recent call on this context:
  * names is a ';'-separated list written into name_buf, ms[i] the matching durations. */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "gpb_get": (C.c_int, [_ctx_p, C.c_int, _dp]),
     "gpb_lml": (C.c_int, [_ctx_p, _dp, _dp, _ip]),
     "gpb_lml_grad": (C.c_int, [_ctx_p, _dp, _dp, _dp, _ip]),
+    "gpb_lml_grad_batch": (C.c_int, [C.POINTER(_ctx_p), C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, _ip]),
     "gpb_loo": (C.c_int, [_ctx_p, _dp, _dp, _dp, _ip]),
     "gpb_loo_predictions": (C.c_int, [_ctx_p, _dp, _dp]),
     "gpb_predict": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
@@ -54,13 +55,17 @@ SIGNATURES = {
     "gpb_acquisition": (C.c_int, [_ctx_p, C.c_int, C.c_double, _dp, C.c_int64, C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
     "gpb_dist_unique_id": (C.c_int, [C.c_char_p]),
     "gpb_dist_init": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_char_p]),
+    "gpb_dist_factor": (C.c_int, [_ctx_p, _dp, C.c_int, _ip, _dp]),
     "gpb_dist_lml": (C.c_int, [_ctx_p, _dp, C.c_int, _dp, _ip, _dp]),
+    "gpb_dist_alpha": (C.c_int, [_ctx_p, _dp]),
+    "gpb_dist_predict": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_dist_finalize": (C.c_int, [_ctx_p]),
     "gpb_dist_plan": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _ip]),
     "gpb_linv_set_problem": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_linv_lml": (C.c_int, [_ctx_p, _dp, _dp, _ip]),
     "gpb_linv_lml_grad": (C.c_int, [_ctx_p, _dp, _dp, _dp, _ip]),
     "gpb_linv_posterior": (C.c_int, [_ctx_p, _dp, _dp, _dp, _ip]),
+    "gpb_ctx_stat": (C.c_int, [_ctx_p, C.c_char_p, _dp]),
     "gpb_timers": (C.c_int, [_ctx_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
     "gpb_dev_alloc": (C.c_int, [_ctx_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "gpb_dev_free": (C.c_int, [_ctx_p, C.c_void_p]),
@@ -353,6 +358,26 @@ class Engine:
         self._check(self.lib.gpb_dist_lml(self._ctx, _ptr(th), block, C.byref(val), C.byref(info), secs))
         return val.value, info.value, {"assemble_s": secs[0], "factor_s": secs[1], "total_s": secs[2]}
 
+    def dist_factor(self, theta, block: int = 1024):
+        th = _f64(theta)
+        info = C.c_int(0)
+        secs = (C.c_double * 3)()
+        self._check(self.lib.gpb_dist_factor(self._ctx, _ptr(th), block, C.byref(info), secs))
+        return info.value, {"assemble_s": secs[0], "factor_s": secs[1], "total_s": secs[2]}
+
+    def dist_alpha(self):
+        out = np.empty(self.n)
+        self._check(self.lib.gpb_dist_alpha(self._ctx, _ptr(out)))
+        return out
+
+    def dist_predict(self, q):
+        """collective: this rank's slab of query points (may be empty) against the sharded factor"""
+        q = _f64(q).reshape(-1, self.d)
+        m = q.shape[0]
+        mu, sig = np.empty(m), np.empty(m)
+        self._check(self.lib.gpb_dist_predict(self._ctx, _ptr(q) if m else None, m, _ptr(mu) if m else None, _ptr(sig) if m else None))
+        return mu, sig
+
     def dist_finalize(self):
         self._check(self.lib.gpb_dist_finalize(self._ctx))
 
@@ -393,6 +418,11 @@ class Engine:
         keys = names.value.decode().split(";") if n.value else []
         return {k: ms[i] for i, k in enumerate(keys)}
 
+    def stat(self, name: str) -> float:
+        v = C.c_double(0)
+        self._check(self.lib.gpb_ctx_stat(self._ctx, name.encode(), C.byref(v)))
+        return v.value
+
     def launch_count(self):
         return int(self.lib.gpb_launch_count())
 
@@ -401,6 +431,24 @@ class Engine:
 
     def gemm_flops_int8(self):
         return float(self.lib.gpb_gemm_flops_int8())
+
+
+def lml_grad_batch(engines, thetas, want_grad=True):
+    """(lml[R], grad[R, p] or None, info[R]) for R hyper-parameter vectors, sharded over `engines` (one per GPU, same data
+    and model), each engine driven by its own thread inside the library."""
+    lib = load_library()
+    thetas = _f64(thetas)
+    if thetas.ndim != 2:
+        raise ValueError("thetas must be (R, p)")
+    r, p = thetas.shape
+    ctxs = (_ctx_p * len(engines))(*[e._ctx for e in engines])
+    lml = np.empty(r)
+    grad = np.empty((r, p)) if want_grad else None
+    info = np.zeros(r, dtype=np.int32)
+    rc = lib.gpb_lml_grad_batch(ctxs, len(engines), _ptr(thetas), r, p, _ptr(lml), _ptr(grad), info.ctypes.data_as(_ip))
+    if rc != 0:
+        raise EngineError(f"libgpb200 error {rc}: {lib.gpb_last_error().decode()}")
+    return lml, grad, info
 
 
 def device_count() -> int:

@@ -3,6 +3,8 @@
 // hyper-parameters (a handful of exp() calls), sequences launches and moves results.
 #include "ctx.cuh"
 
+#include <thread>
+
 namespace gpb {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -278,6 +280,9 @@ void gpb_ctx_destroy(gpb_ctx* c) {
                       reinterpret_cast<double*>(c->argws)};
     for (double* p : ptrs)
         if (p) cudaFree(p);
+    for (void* p : {(void*)c->pp.lbuf, (void*)c->pp.wbuf, (void*)c->pp.xbuf, (void*)c->pp.tbuf, (void*)c->pp.lscale,
+                    (void*)c->pp.wscale, (void*)c->pp.xscale, (void*)c->pp.tscale, (void*)c->pp.bound, (void*)c->pp.wtmp})
+        if (p) cudaFree(p);
     dist_destroy(c);
     linv_destroy(c);
     clear_graphs(c);
@@ -483,6 +488,8 @@ static int factor_impl(gpb_ctx* c, const double* theta, int* info) {
     GPB_TRY(ensure(c->alpha, c->alpha_cap, sizeof(double) * np));
     GPB_TRY(ensure(c->mu, c->mu_cap, sizeof(double) * np));
     c->fitted = false;
+    c->pp.valid = false;  // cached digit planes of L belong to the previous fit
+    c->pp.ns = 0;
     GPB_TRY(make_cov_params(c, theta + c->n_mean, c->cp_fit));
     make_mean_params(c, theta, c->mp_fit);
     int info_h = 0;
@@ -548,6 +555,17 @@ static int lml_impl(gpb_ctx* c, const double* theta, double* lml, int* info) {
     return 0;
 }
 
+// Error guard of the INT8 inverse chain.  The digit-split GEMM is accurate normwise: every entry of K^-1 = W^T W comes
+// out with an absolute error of about 2^-56 sqrt(N) max|W|^2, however small the entry is, and the gradient trace
+// 1/2 sum (alpha alpha^T - K^-1) o dK_p sums those errors against a smooth dK_p while the exact terms largely cancel.  The
+// FP64 DMMA kernels are accurate componentwise and do not have this problem.  After the INT8 pass the estimate
+//     est = GUARD_C 2^-56 sqrt(N) (1 / min L_ii)^2 1/2 max_c sqrt(sum_ij max_p dK_p,ij^2)
+// (the Frobenius sum comes out of the trace kernel for free) is compared with GUARD_TOL max|grad|; when it is larger,
+// inverse, alpha and traces are recomputed on DMMA from the same factor.  GUARD_C = 20 and GUARD_TOL = 2e-10 are
+// calibrated on the conditioning sweep (profiles/conditioning_sweep_r2.md: measured error / est between 4 and 60 with
+// GUARD_C = 1; every case whose INT8 gradient error exceeded 1e-9 has est well above the threshold).
+constexpr double GUARD_C = 20.0, GUARD_TOL = 2e-10;
+
 static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* grad, int* info) {
     GPB_TRY(use(c));
     GPB_TRY(need_model(c));
@@ -559,36 +577,59 @@ static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* g
     GPB_TRY(ensure(c->W, c->W_cap, sizeof(double) * np * np));
     GPB_TRY(ensure(c->Kinv, c->Kinv_cap, sizeof(double) * np * np));
     GPB_TRY(ensure(c->partials, c->partials_cap, std::max(trace_partials_size(npad), col_dot_ws_bytes(npad, npad))));
-    GPB_TRY(ensure(c->grad_dev, c->grad_cap, sizeof(double) * (nt + 2)));
+    GPB_TRY(ensure(c->grad_dev, c->grad_cap, sizeof(double) * (nt + 2 + MAX_COMP)));
     CovParams cp;
     MeanParams mp;
     GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
     make_mean_params(c, theta, mp);
     int info_h = 0;
     GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_NONE, nullptr, &info_h));
-    c->timer.mark("trtri");
-    GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
-        GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
-        return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
-    }));
-    // alpha = K^-1 r through the explicit inverse, as the reference does here (regression.py:556-559):
-    // v = W r, alpha = W^T v -- two fully parallel matrix-vector passes instead of 2 N/128 dependent block steps
-    c->timer.mark("alpha");
-    GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->resid, c->vec, c->s));
-    GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->partials, c->s));
-    // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
-    GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
-    c->timer.mark("lauum");
-    GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
-    c->timer.mark("trace");
-    GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2), c->s));
-    GPB_TRY(launch_lml_grad(cp, mp, c->n_mean, c->x, n, npad, c->alpha_work, c->Kinv, npad, c->partials, c->grad_dev,
-                            c->s));
-    double sc[2];
-    GPB_CUDA(cudaMemcpyAsync(sc, c->scal, sizeof(sc), cudaMemcpyDeviceToHost, c->s));
-    GPB_CUDA(cudaMemcpyAsync(grad, c->grad_dev, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->s));
-    c->timer.mark("end");
-    GPB_CUDA(cudaStreamSynchronize(c->s));
+    double sc[3], fro2[MAX_COMP];
+    auto inverse_and_traces = [&]() -> int {
+        c->timer.mark("trtri");
+        GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
+            GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+            return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
+        }));
+        // alpha = K^-1 r through the explicit inverse, as the reference does here (regression.py:556-559):
+        // v = W r, alpha = W^T v -- two fully parallel matrix-vector passes instead of 2 N/128 dependent block steps
+        c->timer.mark("alpha");
+        GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->resid, c->vec, c->s));
+        GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->partials, c->s));
+        // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
+        GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
+        c->timer.mark("lauum");
+        GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+        c->timer.mark("trace");
+        GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2 + MAX_COMP), c->s));
+        GPB_TRY(launch_lml_grad(cp, mp, c->n_mean, c->x, n, npad, c->alpha_work, c->Kinv, npad, c->partials, c->grad_dev,
+                                c->grad_dev + nt + 2, c->s));
+        GPB_CUDA(cudaMemcpyAsync(sc, c->scal, sizeof(sc), cudaMemcpyDeviceToHost, c->s));
+        GPB_CUDA(cudaMemcpyAsync(grad, c->grad_dev, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->s));
+        GPB_CUDA(cudaMemcpyAsync(fro2, c->grad_dev + nt + 2, sizeof(fro2), cudaMemcpyDeviceToHost, c->s));
+        c->timer.mark("end");
+        GPB_CUDA(cudaStreamSynchronize(c->s));
+        return 0;
+    };
+    const double i8_before = thread_gemm_flops_i8();
+    GPB_TRY(inverse_and_traces());
+    c->grad_guard_est = 0.0;
+    if (info_h == 0 && option(OPT_I8_GRAD_GUARD) && gemm_i8_override() < 0 && thread_gemm_flops_i8() > i8_before) {
+        double fmax2 = 0.0, gmax = 0.0;
+        for (int i = 0; i < c->ncomp; ++i) fmax2 = std::max(fmax2, fro2[i]);
+        for (int i = 0; i < nt; ++i) gmax = std::max(gmax, std::fabs(grad[i]));
+        const double wmax = 1.0 / sc[2];
+        const double est = GUARD_C * 1.3877787807814457e-17 * std::sqrt((double)n) * wmax * wmax * 0.5 * std::sqrt(fmax2);
+        c->grad_guard_est = gmax > 0.0 ? est / gmax : 0.0;
+        if (!(est <= GUARD_TOL * gmax)) {  // also taken when anything is NaN
+            c->timer.unmark_last();        // the "end" mark: the repeated phases extend this call's timeline
+            set_gemm_i8_override(0);
+            const int rc = inverse_and_traces();
+            set_gemm_i8_override(-1);
+            ++c->grad_guard_retries;
+            GPB_TRY(rc);
+        }
+    }
     *info = info_h;
     *lml = -0.5 * sc[1] - sc[0];
     return 0;
@@ -651,7 +692,69 @@ int gpb_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad, int
     return with_dmma_retry(c, info, [&]() { return lml_grad_impl(c, theta, lml, grad, info); });
 }
 int gpb_loo(gpb_ctx* c, const double* theta, double* loo, double* grad, int* info) {
-    return with_dmma_retry(c, info, [&]() { return loo_impl(c, theta, loo, grad, info); });
+    // The leave-one-out objective reads diag(K^-1) and K^-1 dK_p entry by entry: it needs the componentwise accuracy of
+    // the FP64 DMMA kernels for the inverse chain (see the gradient error guard above), so the whole call runs on them.
+    const int prev = gemm_i8_override();
+    set_gemm_i8_override(0);
+    const int rc = loo_impl(c, theta, loo, grad, info);
+    set_gemm_i8_override(prev);
+    return rc;
+}
+
+int gpb_ctx_stat(gpb_ctx* c, const char* name, double* out) {
+    if (!c || !name || !out) {
+        set_error("gpb_ctx_stat: bad arguments");
+        return -2;
+    }
+    const std::string k(name);
+    if (k == "dmma_retries") *out = (double)c->dmma_retries;
+    else if (k == "grad_guard_retries") *out = (double)c->grad_guard_retries;
+    else if (k == "grad_guard_est") *out = c->grad_guard_est;
+    else if (k == "predict_block") *out = c->pp.valid ? (double)c->pp.nb : 0.0;
+    else {
+        set_error("gpb_ctx_stat: unknown statistic '" + k + "'");
+        return -2;
+    }
+    return 0;
+}
+
+// Population / multistart evaluation: R hyper-parameter vectors, theta r on context r % nctx, one host thread per context
+// (the contexts sit on different GPUs and hold the same data and model).  No collective: the units are independent.
+int gpb_lml_grad_batch(gpb_ctx** ctxs, int nctx, const double* thetas, int n_theta, int p, double* lml,
+                       double* grad_or_null, int* info) {
+    if (!ctxs || nctx < 1 || n_theta < 0 || !thetas || !lml || !info) {
+        set_error("gpb_lml_grad_batch: bad arguments");
+        return -2;
+    }
+    for (int i = 0; i < nctx; ++i) {
+        if (!ctxs[i] || !ctxs[i]->model_set || ctxs[i]->n_mean + ctxs[i]->n_cov != p) {
+            set_error("gpb_lml_grad_batch: every context needs data, a model and p = n_mean + n_cov hyper-parameters");
+            return -2;
+        }
+    }
+    std::vector<int> rc(nctx, 0);
+    std::vector<std::string> err(nctx);
+    auto work = [&](int i) {
+        for (int r = i; r < n_theta && rc[i] == 0; r += nctx) {
+            const double* th = thetas + (size_t)r * p;
+            rc[i] = grad_or_null ? gpb_lml_grad(ctxs[i], th, lml + r, grad_or_null + (size_t)r * p, info + r)
+                                 : gpb_lml(ctxs[i], th, lml + r, info + r);
+        }
+        if (rc[i] != 0) err[i] = gpb_last_error();  // the message is thread-local: carry it to the caller
+    };
+    if (nctx == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int i = 0; i < nctx; ++i) threads.emplace_back(work, i);
+        for (auto& t : threads) t.join();
+    }
+    for (int i = 0; i < nctx; ++i)
+        if (rc[i] != 0) {
+            set_error(err[i]);
+            return rc[i];
+        }
+    return 0;
 }
 
 int gpb_loo_predictions(gpb_ctx* c, double* mu, double* sigma) {
@@ -694,6 +797,130 @@ int64_t chunk_rows(const gpb_ctx* c) {
     return base * 4;
 }
 
+// ---- blocked predict solve on cached digit planes --------------------------------------------------------------------------
+// X = S L^-T for a chunk of stacked cross-covariance rows, left-looking over block columns of width nb:
+//     T_j = S_j - X_{<j} L_{j,<j}^T        one INT8 GEMM, k = j nb, both operands already split
+//     X_j = T_j inv(L_jj)^T                 one INT8 GEMM, k = nb_j (triangular)
+// L's planes and the inverted diagonal blocks are split ONCE per fit; each block of X is split once, right after it is
+// solved.  A GEMM needs one scale per operand row over its whole k extent, while the blocks of a row of X appear one at a
+// time -- so X uses an a-priori bound instead of the measured row maximum: row 0 of a query's stack is v = L^-1 k_q with
+// |v|^2 <= k(q, q) (the posterior variance k(q,q) - |v|^2 is non-negative); rows a >= 1 (SquaredExponential gradient
+// terms) are L^-1 (A_a o k_q) with squared norm <= a^2 / l_a^2, the prior variance of df/dx_a.  HEADROOM = 8 covers
+// rounding in badly conditioned fits (values beyond it are clamped); it costs 3 of the 55 bits kept per element.
+// Replaces the recursion (trsm_right_lt), which re-split L for every chunk and level, dropped to DMMA for its k < 512
+// leaves and copied every leaf result (round-1 profile: 1108 split launches, 3584 copy2d launches per step).
+constexpr double X_BOUND_HEADROOM = 8.0;
+
+int predict_block_width(const gpb_ctx* c, int rows_pad) {
+    const int mode = gemm_i8_override() >= 0 ? gemm_i8_override() : (int)option(OPT_GEMM_I8);
+    const int want = (int)option(OPT_PREDICT_BLOCK);
+    if (mode == 0 || want < NB) return 0;
+    const int npad = (int)c->npad;
+    const int quarter = (npad / 4) / NB * NB;
+    if (mode == 2) {  // forced INT8 (tests): any size the kernel's shape rules allow
+        if (npad < 512) return 0;
+        return std::min(want / NB * NB, std::max(256, quarter));
+    }
+    const int nb = std::min(want / NB * NB, std::max(512, quarter));
+    if (npad < 2 * nb || nb < (int)option(OPT_GEMM_I8_MIN_K)) return 0;
+    if ((int64_t)(rows_pad / NB) * (nb / NB) < 148) return 0;  // too few tiles to fill the machine: recursion on DMMA
+    return nb;
+}
+
+int build_predict_planes(gpb_ctx* c, int nb, int ns, int64_t rows_cap) {
+    PredictPlanes& pp = c->pp;
+    const int npad = (int)c->npad;
+    const int nblk = (npad + nb - 1) / nb;
+    auto cols_of = [&](int j) { return std::min(nb, npad - j * nb); };
+    if (!(pp.valid && pp.nb == nb)) {
+        pp.valid = false;
+        size_t lbytes = 0, wbytes = 0;
+        for (int j = 0; j < nblk; ++j) {
+            lbytes += i8_plane_bytes(cols_of(j), (int64_t)j * nb);
+            wbytes += i8_plane_bytes(cols_of(j), cols_of(j));
+        }
+        GPB_TRY(ensure(pp.lbuf, pp.lbuf_cap, std::max<size_t>(lbytes, 16)));
+        GPB_TRY(ensure(pp.wbuf, pp.wbuf_cap, wbytes));
+        GPB_TRY(ensure(pp.lscale, pp.lscale_cap, sizeof(double) * npad));
+        GPB_TRY(ensure(pp.wscale, pp.wscale_cap, sizeof(double) * npad));
+        GPB_TRY(ensure(pp.wtmp, pp.wtmp_cap, sizeof(double) * 2 * (size_t)nb * nb));
+        pp.Lp.assign(nblk, I8Planes());
+        pp.Wp.assign(nblk, I8Planes());
+        size_t lo = 0, wo = 0;
+        const LinalgWs ws = ws_of(c, c->dinv_fit);
+        for (int j = 0; j < nblk; ++j) {
+            const int k0 = j * nb, nbj = cols_of(j);
+            I8Planes& L = pp.Lp[j];
+            L.q = pp.lbuf + lo;
+            L.scale = pp.lscale + k0;
+            L.rows = nbj;
+            L.ld = k0;
+            L.plane = (int64_t)nbj * k0;
+            lo += i8_plane_bytes(nbj, k0);
+            if (j > 0) GPB_TRY(i8_split_rows(c->Lfit + (size_t)k0 * npad, npad, nbj, k0, false, nullptr, 1, L, 0, 0, c->s));
+            I8Planes& W = pp.Wp[j];
+            W.q = pp.wbuf + wo;
+            W.scale = pp.wscale + k0;
+            W.rows = nbj;
+            W.ld = nbj;
+            W.plane = (int64_t)nbj * nbj;
+            wo += i8_plane_bytes(nbj, nbj);
+            // inv(L_jj) in FP64 (recursion on the inverted 128-blocks), then its planes
+            double* Wd = pp.wtmp;
+            GPB_CUDA(cudaMemsetAsync(Wd, 0, sizeof(double) * (size_t)nbj * nbj, c->s));
+            GPB_TRY(trtri_lower(c->Lfit + (size_t)k0 * npad + k0, npad, Wd, nbj, nbj, k0 / NB, ws, pp.wtmp + (size_t)nb * nb, nb,
+                                c->s));
+            GPB_TRY(i8_split_rows(Wd, nbj, nbj, nbj, false, nullptr, 1, W, 0, 0, c->s));
+        }
+        pp.nb = nb;
+        pp.nblk = nblk;
+        pp.valid = true;
+    }
+    // per-chunk planes
+    GPB_TRY(ensure(pp.xbuf, pp.xbuf_cap, i8_plane_bytes(rows_cap, npad)));
+    GPB_TRY(ensure(pp.tbuf, pp.tbuf_cap, i8_plane_bytes(rows_cap, nb)));
+    GPB_TRY(ensure(pp.xscale, pp.xscale_cap, sizeof(double) * rows_cap));
+    GPB_TRY(ensure(pp.tscale, pp.tscale_cap, sizeof(double) * rows_cap));
+    pp.Xp.q = pp.xbuf;
+    pp.Xp.scale = pp.xscale;
+    pp.Xp.rows = rows_cap;
+    pp.Xp.ld = npad;
+    pp.Xp.plane = rows_cap * (int64_t)npad;
+    pp.Tp.q = pp.tbuf;
+    pp.Tp.scale = pp.tscale;
+    pp.Tp.rows = rows_cap;
+    pp.Tp.ld = nb;
+    pp.Tp.plane = rows_cap * (int64_t)nb;
+    if (pp.ns != ns || !pp.bound) {  // a-priori bounds of the rows of a query's stack
+        GPB_TRY(ensure(pp.bound, pp.bound_cap, sizeof(double) * (MAX_DIM + 1)));
+        double b[MAX_DIM + 1] = {0};
+        double kqq = 0.0;
+        for (int i = 0; i < c->ncomp; ++i)
+            if (c->kinds[i] <= COV_RQ) kqq += c->cp_fit.amp2[i];
+        b[0] = X_BOUND_HEADROOM * std::sqrt(kqq);
+        for (int a = 1; a < ns; ++a) b[a] = X_BOUND_HEADROOM * std::sqrt(c->cp_fit.amp2[0] * c->cp_fit.inv_l2[0][a - 1]);
+        GPB_CUDA(cudaMemcpyAsync(pp.bound, b, sizeof(b), cudaMemcpyHostToDevice, c->s));
+        GPB_CUDA(cudaStreamSynchronize(c->s));  // b is a stack array
+        pp.ns = ns;
+    }
+    return 0;
+}
+
+int predict_solve_blocked(gpb_ctx* c, int rows_pad, int ns) {
+    PredictPlanes& pp = c->pp;
+    const int npad = (int)c->npad, nb = pp.nb;
+    for (int j = 0; j < pp.nblk; ++j) {
+        const int k0 = j * nb, nbj = std::min(nb, npad - k0);
+        double* Sj = c->S + k0;
+        if (j > 0)
+            GPB_TRY(i8_gemm_planes(pp.Xp, 0, pp.Lp[j], 0, rows_pad, nbj, k0, Sj, npad, Sj, npad, -1.0, 1.0, GEMM_FULL, c->s));
+        GPB_TRY(i8_split_rows(Sj, npad, rows_pad, nbj, true, nullptr, 1, pp.Tp, 0, 0, c->s));
+        GPB_TRY(i8_gemm_planes(pp.Tp, 0, pp.Wp[j], 0, rows_pad, nbj, nbj, nullptr, 0, Sj, npad, 1.0, 0.0, GEMM_TRIL_B, c->s));
+        if (j + 1 < pp.nblk) GPB_TRY(i8_split_rows(Sj, npad, rows_pad, nbj, true, pp.bound, ns, pp.Xp, 0, k0, c->s));
+    }
+    return 0;
+}
+
 // Shared driver: out pointers are DEVICE pointers sized for all m queries.
 //   PM_PREDICT : o_a = mu (m), o_b = sig (m)
 //   PM_GRADIENT: o_a = mean (m x d), o_b = cov (m x d x d)
@@ -707,8 +934,13 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
     const int64_t rc = chunk_rows(c);
     const int64_t qc = std::max<int64_t>(1, rc / ns);  // queries per chunk
     const int64_t qmax = std::min<int64_t>(qc, m);
-    const int64_t rows_cap = round_up(qmax * ns, 128);
+    const int64_t rows_cap = round_up(qmax * ns, 256);
     GPB_TRY(ensure(c->S, c->S_cap, sizeof(double) * (size_t)rows_cap * npad));
+    const int nb_solve = predict_block_width(c, (int)rows_cap);
+    if (nb_solve) {
+        c->timer.mark("planes");
+        GPB_TRY(build_predict_planes(c, nb_solve, ns, rows_cap));
+    }
     GPB_TRY(ensure(c->dots, c->dots_cap, sizeof(double) * (size_t)rows_cap));
     GPB_TRY(ensure(c->G, c->G_cap, sizeof(double) * (size_t)qmax * ns * ns));
     if (mode == PM_EI) {
@@ -726,7 +958,9 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
     const LinalgWs ws = ws_of(c, c->dinv_fit);
     for (int64_t q0 = 0; q0 < m; q0 += qc) {
         const int mq = (int)std::min<int64_t>(qc, m - q0);
-        const int rows = mq * ns, rows_pad = (int)round_up(rows, 128);
+        const int rows = mq * ns;
+        const bool blocked = nb_solve && predict_block_width(c, (int)round_up(rows, 256)) == nb_solve;
+        const int rows_pad = (int)round_up(rows, blocked ? 256 : 128);
         const double* qp = q_dev + q0 * d;
         c->timer.mark("cross_cov");
         GPB_TRY(launch_cross_stack(c->cp_fit, qp, mq, ns, c->x, n, npad, c->S, npad, c->s));
@@ -736,8 +970,13 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
         c->timer.mark("mean_dot");
         GPB_TRY(launch_row_dot(c->S, npad, rows, npad, c->alpha, c->dots, c->s));
         c->timer.mark("trsm");
-        GPB_TRY(run_graphed(c, pkey("ptrsm", {c->S, c->Lfit, c->dinv_fit, c->tmp}, {npad, rows_pad}),
-                            [&]() { return trsm_right_lt(c->S, npad, rows_pad, c->Lfit, npad, npad, 0, ws, c->s); }));
+        if (blocked) {
+            GPB_TRY(run_graphed(c, pkey("pblk", {c->S, c->pp.lbuf, c->pp.wbuf, c->pp.xbuf, c->pp.tbuf}, {npad, rows_pad, nb_solve, ns}),
+                                [&]() { return predict_solve_blocked(c, rows_pad, ns); }));
+        } else {
+            GPB_TRY(run_graphed(c, pkey("ptrsm", {c->S, c->Lfit, c->dinv_fit, c->tmp}, {npad, rows_pad}),
+                                [&]() { return trsm_right_lt(c->S, npad, rows_pad, c->Lfit, npad, npad, 0, ws, c->s); }));
+        }
         c->timer.mark("gram");
         GPB_TRY(launch_row_gram(c->S, npad, mq, ns, npad, c->G, c->s));
         c->timer.mark("finalize");

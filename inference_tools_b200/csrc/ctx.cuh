@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/gpb200.h"
 #include "kernels.cuh"
+#include "gemm_i8.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -29,6 +30,11 @@ struct PhaseTimer {
         cudaEventRecord(e, s);
         marks.emplace_back(name, e);
     }
+    void unmark_last() {  // drop the most recent mark (a call that extends its own timeline)
+        if (marks.empty()) return;
+        pool.push_back(marks.back().second);
+        marks.pop_back();
+    }
     ~PhaseTimer() {
         reset();
         for (auto e : pool) cudaEventDestroy(e);
@@ -47,6 +53,21 @@ int ensure(T*& p, size_t& cap, size_t bytes) {
 }
 
 }  // namespace gpb
+
+// Digit planes of the fitted factor for the blocked predict solve (api.cu: predict_solve_blocked), built once per fit:
+//   Lp[j]  rows of block row j of L left of its diagonal block (nb_j x j nb), the B operand of T_j = S_j - X_<j L_j,<j^T
+//   Wp[j]  inv(L_jj) (nb_j x nb_j, lower), the B operand of X_j = T_j inv(L_jj)^T
+// and per query chunk: Xp the solved columns (a-priori row scale), Tp the current block before its diagonal solve.
+struct PredictPlanes {
+    bool valid = false;
+    int nb = 0, nblk = 0, ns = 0;
+    std::vector<gpb::I8Planes> Lp, Wp;
+    gpb::I8Planes Xp, Tp;
+    signed char *lbuf = nullptr, *wbuf = nullptr, *xbuf = nullptr, *tbuf = nullptr;
+    double *lscale = nullptr, *wscale = nullptr, *xscale = nullptr, *tscale = nullptr, *bound = nullptr, *wtmp = nullptr;
+    size_t lbuf_cap = 0, wbuf_cap = 0, xbuf_cap = 0, tbuf_cap = 0, lscale_cap = 0, wscale_cap = 0, xscale_cap = 0,
+           tscale_cap = 0, bound_cap = 0, wtmp_cap = 0;
+};
 
 struct gpb_dist;  // dist.cu
 struct gpb_linv;  // inverter.cu
@@ -98,6 +119,9 @@ struct gpb_ctx {
     bool use_graphs = true;
     uint64_t opt_epoch = 0;  // option_epoch() the graphs were recorded under
     int64_t dmma_retries = 0;  // factorisations repeated on the DMMA kernels after the INT8 path reported info > 0
+    int64_t grad_guard_retries = 0;  // gradient evaluations whose inverse chain was repeated on DMMA (error guard)
+    double grad_guard_est = 0.0;     // last estimate of the INT8 gradient error relative to max|grad|
+    PredictPlanes pp;
     gpb_dist* dist = nullptr;
     gpb_linv* linv = nullptr;
 };

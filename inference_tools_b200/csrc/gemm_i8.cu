@@ -24,6 +24,7 @@
 // (7 * K * 2^14 < 2^31), longer ones are chunked.
 // M and N must be multiples of 128; the caller (gemm_nt) falls back to the DMMA kernels otherwise.
 #include "common.cuh"
+#include "gemm_i8.cuh"
 
 #include <cuda.h>
 #include <cstdlib>
@@ -71,6 +72,7 @@ struct I8Args {
     int flags, tiles_m, tiles_n;
     double* scratch;     // gridDim.x * 128 * 128 doubles: first-sweep partial sums, private to each thread
     int k_off, k_total;  // this launch covers [k_off, k_off + K) of the full k extent (int32 sums stay exact)
+    int a_row_off, b_row_off;  // first row of the operands inside their digit-plane buffers (cached planes hold more rows)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
         };
         for (int t = unit; t < n_tiles; t += n_units) {
             const TileRange tr = tile_range<CTAS>(p, t);
-            const int arow = tr.row0 + (int)rank * BM, brow = tr.col0 + (int)rank * B_ROWS;
+            const int arow = p.a_row_off + tr.row0 + (int)rank * BM, brow = p.b_row_off + tr.col0 + (int)rank * B_ROWS;
             for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: A planes -> slot it, B planes -> slot it + 1
                 acquire(it);
                 acquire(it + 1);
@@ -576,18 +578,26 @@ __device__ __forceinline__ void put_digits(long long m, int lane, unsigned (&wor
 
 // k-contiguous operand (X[row * ld + k]).  One CTA per row: row maximum over the valid k range, then the digits,
 // 16 consecutive k per thread (one 16-byte store per plane).
+// bound != nullptr: the row's scale comes from an a-priori bound bound[row % bound_period] on |x| instead of the measured
+// maximum (operands whose blocks are split at different times but must share one scale per row); values are clamped to
+// the representable range.  qld / qplane: row and plane strides of the digit buffer (compact: K and rows * K).
 __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ X, int64_t ld, int K, int k_off,
                                                          int rows, signed char* __restrict__ q,
                                                          double* __restrict__ scale_out, double extra, int flags,
-                                                         int which) {
+                                                         int which, const double* __restrict__ bound, int bound_period,
+                                                         int64_t qld, int64_t qplane) {
     const int row = blockIdx.x, tid = threadIdx.x;
     int k_lo, k_hi;
     row_k_range(row, flags, which, k_off, K, k_lo, k_hi);
     const double* x = X + (int64_t)row * ld;
     double amax = 0.0;
-    for (int k = k_lo + 2 * tid; k < k_hi; k += 512) {
-        const double2 w = *reinterpret_cast<const double2*>(x + k);
-        amax = finite_abs_max(finite_abs_max(amax, w.x), w.y);
+    if (bound != nullptr) {
+        amax = bound[row % bound_period];
+    } else {
+        for (int k = k_lo + 2 * tid; k < k_hi; k += 512) {
+            const double2 w = *reinterpret_cast<const double2*>(x + k);
+            amax = finite_abs_max(finite_abs_max(amax, w.x), w.y);
+        }
     }
     __shared__ double red[8];
     __shared__ double mult_s;
@@ -602,12 +612,14 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
         double mult, scale;
         row_scale(m, extra, mult, scale);
         mult_s = mult;
-        scale_out[row] = scale;
+        if (scale_out) scale_out[row] = scale;
     }
     __syncthreads();
     const double mult = mult_s;
-    signed char* qrow = q + (int64_t)row * K;
-    const int64_t plane = (int64_t)rows * K;
+    signed char* qrow = q + (int64_t)row * qld;
+    const int64_t plane = qplane;
+    const bool clamp = bound != nullptr;
+    constexpr double LIM = 127.0 * 281474976710656.0;  // 127 * 2^48: the largest |m| whose top digit fits
     for (int k0 = tid * 16; k0 < K; k0 += 256 * 16) {
         unsigned packed[4][S];
 #pragma unroll
@@ -618,8 +630,13 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
                 const double2 w = *reinterpret_cast<const double2*>(x + k0 + 2 * h);
-                put_digits(__double2ll_rn(w.x * mult), (2 * h) & 3, packed[h >> 1]);
-                put_digits(__double2ll_rn(w.y * mult), (2 * h + 1) & 3, packed[h >> 1]);
+                double m0 = w.x * mult, m1 = w.y * mult;
+                if (clamp) {
+                    m0 = fmin(fmax(m0, -LIM), LIM);
+                    m1 = fmin(fmax(m1, -LIM), LIM);
+                }
+                put_digits(__double2ll_rn(m0), (2 * h) & 3, packed[h >> 1]);
+                put_digits(__double2ll_rn(m1), (2 * h + 1) & 3, packed[h >> 1]);
             }
         }
 #pragma unroll
@@ -702,12 +719,14 @@ EncodeFn get_encode() {
     return fn;
 }
 
-// planes[S][rows][K] int8: dims (k, row, plane), box (64, box_rows, box_planes)
-int make_plane_map(CUtensorMap* m, const signed char* base, int64_t rows, int64_t K, int box_rows, int box_planes) {
+// planes[S][rows][ldk] int8 (plane stride `plane`): dims (k, row, plane), box (64, box_rows, box_planes); the map covers k
+// in [0, K) from `base`
+int make_plane_map(CUtensorMap* m, const signed char* base, int64_t rows, int64_t K, int64_t ldk, int64_t plane, int box_rows,
+                   int box_planes) {
     EncodeFn enc = get_encode();
     if (!enc) return 1;
     const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)S};
-    const cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)rows * (cuuint64_t)K};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)plane};
     const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<signed char*>(base), dims, strides, box, estr,
@@ -741,6 +760,95 @@ int grow(T*& p, size_t& cap, size_t bytes, std::vector<void*>& retired) {
     return 0;
 }
 
+int get_workspace(cudaStream_t s, Workspace*& w) {
+    int dev = 0;
+    GPB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    w = &g_ws[{dev, s}];
+    if (w->sm_count == 0) {  // once per (device, stream), under the lock: worker threads share nothing else here
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        int sms = 0;
+        GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        w->sm_count = sms;
+    }
+    return 0;
+}
+
+// tile height: CTA pairs (256 x 128 tiles) whenever the rows allow it; option "gemm_i8_pair" = 0 forces single-CTA tiles.
+// Measured on B200 at 8192^3: 9.65 ms against 10.44 ms -- the pair reads 6 KB instead of 8 KB of shared memory per
+// MMA; its loads have a longer round trip (credited to the leader's barrier) and now set the pace.
+int ctas_for(int M) { return (option(OPT_GEMM_I8_PAIR) && M % (2 * BM) == 0) ? 2 : 1; }
+
+// One launch of gemm_i8_kernel on digit planes: k in [k_off, k_off + Kc) of the full extent k_total; the tensor maps
+// start map_k_off bytes into the plane rows (k_off for planes that hold the whole extent, 0 for a compact chunk).
+// qa / qb: planes with row strides lda_q / ldb_q and plane strides pa / pb, holding rows_a / rows_b rows.
+int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t lda_q, int64_t pa, int64_t rows_a,
+                  int a_row_off, const double* sa, const signed char* qb, int64_t ldb_q, int64_t pb, int64_t rows_b,
+                  int b_row_off, const double* sb, int M, int N, int Kc, int k_off, int map_k_off, int k_total, const double* C,
+                  int64_t ldc, double* D, int64_t ldd, double* D2, int64_t ldd2, double alpha, double beta, int flags,
+                  int ctas) {
+    const int bmt = BM * ctas;
+    const int tm = M / bmt, tn = N / BN;
+    const int64_t tiles = (flags & GEMM_LOWER) ? (ctas == 2 ? (int64_t)tm * (tm + 1) : (int64_t)tm * (tm + 1) / 2)
+                                               : (int64_t)tm * tn;
+    const int units = (int)std::min<int64_t>(tiles, w->sm_count / ctas);
+    const int grid = units * ctas;
+    GPB_TRY(grow(w->scratch, w->scratch_cap, sizeof(double) * (size_t)grid * BM * BN, w->retired));
+    CUtensorMap tmA, tmB, tmA_hi, tmB_hi;
+    if (make_plane_map(&tmA, qa + map_k_off, rows_a, Kc, lda_q, pa, BM, S) ||
+        make_plane_map(&tmB, qb + map_k_off, rows_b, Kc, ldb_q, pb, BN / ctas, S) ||
+        make_plane_map(&tmA_hi, qa + map_k_off, rows_a, Kc, lda_q, pa, BM, S_HI) ||
+        make_plane_map(&tmB_hi, qb + map_k_off, rows_b, Kc, ldb_q, pb, BN / ctas, S_HI)) {
+        set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
+        return -3;
+    }
+    const int debug = (int)option(OPT_GEMM_I8_DEBUG);
+    I8Args p{M, N, Kc, sa, sb, C, ldc, D, ldd, D2, ldd2, alpha, beta, flags | (debug << 20), tm, tn, w->scratch, k_off, k_total,
+             a_row_off, b_row_off};
+    if (ctas == 1) {
+        gemm_i8_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int nt = (int)tiles;
+        GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+    }
+    GPB_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+double algorithmic_flops(int M, int N, int K, int flags, int ctas) {
+    const int bmt = BM * ctas, tm = M / bmt, tn = N / BN;
+    const int64_t tiles = (flags & GEMM_LOWER) ? (ctas == 2 ? (int64_t)tm * (tm + 1) : (int64_t)tm * (tm + 1) / 2)
+                                               : (int64_t)tm * tn;
+    if (!(flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) return (double)tiles * 2.0 * bmt * BN * K;
+    double kext = 0.0;
+    for (int bi = 0; bi < tm; ++bi) {
+        const int ntile = (flags & GEMM_LOWER) ? (ctas == 2 ? 2 * bi + 2 : bi + 1) : tn;
+        for (int bj = 0; bj < ntile; ++bj) {
+            int kb = 0, ke = K;
+            if (flags & GEMM_TRIK_A) kb = std::max(kb, bi * bmt);
+            if (flags & GEMM_TRIK_B) kb = std::max(kb, bj * BN);
+            if (flags & GEMM_TRIL_B) ke = std::min(ke, bj * BN + BN);
+            if (flags & GEMM_TRIL_A) ke = std::min(ke, bi * bmt + bmt);
+            kext += std::max(0, ke - kb);
+        }
+    }
+    return kext * 2.0 * bmt * BN;
+}
+
 }  // namespace
 
 void gemm_i8_release(cudaStream_t s) {
@@ -756,6 +864,49 @@ void gemm_i8_release(cudaStream_t s) {
     g_ws.erase(it);
 }
 
+// ---- pre-split operands (gemm_i8.cuh): planes that outlive one GEMM call ------------------------------------------------
+int i8_split_rows(const double* X, int64_t ld, int rows, int K, bool as_a, const double* bound, int bound_period,
+                  const I8Planes& out, int row_off, int k_off, cudaStream_t s) {
+    if (rows <= 0 || K <= 0) return 0;
+    if (K % 64 || (reinterpret_cast<uintptr_t>(X) & 15) || (ld & 1) || (k_off % 64) || row_off + rows > out.rows ||
+        k_off + K > out.ld) {
+        set_error("i8_split_rows: bad shape / alignment");
+        return -2;
+    }
+    split_rows_kernel<<<rows, 256, 0, s>>>(X, ld, K, 0, rows, out.q + (int64_t)row_off * out.ld + k_off,
+                                           k_off == 0 || bound == nullptr ? out.scale + row_off : nullptr,
+                                           as_a ? 1.0 / 16384.0 : 1.0, 0, 0, bound, bound_period > 0 ? bound_period : 1,
+                                           out.ld, out.plane);
+    GPB_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int i8_gemm_planes(const I8Planes& A, int a_row_off, const I8Planes& B, int b_row_off, int M, int N, int K,
+                   const double* C, int64_t ldc, double* D, int64_t ldd, double alpha, double beta, int flags,
+                   cudaStream_t s) {
+    if (M <= 0 || N <= 0) return 0;
+    if (M % BM || N % BN || K % 64 || K <= 0 || (reinterpret_cast<uintptr_t>(D) & 15) || (ldd & 1) ||
+        (beta != 0.0 && ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc & 1))) || !get_encode()) {
+        set_error("i8_gemm_planes: shape / alignment not supported by the INT8 kernel");
+        return -2;
+    }
+    Workspace* w;
+    GPB_TRY(get_workspace(s, w));
+    const int ctas = ctas_for(M);
+    const int chunks = (K + MAX_K - 1) / MAX_K;
+    const int Kc_max = ((K / 64 + chunks - 1) / chunks) * 64;
+    for (int k0 = 0, c = 0; k0 < K; k0 += Kc_max, ++c) {
+        const int Kc = std::min(Kc_max, K - k0);
+        GPB_TRY(launch_planes(w, s, A.q, A.ld, A.plane, A.rows, a_row_off, A.scale + a_row_off, B.q, B.ld, B.plane, B.rows,
+                              b_row_off, B.scale + b_row_off, M, N, Kc, k0, k0, K, c == 0 ? C : D, c == 0 ? ldc : ldd, D, ldd,
+                              nullptr, 0, alpha, c == 0 ? beta : 1.0, flags, ctas));
+    }
+    const double fl = algorithmic_flops(M, N, K, flags, ctas);
+    credit_gemm_flops(fl, fl);
+    return 0;
+}
+
 // Returns 0 when launched, 1 when this path does not apply (caller falls back to the DMMA kernels), < 0 on error.
 int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     const bool a_t = a.flags & GEMM_A_MMAJOR, b_t = a.flags & GEMM_B_NMAJOR;
@@ -766,38 +917,16 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     if (a.beta != 0.0 && misaligned(a.C, a.ldc)) return 1;
     if (a.D2 && misaligned(a.D2, a.ldd2)) return 1;
     if (!get_encode()) return 1;
-    int dev = 0;
-    GPB_CUDA(cudaGetDevice(&dev));
     Workspace* w;
-    {
-        std::lock_guard<std::mutex> lock(g_ws_mutex);
-        w = &g_ws[{dev, s}];
-        if (w->sm_count == 0) {  // once per (device, stream), under the lock: worker threads share nothing else here
-            GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            int sms = 0;
-            GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            w->sm_count = sms;
-        }
-    }
+    GPB_TRY(get_workspace(s, w));
     const int chunks = (a.K + MAX_K - 1) / MAX_K;
     const int Kc_max = ((a.K / 64 + chunks - 1) / chunks) * 64;  // balanced chunks, multiples of 64
     GPB_TRY(grow(w->qa, w->qa_cap, (size_t)S * a.M * Kc_max, w->retired));
     GPB_TRY(grow(w->qb, w->qb_cap, (size_t)S * a.N * Kc_max, w->retired));
     GPB_TRY(grow(w->sa, w->sa_cap, sizeof(double) * 2 * a.M, w->retired));  // scales, then the 2^(55-e) multipliers
     GPB_TRY(grow(w->sb, w->sb_cap, sizeof(double) * 2 * a.N, w->retired));
-    // CTA pairs (256 x 128 tiles) whenever the rows allow it; GPB200_GEMM_I8_PAIR=0 forces single-CTA tiles.
-    // Measured on B200 at 8192^3: 9.65 ms against 10.44 ms -- the pair reads 6 KB instead of 8 KB of shared memory per
-    // MMA; its loads have a longer round trip (credited to the leader's barrier) and now set the pace.
-    const int pair_env = (int)option(OPT_GEMM_I8_PAIR);
-    const int ctas = (pair_env && a.M % (2 * BM) == 0) ? 2 : 1;
+    const int ctas = ctas_for(a.M);
     const int bmt = BM * ctas;
-    const int tm = a.M / bmt, tn = a.N / BN;
-    const int64_t tiles = (a.flags & GEMM_LOWER) ? (ctas == 2 ? (int64_t)tm * (tm + 1) : (int64_t)tm * (tm + 1) / 2)
-                                                 : (int64_t)tm * tn;
-    const int units = (int)std::min<int64_t>(tiles, w->sm_count / ctas);
-    const int grid = units * ctas;
-    GPB_TRY(grow(w->scratch, w->scratch_cap, sizeof(double) * (size_t)grid * BM * BN, w->retired));
     for (int k0 = 0, c = 0; k0 < a.K; k0 += Kc_max, ++c) {
         const int Kc = std::min(Kc_max, a.K - k0);
         if (a_t) {
@@ -806,7 +935,8 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
             split_cols_digits_kernel<<<dim3(a.M / 64, Kc / 64), 256, 0, s>>>(X, a.lda, Kc, k0, a.M, w->qa, w->sa + a.M,
                                                                              a.flags, bmt);
         } else {
-            split_rows_kernel<<<a.M, 256, 0, s>>>(a.A + k0, a.lda, Kc, k0, a.M, w->qa, w->sa, 1.0 / 16384.0, a.flags, bmt);
+            split_rows_kernel<<<a.M, 256, 0, s>>>(a.A + k0, a.lda, Kc, k0, a.M, w->qa, w->sa, 1.0 / 16384.0, a.flags, bmt,
+                                                  nullptr, 1, Kc, (int64_t)a.M * Kc);
         }
         GPB_CUDA(cudaGetLastError());
         if (b_t) {
@@ -815,58 +945,17 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
             split_cols_digits_kernel<<<dim3(a.N / 64, Kc / 64), 256, 0, s>>>(X, a.ldb, Kc, k0, a.N, w->qb, w->sb + a.N,
                                                                              a.flags, 0);
         } else {
-            split_rows_kernel<<<a.N, 256, 0, s>>>(a.B + k0, a.ldb, Kc, k0, a.N, w->qb, w->sb, 1.0, a.flags, 0);
+            split_rows_kernel<<<a.N, 256, 0, s>>>(a.B + k0, a.ldb, Kc, k0, a.N, w->qb, w->sb, 1.0, a.flags, 0, nullptr, 1, Kc,
+                                                  (int64_t)a.N * Kc);
         }
         GPB_CUDA(cudaGetLastError());
-        CUtensorMap tmA, tmB, tmA_hi, tmB_hi;
-        if (make_plane_map(&tmA, w->qa, a.M, Kc, BM, S) || make_plane_map(&tmB, w->qb, a.N, Kc, BN / ctas, S) ||
-            make_plane_map(&tmA_hi, w->qa, a.M, Kc, BM, S_HI) || make_plane_map(&tmB_hi, w->qb, a.N, Kc, BN / ctas, S_HI)) {
-            set_error("gemm_nt_i8: cuTensorMapEncodeTiled failed");
-            return -3;
-        }
-        const int debug = (int)option(OPT_GEMM_I8_DEBUG);
-        I8Args p{a.M, a.N, Kc, w->sa, w->sb, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2,
-                 a.alpha, c == 0 ? a.beta : 1.0, a.flags | (debug << 20), tm, tn, w->scratch, k0, a.K};
-        if (ctas == 1) {
-            gemm_i8_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
-        } else {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(grid);
-            cfg.blockDim = dim3(THREADS);
-            cfg.dynamicSmemBytes = SMEM_BYTES;
-            cfg.stream = s;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            const int nt = (int)tiles;
-            GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
-        }
-        GPB_CUDA(cudaGetLastError());
-        count_launch(3 + (a_t ? 1 : 0) + (b_t ? 1 : 0));
+        count_launch(2 + (a_t ? 1 : 0) + (b_t ? 1 : 0));
+        // the chunk's planes are compact (k local to the chunk); k_off / k_total only steer the triangular k ranges
+        GPB_TRY(launch_planes(w, s, w->qa, Kc, (int64_t)a.M * Kc, a.M, 0, w->sa, w->qb, Kc, (int64_t)a.N * Kc, a.N, 0, w->sb, a.M,
+                              a.N, Kc, k0, 0, a.K, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2, a.alpha,
+                              c == 0 ? a.beta : 1.0, a.flags, ctas));
     }
-    if (flops_out) {
-        if (!(a.flags & (GEMM_TRIK_A | GEMM_TRIK_B | GEMM_TRIL_A | GEMM_TRIL_B))) {
-            *flops_out = (double)tiles * 2.0 * bmt * BN * a.K;
-        } else {
-            double kext = 0.0;
-            for (int bi = 0; bi < tm; ++bi) {
-                const int ntile = (a.flags & GEMM_LOWER) ? (ctas == 2 ? 2 * bi + 2 : bi + 1) : tn;
-                for (int bj = 0; bj < ntile; ++bj) {
-                    int kb = 0, ke = a.K;
-                    if (a.flags & GEMM_TRIK_A) kb = std::max(kb, bi * bmt);
-                    if (a.flags & GEMM_TRIK_B) kb = std::max(kb, bj * BN);
-                    if (a.flags & GEMM_TRIL_B) ke = std::min(ke, bj * BN + BN);
-                    if (a.flags & GEMM_TRIL_A) ke = std::min(ke, bi * bmt + bmt);
-                    kext += std::max(0, ke - kb);
-                }
-            }
-            *flops_out = kext * 2.0 * bmt * BN;
-        }
-    }
+    if (flops_out) *flops_out = algorithmic_flops(a.M, a.N, a.K, a.flags, ctas);
     return 0;
 }
 

@@ -182,7 +182,7 @@ int gpb_linv_lml_grad(gpb_ctx* c, const double* theta, double* lml, double* grad
     GPB_TRY(gemm_nt(g, c->s));
     GPB_TRY(launch_row_dot(v->At, mpad, npad, mpad, v->alpha, v->a, c->s));
     GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2), c->s));
-    GPB_TRY(launch_lml_grad(cp, mp, c->n_mean, c->x, n, npad, v->a, c->Kinv, npad, c->partials, c->grad_dev, c->s));
+    GPB_TRY(launch_lml_grad(cp, mp, c->n_mean, c->x, n, npad, v->a, c->Kinv, npad, c->partials, c->grad_dev, nullptr, c->s));
     double sc[2];
     GPB_CUDA(cudaMemcpyAsync(sc, c->scal, sizeof(sc), cudaMemcpyDeviceToHost, c->s));
     GPB_CUDA(cudaMemcpyAsync(grad, c->grad_dev, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->s));

@@ -74,15 +74,16 @@ int lauum_lower(const double* W, int64_t ldw, double* Kinv, int64_t ldk, int n, 
 // [npad, 2*npad) = solution.
 int trsv_lower_fwd(const double* L, int64_t ld, int npad, const double* dinv, double* vec, cudaStream_t s);
 int trsv_lower_bwd(const double* L, int64_t ld, int npad, const double* dinv, double* vec, cudaStream_t s);
-// out[0] = sum_i log L_ii (i < n); out[1] = a.b (i < n)
+// out[0] = sum_i log L_ii (i < n); out[1] = a.b (i < n); out[2] = min_i L_ii
 int launch_logdet_dot(const double* L, int64_t ld, const double* a, const double* b, int n, double* out2,
                       cudaStream_t s);
 
 // ---- lml.cu : fused gradient traces (regression.py:563-566)
-// grad layout: [mean params | cov params]; partial buffer sized by trace_partials_size()
+// grad layout: [mean params | cov params]; partial buffer sized by trace_partials_size().  fro2_dev (MAX_COMP doubles,
+// optional): per smooth component sum_ij max_p dK_p,ij^2, an upper bound on every |dK_p|_F^2 (gradient error guard)
 size_t trace_partials_size(int npad);
 int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad, const double* alpha, const double* Kinv, int64_t ld,
-                    double* partials, double* grad_dev, cudaStream_t s);
+                    double* partials, double* grad_dev, double* fro2_dev, cudaStream_t s);
 
 // ---- loo.cu : leave-one-out objective (regression.py:451-526)
 int launch_symmetrize(double* A, int64_t ld, int n, cudaStream_t s);

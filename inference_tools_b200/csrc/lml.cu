@@ -12,7 +12,8 @@ namespace gpb {
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NACC = MAX_DIM + 2;  // [ln a, (ln alpha_rq), ln l_1..l_d]
+constexpr int NACC = MAX_DIM + 3;  // [ln a, (ln alpha_rq), ln l_1..l_d], then the Frobenius bound of the gradient planes
+constexpr int FRO = MAX_DIM + 2;   // sum_ij max_p dK_p,ij^2 (error guard of the INT8 inverse chain, api.cu)
 
 __device__ __forceinline__ void lower_tile(int t, int& bi, int& bj) {
     int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
@@ -84,8 +85,14 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
             const double kv = amp2 * (exp(-z) + (gi == gj ? cp.jitter : 0.0));
             const double qk = Q * kv;
             acc[0] += qk;  // 0.5 * Q * 2K
+            double gmax = 1.0;  // max_p |dK_p| / (2 K)
 #pragma unroll
-            for (int k = 0; k < MAX_DIM; ++k) acc[2 + k] = fma(qk, s[k], acc[2 + k]);  // 0.5 * Q * 2 s_k K
+            for (int k = 0; k < MAX_DIM; ++k) {
+                acc[2 + k] = fma(qk, s[k], acc[2 + k]);  // 0.5 * Q * 2 s_k K
+                gmax = fmax(gmax, s[k]);
+            }
+            const double dk = 2.0 * kv * gmax * (ws[i] * wcol);
+            acc[FRO] = fma(w * dk, dk, acc[FRO]);
         } else {
             // covariance.py:356-364: F = 1 + Z/q; grads = [2K, -K (q ln F - Z/F), (2K/F) s_k]
             const double F = 1.0 + z / q, lnF = log(F);
@@ -94,8 +101,14 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
             acc[0] += qk;
             acc[1] = fma(-0.5 * qk, lnF * q - z / F, acc[1]);
             const double qkf = qk / F;
+            double gmax = fmax(1.0, 0.5 * fabs(lnF * q - z / F));
 #pragma unroll
-            for (int k = 0; k < MAX_DIM; ++k) acc[2 + k] = fma(qkf, s[k], acc[2 + k]);
+            for (int k = 0; k < MAX_DIM; ++k) {
+                acc[2 + k] = fma(qkf, s[k], acc[2 + k]);
+                gmax = fmax(gmax, s[k] / F);
+            }
+            const double dk = 2.0 * kv * gmax * (ws[i] * wcol);
+            acc[FRO] = fma(w * dk, dk, acc[FRO]);
         }
     }
     const int warp = tid >> 5, lane = tid & 31;
@@ -116,11 +129,13 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
 
 // grad[off + map(p)] = sum over tiles of partials[tile][p]; one CTA per accumulator slot
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int ntiles, int d,
-                                                              int is_rq, int off, double* __restrict__ grad) {
+                                                              int is_rq, int off, double* __restrict__ grad,
+                                                              double* __restrict__ fro2_out) {
     __shared__ double sm[256];
     const int p = blockIdx.x;  // accumulator slot
     if (p == 1 && !is_rq) return;
-    if (p >= 2 + d) return;
+    if (p >= 2 + d && p != FRO) return;
+    if (p == FRO && fro2_out == nullptr) return;
     double v = 0.0;
     for (int t = threadIdx.x; t < ntiles; t += 256) v += partials[(int64_t)t * NACC + p];
     sm[threadIdx.x] = v;
@@ -130,8 +145,12 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const int idx = is_rq ? p : (p == 0 ? 0 : p - 1);
-        grad[off + idx] = sm[0];
+        if (p == FRO) {
+            *fro2_out = sm[0];
+        } else {
+            const int idx = is_rq ? p : (p == 0 ? 0 : p - 1);
+            grad[off + idx] = sm[0];
+        }
     }
 }
 
@@ -313,7 +332,7 @@ size_t trace_partials_size(int npad) {
 }
 
 int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad, const double* alpha, const double* Kinv,
-                    int64_t ld, double* partials, double* grad_dev, cudaStream_t s) {
+                    int64_t ld, double* partials, double* grad_dev, double* fro2_dev, cudaStream_t s) {
     const int nb = npad / TILE;
     const int ntiles = nb * (nb + 1) / 2;
     for (int c = 0; c < cp.ncomp; ++c) {
@@ -321,7 +340,7 @@ int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean,
         trace_smooth_kernel<<<ntiles, 256, 0, s>>>(cp, c, x, n, alpha, Kinv, ld, partials);
         GPB_CUDA(cudaGetLastError());
         reduce_partials_kernel<<<NACC, 256, 0, s>>>(partials, ntiles, cp.d, cp.kind[c] == COV_RQ,
-                                                    n_theta_mean + cp.theta_off[c], grad_dev);
+                                                    n_theta_mean + cp.theta_off[c], grad_dev, fro2_dev ? fro2_dev + c : nullptr);
         GPB_CUDA(cudaGetLastError());
         count_launch(2);
     }

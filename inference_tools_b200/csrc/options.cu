@@ -42,6 +42,7 @@ struct OptionTable {
         v[OPT_GRAPHS] = getenv("GPB200_NO_GRAPHS") ? 0 : 1;
         v[OPT_I8_FALLBACK] = env("GPB200_I8_FALLBACK", 1);
         v[OPT_PREDICT_BLOCK] = env("GPB200_PREDICT_BLOCK", 2048);
+        v[OPT_I8_GRAD_GUARD] = env("GPB200_I8_GRAD_GUARD", 1);
     }
 };
 OptionTable& table() {
@@ -50,7 +51,7 @@ OptionTable& table() {
 }
 
 const char* const kNames[OPT_COUNT] = {"gemm_i8",  "gemm_i8_min_k", "gemm_i8_pair", "gemm_i8_debug", "gemm_tile",
-                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block"};
+                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block", "i8_grad_guard"};
 
 int find_option(const char* name) {
     if (!name) return -1;

@@ -81,25 +81,31 @@ __global__ void __launch_bounds__(1024) logdet_dot_kernel(const double* __restri
                                                           int n, double* __restrict__ out2) {
     __shared__ double s0[1024];
     __shared__ double s1[1024];
+    __shared__ double s2[1024];
     const int tid = threadIdx.x;
-    double ld_sum = 0.0, dot = 0.0;
+    double ld_sum = 0.0, dot = 0.0, dmin = 1e300;
     for (int i = tid; i < n; i += 1024) {
-        ld_sum += log(L[(int64_t)i * ld + i]);
+        const double lii = L[(int64_t)i * ld + i];
+        ld_sum += log(lii);
+        dmin = fmin(dmin, lii);
         dot = fma(a[i], b[i], dot);
     }
     s0[tid] = ld_sum;
     s1[tid] = dot;
+    s2[tid] = dmin;
     __syncthreads();
     for (int o = 512; o > 0; o >>= 1) {
         if (tid < o) {
             s0[tid] += s0[tid + o];
             s1[tid] += s1[tid + o];
+            s2[tid] = fmin(s2[tid], s2[tid + o]);
         }
         __syncthreads();
     }
     if (tid == 0) {
         out2[0] = s0[0];
         out2[1] = s1[0];
+        out2[2] = s2[0];  // smallest pivot: 1 / out2[2] bounds |inv(L)| (gradient error guard, api.cu)
     }
 }
 

@@ -10,6 +10,7 @@ from device state on first access.
 """
 from __future__ import annotations
 
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from warnings import warn
 
@@ -36,7 +37,10 @@ class GpRegressor:
     :param str optimizer: ``"bfgs"`` (multi-start L-BFGS-B) or ``"diffev"`` (differential evolution).
     :param int n_processes: concurrent L-BFGS-B restarts.  The reference forks a ``multiprocessing.Pool``
         (regression.py:600-601); CUDA state does not survive ``fork``, so restarts run on worker threads, each
-        with its own engine context, spread round-robin over the visible GPUs.
+        with its own engine context, spread round-robin over the visible GPUs; the threads pull start points from
+        a shared queue, so an uneven mix of short and long restarts still balances.  With ``optimizer="diffev"``
+        and ``n_processes > 1`` every generation's population is evaluated in one batched call sharded over the
+        same contexts (``gpb_lml_grad_batch``).
     :param int n_starts: number of L-BFGS-B starting positions.
     :param int device: CUDA device ordinal (extension; default ``$GPB200_DEVICE`` / ``$LOCAL_RANK`` / 0).
     """
@@ -110,6 +114,8 @@ class GpRegressor:
 
         self._device = device
         self._engine = None
+        self._pool = []
+        self._n_processes = n_processes
         self._cache = {}
         self.hyperpars = None
 
@@ -159,9 +165,19 @@ class GpRegressor:
         if info > 0:
             raise LinAlgError("Matrix is not positive definite")
 
+    def _engine_pool(self, n: int):
+        """``n`` engine contexts holding this model, the first being ``self.engine``, the others on the next visible
+        GPUs round-robin (more contexts than GPUs share devices).  Kept for the life of the object."""
+        first = self.engine
+        n_dev = _lib.device_count()
+        while len(self._pool) < n - 1:
+            self._pool.append(self._new_engine((first.device + len(self._pool) + 1) % n_dev))
+        return [first, *self._pool[: n - 1]]
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_engine"] = None
+        state["_pool"] = []
         state["_cache"] = {}
         return state
 
@@ -365,9 +381,33 @@ class GpRegressor:
             raise LinAlgError("Matrix is not positive definite")
         return np.float64(val), grad
 
+    def marginal_likelihood_batch(self, thetas: np.ndarray, n_devices: int = None) -> np.ndarray:
+        """``marginal_likelihood`` for every row of ``thetas`` (R, p) in one call, sharded over ``n_devices`` GPUs
+        (default: all visible).  Failed factorisations give -1e50 as the scalar method does."""
+        engines = self._engine_pool(min(n_devices or _lib.device_count(), max(1, len(thetas))))
+        val, _, info = _lib.lml_grad_batch(engines, thetas, want_grad=False)
+        return np.where(info > 0, -1e50, val)
+
+    def marginal_likelihood_gradient_batch(self, thetas: np.ndarray, n_devices: int = None):
+        """``marginal_likelihood_gradient`` for every row of ``thetas``: ``(lml[R], grad[R, p])``."""
+        engines = self._engine_pool(min(n_devices or _lib.device_count(), max(1, len(thetas))))
+        val, grad, info = _lib.lml_grad_batch(engines, thetas, want_grad=True)
+        if (info > 0).any():
+            raise LinAlgError("Matrix is not positive definite")
+        return val, grad
+
     # ------------------------------------------------------------------ optimisers (host side)
     def differential_evo(self) -> np.ndarray:
-        """regression.py:569-574"""
+        """regression.py:569-574.  ``n_processes > 1``: scipy's vectorised mode hands over a whole generation
+        (p, S) per call and the population is evaluated by one batched C-ABI call sharded over the GPUs
+        (population updates are then deferred to the end of a generation instead of immediate)."""
+        if self._n_processes > 1 and self.model_selector == self.marginal_likelihood:
+            def population_cost(pop):
+                pop = np.atleast_2d(np.asarray(pop, dtype=float).T)
+                return -self.marginal_likelihood_batch(pop, n_devices=self._n_processes)
+
+            res = differential_evolution(func=population_cost, bounds=self.hp_bounds, vectorized=True, updating="deferred")
+            return res.x
         res = differential_evolution(func=lambda t: -self.model_selector(t), bounds=self.hp_bounds)
         return res.x
 
@@ -394,16 +434,16 @@ class GpRegressor:
         return sorted(results, key=lambda r: r[1])[0][0]
 
     def _threaded_restarts(self, x0s, n_workers):
-        """Independent restarts on worker threads, one private engine context each, devices round-robin."""
-        n_dev = _lib.device_count()
-        base = self.engine.device
+        """Independent restarts on worker threads: one engine context per thread (devices round-robin, kept in the
+        object's pool), start points pulled from a shared queue.  ctypes releases the GIL inside every C-ABI call."""
+        n_workers = min(n_workers, len(x0s))
+        engines = self._engine_pool(n_workers)
         use_loo = self.model_selector_gradient == self.loo_likelihood_gradient
+        results = [None] * len(x0s)
+        lock = threading.Lock()
+        next_start = [0]
 
-        def worker(args):
-            idx, chunk = args
-            eng = self._new_engine((base + idx) % n_dev)
-            out = []
-
+        def worker(eng):
             def cost(theta):
                 th = np.asarray(theta, dtype=float)
                 if use_loo:
@@ -414,19 +454,17 @@ class GpRegressor:
                     raise LinAlgError("Matrix is not positive definite")
                 return -val, -grad
 
-            for x0 in chunk:
-                out.append(fmin_l_bfgs_b(func=cost, x0=x0, approx_grad=False, bounds=self.hp_bounds))
-            eng.close()
-            return out
+            while True:
+                with lock:
+                    i = next_start[0]
+                    next_start[0] += 1
+                if i >= len(x0s):
+                    return
+                results[i] = fmin_l_bfgs_b(func=cost, x0=x0s[i], approx_grad=False, bounds=self.hp_bounds)
 
-        n_workers = min(n_workers, len(x0s))
-        chunks = [(i, x0s[i::n_workers]) for i in range(n_workers)]
         with ThreadPoolExecutor(n_workers) as pool:
-            parts = list(pool.map(worker, chunks))
-        # restore the submission order (results are compared by value only, regression.py:604)
-        results = [None] * len(x0s)
-        for (i, _), part in zip(chunks, parts):
-            results[i::n_workers] = part
+            for f in [pool.submit(worker, e) for e in engines]:
+                f.result()
         return results
 
     def __str__(self):

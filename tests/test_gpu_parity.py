@@ -349,6 +349,32 @@ def test_optimisers_and_threaded_restarts():
     assert d.marginal_likelihood(d.hyperpars) >= a.marginal_likelihood(d.hyperpars) - 1e9
 
 
+def test_batched_objective_and_population_batched_diffev():
+    """gpb_lml_grad_batch: a population of hyper-parameter vectors in one call (sharded over the visible GPUs) gives the
+    scalar methods' values bit for bit; differential evolution in population-batched mode (n_processes > 1) reaches the
+    optimum the multistart L-BFGS-B fit finds."""
+    x, y, e = synth(21, 300, 2)
+    m = gp.GpRegressor(x, y, y_err=e, hyperpars=[0.1, 0.0, -1.0, -1.0])
+    rng = np.random.default_rng(3)
+    lo, hi = (np.array([b[i] for b in m.hp_bounds]) for i in (0, 1))
+    thetas = lo + (hi - lo) * rng.random((24, m.n_hyperpars)) * 0.5 + 0.25 * (hi - lo)
+    vals = m.marginal_likelihood_batch(thetas)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scalar = np.array([m.marginal_likelihood(t) for t in thetas])
+    assert np.array_equal(vals, scalar)
+    v2, g2 = m.marginal_likelihood_gradient_batch(thetas[:8])
+    for t, v, g in zip(thetas[:8], v2, g2):
+        vs, gs = m.marginal_likelihood_gradient(t)
+        assert v == vs and np.array_equal(g, gs)
+    np.random.seed(4)
+    ref = gp.GpRegressor(x, y, y_err=e)
+    np.random.seed(4)
+    de = gp.GpRegressor(x, y, y_err=e, optimizer="diffev", n_processes=2)
+    best = ref.marginal_likelihood(ref.hyperpars)
+    assert de.marginal_likelihood(de.hyperpars) >= best - 1e-3 * abs(best)
+
+
 def test_pickle_round_trip_drops_device_handles():
     x, y, e = synth(12, 64, 2)
     m = gp.GpRegressor(x, y, y_err=e, hyperpars=[0.1, 0.0, -1.0, -1.0])

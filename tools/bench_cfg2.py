@@ -7,7 +7,14 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import inference_tools_b200.gp as gp
 from inference_tools_b200 import _lib
-from oracle.cpu_reference import synth
+
+
+def synth(seed, n, d, sigma_n=0.05):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (n, d))
+    y = np.sin(3 * x).sum(axis=1) + rng.normal(0, sigma_n, n)
+    return x, y, np.full(n, sigma_n)
+
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=8192)
@@ -15,6 +22,7 @@ ap.add_argument("--dim", type=int, default=3)
 ap.add_argument("--starts", type=int, default=None)
 ap.add_argument("--threads", type=int, default=1)
 ap.add_argument("--cpu", action="store_true")
+ap.add_argument("--tag", default="")
 a = ap.parse_args()
 x, y, e = synth(7, a.size, a.dim)
 
@@ -50,4 +58,4 @@ if a.cpu:
     out["cpu_fit_s_extrapolated"] = out["cpu_seconds_per_evaluation"] * calls["n"]
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open(f"gpurun_out/cfg2_N{a.size}_t{a.threads}.json", "w"), indent=1)
+json.dump(out, open(f"gpurun_out/cfg2_N{a.size}_t{a.threads}{a.tag}.json", "w"), indent=1)

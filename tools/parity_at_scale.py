@@ -58,9 +58,10 @@ def engine_results(x, y, e, kernel, theta, q, mode):
         alpha = m.alpha
         secs = time.perf_counter() - t0
         f1, i1 = lib.gpb_gemm_flops(), lib.gpb_gemm_flops_int8()
+        stats = {k: m.engine.stat(k) for k in ("dmma_retries", "grad_guard_retries", "grad_guard_est", "predict_block")}
         m.engine.close()
     return {"alpha": alpha, "mu": mu, "sig": sig, "lml_value_only": float(lml_v), "lml": float(lml), "grad": grad,
-            "int8_share": (i1 - i0) / max(f1 - f0, 1.0), "seconds": secs}
+            "int8_share": (i1 - i0) / max(f1 - f0, 1.0), "seconds": secs, "stats": stats}
 
 
 def oracle_results(x, y, e, comps, theta, q):
@@ -80,7 +81,8 @@ def compare(r, o):
         return r
     out = {"alpha": rel(r["alpha"], o["alpha"]), "mu": rel(r["mu"], o["mu"]), "sigma": float(np.abs(r["sig"] / o["sig"] - 1).max()),
            "lml": abs(r["lml"] - o["lml"]) / abs(o["lml"]), "grad": rel(r["grad"], o["grad"]),
-           "int8_share": r["int8_share"], "engine_seconds": r["seconds"]}
+           "int8_share": r["int8_share"], "engine_seconds": r["seconds"], "stats": r["stats"],
+           "grad_max_abs": float(np.abs(o["grad"]).max())}
     if o["lml_value_only"] is not None:
         out["lml_value_only"] = abs(r["lml_value_only"] - o["lml_value_only"]) / abs(o["lml_value_only"])
     return out
