@@ -168,6 +168,54 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def dist_cholesky_block(args, rank, world, local, gp_engine, barrier, max_over_ranks):
+    """BASELINE config 5 beside the headline number: GpRegressor SquaredExponential 2-D, N = 131072, block-column-cyclic
+    FP64 Cholesky + log marginal likelihood over the `world` ranks of this run (csrc/dist.cu: NCCL panel broadcasts, INT8
+    tensor-core trailing updates and panel solves).  Reported: seconds (max over ranks, CUDA events), aggregate and
+    per-GPU FP64-equivalent TFLOP/s (N^3/3), the LML (must agree across world sizes) and the strong-scaling efficiency
+    against the one-GPU sweep committed under profiles/.  GPB_BENCH_DIST_N=0 skips it."""
+    n = int(os.environ.get("GPB_BENCH_DIST_N", 131072))
+    if n <= 0:
+        return None
+    import torch.distributed as dist
+    from inference_tools_b200 import _lib
+    gp_engine.close()                      # release the headline workload's HBM before the 64 GiB factor
+    d, block = 2, int(os.environ.get("GPB_BENCH_DIST_BLOCK", 1024))
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 1, (n, d))
+    y = np.sin(3 * x).sum(axis=1) + rng.normal(0, 0.05, n)
+    theta = np.array([0.2, 0.1] + [np.log(0.3)] * d)
+    uid = [_lib.nccl_unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    eng = _lib.Engine(local)
+    eng.set_data(x, y, np.full(n, 0.05**2))
+    eng.set_model([_lib.COV_SE], _lib.MEAN_CONST)
+    eng.dist_init(rank, world, uid[0])
+    runs = []
+    for _ in range(2):                     # one warm-up sweep (allocations, kernel attributes, NCCL channels), one timed
+        barrier()
+        lml, info, t = eng.dist_lml(theta, block)
+        runs.append((lml, info, max_over_ranks(t["factor_s"]), max_over_ranks(t["assemble_s"])))
+    eng.dist_finalize()
+    eng.close()
+    lml, info, factor_s, assemble_s = runs[-1]
+    npad = (n + 127) // 128 * 128
+    out = {"workload": f"cfg5: SquaredExponential 2D, N={n}, block-column-cyclic Cholesky + LML, block {block}", "world": world,
+           "factor_seconds": factor_s, "assemble_seconds": assemble_s, "info": info, "lml": lml,
+           "fp64_equiv_tflops_aggregate": npad**3 / 3 / factor_s / 1e12, "fp64_equiv_tflops_per_gpu": npad**3 / 3 / factor_s / 1e12 / world,
+           "collective": "ncclBroadcast per panel (N^2/2 x 8 B received per rank in total) + one 2-double ncclAllReduce"}
+    try:
+        ref = json.load(open(os.path.join(ROOT, "profiles", "dist_cholesky_1gpu_ref_r2.json")))
+        if ref.get("n") == n and ref.get("block") == block:
+            out["one_gpu_factor_seconds_ref"] = ref["factor_s"]
+            out["efficiency_vs_one_gpu_ref"] = ref["factor_s"] / (world * factor_s)
+            out["lml_rel_diff_vs_one_gpu_ref"] = abs(lml - ref["lml"]) / abs(ref["lml"])
+    except Exception:
+        pass
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -281,6 +329,8 @@ def main():
     mu_r = eng.dev_download(mu_dev, m_loc)
     assert np.array_equal(mu_r, mu_h), "device-resident and host-buffer paths disagree"
 
+    dist_block = dist_cholesky_block(args, rank, world, local, gp_engine=eng, barrier=barrier, max_over_ranks=max_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -329,6 +379,7 @@ def main():
         "phases_ms": {k: round(v, 3) for k, v in sorted(ph.items())},
         "lml": float(lml),
     }
+    line["dist_cholesky"] = dist_block
     if world == 1:
         line["cpu_baseline"] = cpu_reference(1, [SAMPLE_N_SMALL])   # ~10-20 s of CPU work on the unmodified reference
     print(json.dumps(line))

@@ -43,6 +43,15 @@ class GpRegressor:
         same contexts (``gpb_lml_grad_batch``).
     :param int n_starts: number of L-BFGS-B starting positions.
     :param int device: CUDA device ordinal (extension; default ``$GPB200_DEVICE`` / ``$LOCAL_RANK`` / 0).
+    :param distributed: extension for training sets beyond one GPU's memory (BASELINE config 5).  ``True`` = this
+        process is one rank of an initialised ``torch.distributed`` group (one process per GPU); or a tuple
+        ``(rank, world, nccl_unique_id_bytes)`` when another channel shares the id.  Every rank constructs the
+        regressor with the same data; the covariance matrix is then assembled, factored and solved in a
+        block-column-cyclic layout over the ranks (NCCL panel broadcasts, ``csrc/dist.cu``).  In this mode
+        ``set_hyperparameters``, ``marginal_likelihood``, ``alpha`` and ``__call__`` are COLLECTIVE calls (every
+        rank makes them in the same order; ``__call__`` takes this rank's own slab of query points);
+        ``hyperpars`` must be given (the distributed path has the likelihood value but not its gradient).
+    :param int dist_block: panel width of the distributed layout (multiple of 128, default 1024).
     """
 
     def __init__(
@@ -59,6 +68,8 @@ class GpRegressor:
         n_processes: int = 1,
         n_starts: int = None,
         device: int = None,
+        distributed=False,
+        dist_block: int = 1024,
     ):
         self.x = x if isinstance(x, np.ndarray) else np.array(x)
         self.y = (y if isinstance(y, np.ndarray) else np.array(y)).squeeze()
@@ -113,6 +124,9 @@ class GpRegressor:
         self.hyperpar_labels = [*self.mean.hyperpar_labels, *self.cov.hyperpar_labels]
 
         self._device = device
+        self._dist = self._resolve_distributed(distributed)
+        self._dist_block = int(dist_block)
+        self._dist_theta = None   # hyper-parameters the sharded factor currently belongs to
         self._engine = None
         self._pool = []
         self._n_processes = n_processes
@@ -126,6 +140,16 @@ class GpRegressor:
             self.model_selector = self.marginal_likelihood
             self.model_selector_gradient = self.marginal_likelihood_gradient
 
+        if hyperpars is None and self._dist is not None:
+            raise ValueError(
+                """\n
+                [ GpRegressor error ]
+                >> distributed=True needs the 'hyperpars' argument: the block-cyclic path evaluates
+                >> the marginal likelihood (collectively) but not its gradient; optimise the
+                >> hyper-parameters on a subsample, or drive 'marginal_likelihood' from an optimiser
+                >> that takes identical steps on every rank.
+                """
+            )
         if hyperpars is None:
             if optimizer not in ["bfgs", "diffev"]:
                 optimizer = "bfgs"
@@ -152,15 +176,49 @@ class GpRegressor:
             raise RuntimeError("engine / host hyper-parameter layout mismatch")
         return eng
 
+    @staticmethod
+    def _resolve_distributed(distributed):
+        """None (single GPU) or (rank, world, unique id).  ``True`` takes rank / world from torch.distributed and shares
+        the NCCL unique id of the engine's own communicator through it (rendezvous plumbing only)."""
+        if not distributed:
+            return None
+        if distributed is True:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise RuntimeError("GpRegressor(distributed=True) needs an initialised torch.distributed process group")
+            rank, world = dist.get_rank(), dist.get_world_size()
+            box = [_lib.nccl_unique_id() if (rank == 0 and world > 1) else None]
+            if world > 1:
+                dist.broadcast_object_list(box, src=0)
+            return rank, world, box[0]
+        rank, world, uid = distributed
+        return int(rank), int(world), uid
+
+    def _dist_factor(self, theta):
+        """(re)factor the sharded covariance at ``theta`` unless it already belongs to it; collective"""
+        theta = np.asarray(theta, dtype=float)
+        if self._dist_theta is not None and np.array_equal(self._dist_theta, theta):
+            return
+        self._dist_theta = None
+        info, _ = self._engine.dist_factor(theta, self._dist_block)
+        if info > 0:
+            raise LinAlgError("Matrix is not positive definite")
+        self._dist_theta = theta.copy()
+
     @property
     def engine(self) -> _lib.Engine:
         if self._engine is None:
             self._engine = self._new_engine()
+            if self._dist is not None:
+                self._engine.dist_init(*self._dist)
             if self.hyperpars is not None:
                 self._factor(self.hyperpars)
         return self._engine
 
     def _factor(self, theta):
+        if self._dist is not None:
+            return self._dist_factor(theta)
         info = self._engine.factor(theta)
         if info > 0:
             raise LinAlgError("Matrix is not positive definite")
@@ -179,12 +237,17 @@ class GpRegressor:
         state["_engine"] = None
         state["_pool"] = []
         state["_cache"] = {}
+        state["_dist_theta"] = None
         return state
 
     # ------------------------------------------------------------------ reference API
     def __call__(self, points: np.ndarray):
         """Mean and standard deviation of the regression estimate at ``points`` (regression.py:188-216)."""
         p = self.process_points(points)
+        if self._dist is not None:      # collective: this rank's slab against the sharded factor
+            eng = self.engine
+            self._dist_factor(self.hyperpars)
+            return eng.dist_predict(p)
         return self.engine.predict(p)
 
     def set_hyperparameters(self, hyperpars: np.ndarray):
@@ -204,12 +267,24 @@ class GpRegressor:
         self._cache = {}
         if self._engine is None:
             self._engine = self._new_engine()
+            if self._dist is not None:
+                self._engine.dist_init(*self._dist)
         self._factor(np.asarray(hyperpars, dtype=float))
 
     # dense attributes of the reference object, fetched from the device on demand
     def _fetch(self, which):
         if which not in self._cache:
-            self._cache[which] = self.engine.get(which)
+            if self._dist is not None:
+                eng = self.engine
+                if which == _lib.GET_ALPHA:     # collective block back-substitution over the sharded factor
+                    self._dist_factor(self.hyperpars)
+                    self._cache[which] = eng.dist_alpha()
+                elif which == _lib.GET_MU:
+                    self._cache[which] = self.mean.build_mean(np.asarray(self.mean_hyperpars, dtype=float))
+                else:
+                    raise NotImplementedError("K_xx and L are sharded over the ranks in distributed mode; they are not gathered")
+            else:
+                self._cache[which] = self.engine.get(which)
         return self._cache[which]
 
     @property
@@ -367,7 +442,14 @@ class GpRegressor:
 
     def marginal_likelihood(self, theta: np.ndarray) -> float:
         """Log-marginal likelihood (regression.py:528-542)."""
-        val, info = self.engine.lml(np.asarray(theta, dtype=float))
+        if self._dist is not None:      # collective; the sharded factor then belongs to `theta` until it is next needed
+            eng = self.engine
+            self._dist_theta = None
+            val, info, _ = eng.dist_lml(np.asarray(theta, dtype=float), self._dist_block)
+            if info == 0:
+                self._dist_theta = np.asarray(theta, dtype=float).copy()
+        else:
+            val, info = self.engine.lml(np.asarray(theta, dtype=float))
         if info > 0:
             warn("Cholesky decomposition failure in marginal_likelihood")
             return -1e50
@@ -376,6 +458,9 @@ class GpRegressor:
     def marginal_likelihood_gradient(self, theta: np.ndarray):
         """Log-marginal likelihood and its gradient (regression.py:544-567); a failed factorisation raises
         ``LinAlgError`` as numpy.linalg.cholesky does at regression.py:555."""
+        if self._dist is not None:
+            raise NotImplementedError("the distributed path provides marginal_likelihood but not its gradient "
+                                      "(the explicit inverse is not built in the block-cyclic layout)")
         val, grad, info = self.engine.lml_grad(np.asarray(theta, dtype=float))
         if info > 0:
             raise LinAlgError("Matrix is not positive definite")

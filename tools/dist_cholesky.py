@@ -55,6 +55,8 @@ if rank == 0:
     out = {"n": a.size, "d": a.dim, "block": a.block, "world": world, "lml": best[0], "info": best[1], "assemble_s": best[2][0],
            "factor_s": best[2][1], "total_s": best[2][2], "cholesky_tflops_aggregate": npad**3 / 3 / best[2][1] / 1e12,
            "cholesky_tflops_per_gpu": npad**3 / 3 / best[2][1] / 1e12 / world, "lml_all_reps": [v[0] for v in res]}
+    out["launches"] = eng.launch_count()
+    out["int8_share_of_gemm_flops"] = eng.gemm_flops_int8() / max(eng.gemm_flops(), 1.0)
     if a.check:
         ref, info = eng.lml(theta)
         out["single_gpu_lml"] = ref
