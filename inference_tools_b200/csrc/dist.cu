@@ -72,12 +72,22 @@ int load_nccl() {
         }                                                                                           \
     } while (0)
 
-// aug rows of one panel: row 0 = residual slice of the block's columns, rows 1..127 = 0
+// The residual rides along as extra matrix rows below row npad of every panel.  AUG = 256 of them (row 0 = residual, the
+// rest zero) keeps every row count of the sweep a multiple of 256 when npad is, so the INT8 GEMM can use its 256 x 128
+// CTA-pair tiles.
+constexpr int AUG = 256;
 __global__ void fill_aug_rows_kernel(double* __restrict__ aug, int64_t ld, int ncols, const double* __restrict__ resid) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
     aug[c] = resid[c];
-    for (int a = 1; a < NB; ++a) aug[(int64_t)a * ld + c] = 0.0;
+    for (int a = 1; a < AUG; ++a) aug[(int64_t)a * ld + c] = 0.0;
+}
+
+// sa[i] = sb[i] / 2^14: the same digit planes used as the left operand of a product (gemm_i8.cu: the A scale carries the
+// 2^-14 of the digit weights)
+__global__ void a_scale_kernel(const double* __restrict__ sb, double* __restrict__ sa, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sa[i] = sb[i] * (1.0 / 16384.0);
 }
 
 // acc[0] += sum log diag(panel block), acc[1] += sum aug_row0^2  (single CTA, sequential launches => fixed order)
@@ -155,9 +165,10 @@ struct gpb_dist {
     CovParams cp;
     MeanParams mp;
     double *panels = nullptr, *pbuf = nullptr, *tmp = nullptr, *acc = nullptr, *resid = nullptr, *winv = nullptr,
-           *v_full = nullptr, *alpha_full = nullptr, *bacc = nullptr, *bvec = nullptr;
+           *v_full = nullptr, *alpha_full = nullptr, *bacc = nullptr, *bvec = nullptr, *pscale = nullptr;
     size_t panels_cap = 0, pbuf_cap = 0, tmp_cap = 0, acc_cap = 0, resid_cap = 0, winv_cap = 0, v_cap = 0, alpha_cap = 0,
-           bacc_cap = 0, bvec_cap = 0;
+           bacc_cap = 0, bvec_cap = 0, pscale_cap = 0, pplanes_cap = 0;
+    signed char* pplanes = nullptr;  // digit planes of the two broadcast buffers (split once per step, used by every update)
     int64_t tmp_rows = 0;
     bool have_alpha = false;
     int* info = nullptr;
@@ -174,7 +185,7 @@ struct gpb_dist {
     int owner(int j) const { return j % world; }
     int cols_of(int j) const { return (int)std::min<int64_t>(nbd, npad - (int64_t)j * nbd); }
     int64_t row_end(int j) const { return (int64_t)j * nbd + cols_of(j); }
-    int64_t rows_aug() const { return npad + NB; }
+    int64_t rows_aug() const { return npad + AUG; }
     int64_t panel_rows(int j) const { return rows_aug() - (int64_t)j * nbd; }
     size_t panel_doubles(int j) const { return (size_t)panel_rows(j) * nbd + (size_t)nbd * NB; }
     double* panel(int j) { return panels + off[j]; }
@@ -185,7 +196,8 @@ namespace gpb {
 void dist_destroy(gpb_ctx* c) {
     gpb_dist* d = c->dist;
     if (!d) return;
-    for (double* p : {d->panels, d->pbuf, d->tmp, d->acc, d->resid, d->winv, d->v_full, d->alpha_full, d->bacc, d->bvec})
+    for (double* p : {d->panels, d->pbuf, d->tmp, d->acc, d->resid, d->winv, d->v_full, d->alpha_full, d->bacc, d->bvec,
+                      d->pscale, reinterpret_cast<double*>(d->pplanes)})
         if (p) cudaFree(p);
     if (d->info) cudaFree(d->info);
     for (auto e : d->events) cudaEventDestroy(e);
@@ -277,6 +289,25 @@ int dist_factor_impl(gpb_ctx* c, const double* theta, int block, int* info_out, 
     GPB_TRY(ensure(d->v_full, d->v_cap, sizeof(double) * (size_t)npad));
     GPB_TRY(ensure(d->info, d->info_cap, sizeof(int) * (size_t)(nblk + 1)));
     double* pb[2] = {d->pbuf, d->pbuf + pb_doubles};
+    // Every trailing update of step k multiplies rows of the same panel P_k: its digit planes are split ONCE per step,
+    // right after the broadcast, and shared by all updates (the per-call splitting of gemm_nt re-split the panel for
+    // every owned column: N^3 / (6 nbd) elements of traffic, more than the factorisation's own at nbd = 1024).
+    const int i8_mode = gemm_i8_override() >= 0 ? gemm_i8_override() : (int)option(OPT_GEMM_I8);
+    const bool use_planes = i8_mode >= 1 && nbd % 64 == 0 && (nbd >= (int)option(OPT_GEMM_I8_MIN_K) || i8_mode == 2);
+    I8Planes Pa[2], Pb[2];
+    if (use_planes) {
+        GPB_TRY(ensure(d->pplanes, d->pplanes_cap, 2 * i8_plane_bytes(rows_aug, nbd)));
+        GPB_TRY(ensure(d->pscale, d->pscale_cap, sizeof(double) * 4 * (size_t)rows_aug));
+        for (int b = 0; b < 2; ++b) {
+            Pb[b].q = d->pplanes + (size_t)b * i8_plane_bytes(rows_aug, nbd);
+            Pb[b].scale = d->pscale + (size_t)(2 * b) * rows_aug;
+            Pb[b].rows = rows_aug;
+            Pb[b].ld = nbd;
+            Pb[b].plane = rows_aug * (int64_t)nbd;
+            Pa[b] = Pb[b];
+            Pa[b].scale = d->pscale + (size_t)(2 * b + 1) * rows_aug;
+        }
+    }
 
     GPB_TRY(ctx_make_cov_params(c, theta + c->n_mean, d->cp));
     ctx_make_mean_params(c, theta, d->mp);
@@ -336,9 +367,13 @@ int dist_factor_impl(gpb_ctx* c, const double* theta, int block, int* info_out, 
         return 0;
     };
     auto update_col = [&](int j, int k, cudaStream_t s) -> int {  // C_j -= P_k[rows >= j*nbd] P_k[block j rows]^T
-        const double* P = pb[k & 1] + (size_t)((int64_t)j * nbd - d->row_end(k)) * nbd;
-        GemmArgs g{(int)(rows_aug - (int64_t)j * nbd), d->cols_of(j), d->cols_of(k), P, nbd, P, nbd, d->panel(j), nbd,
-                   d->panel(j), nbd, nullptr, 0, -1.0, 1.0, GEMM_FULL};
+        const int M = (int)(rows_aug - (int64_t)j * nbd), Nc = d->cols_of(j), K = d->cols_of(k);
+        const int row_off = (int)((int64_t)j * nbd - d->row_end(k));
+        if (use_planes && K % 64 == 0 && ((int64_t)(M / NB) * (Nc / 64) >= 148 || i8_mode == 2))
+            return i8_gemm_planes(Pa[k & 1], row_off, Pb[k & 1], row_off, M, Nc, K, d->panel(j), nbd, d->panel(j), nbd, -1.0, 1.0,
+                                  GEMM_FULL, s);
+        const double* P = pb[k & 1] + (size_t)row_off * nbd;
+        GemmArgs g{M, Nc, K, P, nbd, P, nbd, d->panel(j), nbd, d->panel(j), nbd, nullptr, 0, -1.0, 1.0, GEMM_FULL};
         return gemm_nt(g, s);
     };
 
@@ -354,6 +389,12 @@ int dist_factor_impl(gpb_ctx* c, const double* theta, int block, int* info_out, 
         }
         if (ok == me) GPB_CUDA(cudaStreamWaitEvent(s_comm, d->ev(EV_PANEL(k)), 0));
         GPB_TRY(bcast(d, pb[k & 1], pb[k & 1], count, ok, s_comm));
+        if (use_planes && d->cols_of(k) % 64 == 0) {  // digit planes of the received panel, once for all of step k's updates
+            GPB_TRY(i8_split_rows(pb[k & 1], nbd, (int)below, d->cols_of(k), false, nullptr, 1, Pb[k & 1], 0, 0, s_comm));
+            a_scale_kernel<<<(int)((below + 255) / 256), 256, 0, s_comm>>>(Pb[k & 1].scale, Pa[k & 1].scale, (int)below);
+            GPB_CUDA(cudaGetLastError());
+            count_launch();
+        }
         GPB_CUDA(cudaEventRecord(d->ev(EV_BCAST(k)), s_comm));
         if (ok == me)  // the solved rows into the panel's own storage (needed by alpha / predict, not by the sweep)
             GPB_CUDA(cudaMemcpyAsync(d->panel(k) + (size_t)d->cols_of(k) * nbd, pb[k & 1], sizeof(double) * count,
@@ -481,7 +522,7 @@ int gpb_dist_plan(int64_t n, int block, int world, int rank, int* n_blocks, int*
         set_error("gpb_dist_plan: bad arguments");
         return -2;
     }
-    const int64_t npad = round_up(n, NB), rows_aug = npad + NB;
+    const int64_t npad = round_up(n, NB), rows_aug = npad + AUG;
     const int nblk = (int)((npad + block - 1) / block);
     int owned = 0;
     int64_t total = 0;

@@ -85,14 +85,15 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
             const double kv = amp2 * (exp(-z) + (gi == gj ? cp.jitter : 0.0));
             const double qk = Q * kv;
             acc[0] += qk;  // 0.5 * Q * 2K
-            double gmax = 1.0;  // max_p |dK_p| / (2 K)
 #pragma unroll
-            for (int k = 0; k < MAX_DIM; ++k) {
-                acc[2 + k] = fma(qk, s[k], acc[2 + k]);  // 0.5 * Q * 2 s_k K
-                gmax = fmax(gmax, s[k]);
+            for (int k = 0; k < MAX_DIM; ++k) acc[2 + k] = fma(qk, s[k], acc[2 + k]);  // 0.5 * Q * 2 s_k K
+            if ((r & 3) == 0) {     // Frobenius bound of the gradient planes from every 4th row (an estimate is enough)
+                double gmax = 1.0;  // max_p |dK_p| / (2 K)
+#pragma unroll
+                for (int k = 0; k < MAX_DIM; ++k) gmax = fmax(gmax, s[k]);
+                const double dk = 2.0 * kv * gmax * (ws[i] * wcol);
+                acc[FRO] = fma(4.0 * w * dk, dk, acc[FRO]);
             }
-            const double dk = 2.0 * kv * gmax * (ws[i] * wcol);
-            acc[FRO] = fma(w * dk, dk, acc[FRO]);
         } else {
             // covariance.py:356-364: F = 1 + Z/q; grads = [2K, -K (q ln F - Z/F), (2K/F) s_k]
             const double F = 1.0 + z / q, lnF = log(F);
@@ -101,14 +102,15 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
             acc[0] += qk;
             acc[1] = fma(-0.5 * qk, lnF * q - z / F, acc[1]);
             const double qkf = qk / F;
-            double gmax = fmax(1.0, 0.5 * fabs(lnF * q - z / F));
 #pragma unroll
-            for (int k = 0; k < MAX_DIM; ++k) {
-                acc[2 + k] = fma(qkf, s[k], acc[2 + k]);
-                gmax = fmax(gmax, s[k] / F);
+            for (int k = 0; k < MAX_DIM; ++k) acc[2 + k] = fma(qkf, s[k], acc[2 + k]);
+            if ((r & 3) == 0) {
+                double gmax = fmax(1.0, 0.5 * fabs(lnF * q - z / F));
+#pragma unroll
+                for (int k = 0; k < MAX_DIM; ++k) gmax = fmax(gmax, s[k] / F);
+                const double dk = 2.0 * kv * gmax * (ws[i] * wcol);
+                acc[FRO] = fma(4.0 * w * dk, dk, acc[FRO]);
             }
-            const double dk = 2.0 * kv * gmax * (ws[i] * wcol);
-            acc[FRO] = fma(w * dk, dk, acc[FRO]);
         }
     }
     const int warp = tid >> 5, lane = tid & 31;

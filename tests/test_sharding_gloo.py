@@ -38,9 +38,9 @@ def test_block_cyclic_plan_tiles_the_matrix_once():
         assert sum(p["n_owned"] for p in plans) == nblk
         assert max(p["n_owned"] for p in plans) - min(p["n_owned"] for p in plans) <= 1
         # each panel: its rows of the augmented lower block triangle + the inverted 128-blocks of its diagonal block
-        expect = sum((npad + 128 - j * block) * block + block * 128 for j in range(nblk))
+        expect = sum((npad + 256 - j * block) * block + block * 128 for j in range(nblk))   # 256 augmented rows
         assert sum(p["panel_doubles"] for p in plans) == expect
-        assert all(p["staging_doubles"] == 2 * ((npad + 128) * block + block * 128) for p in plans)
+        assert all(p["staging_doubles"] == 2 * ((npad + 256) * block + block * 128) for p in plans)
     big = _lib.dist_plan(131072, 1024, 8, 0)
     assert (big["panel_doubles"] + big["staging_doubles"]) * 8 < 12e9          # fits one B200 many times over
     with pytest.raises(_lib.EngineError):
