@@ -127,6 +127,13 @@ int gpb_posterior(gpb_ctx* ctx, const double* q, int64_t m, double* mu, double* 
 int gpb_expected_improvement(gpb_ctx* ctx, const double* q, int64_t m, double y_max, int mode, double* out,
                              double* grad_or_null, int64_t* argmax_or_null);
 
+/* Adds one training point to the FITTED model with the hyper-parameters kept (extension for GpOptimiser.add_evaluation,
+ * optimisation.py:136-190, which re-builds the regressor from scratch): appends a row to the Cholesky factor with one
+ * forward substitution (O(n^2)) and recomputes alpha.  x_new has d entries; noise_var_new is ignored when the model was
+ * set up without y_err.  info > 0: the enlarged matrix is not positive definite and the old state is kept.  Not
+ * available with y_cov, HeteroscedasticNoise or ChangePoint models. */
+int gpb_append_point(gpb_ctx* ctx, const double* x_new, double y_new, double noise_var_new, int* info);
+
 /* Any acquisition function over a batch of candidates: kind = GPB_ACQ_*, param = y_max (EI, acquisition.py:41) or
  * kappa (UCB, :162); argbest_or_null receives the index of the best candidate (largest value = smallest opt_func; lowest
  * index on ties), found by a device reduction. */

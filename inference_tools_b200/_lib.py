@@ -52,6 +52,7 @@ SIGNATURES = {
     "gpb_spatial_derivatives": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_posterior": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_expected_improvement": (C.c_int, [_ctx_p, _dp, C.c_int64, C.c_double, C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
+    "gpb_append_point": (C.c_int, [_ctx_p, _dp, C.c_double, C.c_double, _ip]),
     "gpb_acquisition": (C.c_int, [_ctx_p, C.c_int, C.c_double, _dp, C.c_int64, C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
     "gpb_dist_unique_id": (C.c_int, [C.c_char_p]),
     "gpb_dist_init": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_char_p]),
@@ -311,6 +312,14 @@ class Engine:
         best = C.c_int64(-1)
         self._check(self.lib.gpb_expected_improvement(self._ctx, _ptr(q), m, float(y_max), mode, _ptr(out), _ptr(grad), C.byref(best)))
         return out, grad, best.value
+
+    def append_point(self, x_new, y_new, noise_var_new=0.0):
+        x_new = _f64(x_new).reshape(self.d)
+        info = C.c_int(0)
+        self._check(self.lib.gpb_append_point(self._ctx, _ptr(x_new), float(y_new), float(noise_var_new), C.byref(info)))
+        if info.value == 0:
+            self.n += 1
+        return info.value
 
     def acquisition(self, kind, param, q, mode=ACQ_VALUE):
         """(values, gradient or None, index of the best candidate) for ACQ_EI (param = y_max), ACQ_UCB (kappa), ACQ_MAXVAR"""

@@ -583,14 +583,32 @@ static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* g
     GPB_TRY(make_cov_params(c, theta + c->n_mean, cp));
     make_mean_params(c, theta, mp);
     int info_h = 0;
-    GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_NONE, nullptr, &info_h));
+    // diagnostic: "i8_grad_phases" bit mask (1 potrf, 2 trtri, 4 lauum) -- a cleared bit runs that phase on DMMA
+    const int phases = (int)option(OPT_I8_GRAD_PHASES);
+    struct PhaseMode {
+        int prev;
+        bool active;
+        PhaseMode(int ph, int bit) : prev(gemm_i8_override()), active(prev < 0 && !(ph & bit)) {
+            if (active) set_gemm_i8_override(0);
+        }
+        ~PhaseMode() {
+            if (active) set_gemm_i8_override(prev);
+        }
+    };
+    {
+        PhaseMode pm(phases, 1);
+        GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_NONE, nullptr, &info_h));
+    }
     double sc[3], fro2[MAX_COMP];
     auto inverse_and_traces = [&]() -> int {
         c->timer.mark("trtri");
-        GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
-            GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
-            return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
-        }));
+        {
+            PhaseMode pm(phases, 2);
+            GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
+                GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+                return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
+            }));
+        }
         // alpha = K^-1 r through the explicit inverse, as the reference does here (regression.py:556-559):
         // v = W r, alpha = W^T v -- two fully parallel matrix-vector passes instead of 2 N/128 dependent block steps
         c->timer.mark("alpha");
@@ -599,7 +617,10 @@ static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* g
         // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
         GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
         c->timer.mark("lauum");
-        GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+        {
+            PhaseMode pm(phases, 4);
+            GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+        }
         c->timer.mark("trace");
         GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2 + MAX_COMP), c->s));
         GPB_TRY(launch_lml_grad(cp, mp, c->n_mean, c->x, n, npad, c->alpha_work, c->Kinv, npad, c->partials, c->grad_dev,
@@ -1103,6 +1124,164 @@ int gpb_acquisition(gpb_ctx* c, int kind, double param, const double* q, int64_t
 int gpb_expected_improvement(gpb_ctx* c, const double* q, int64_t m, double y_max, int mode, double* out,
                              double* grad_or_null, int64_t* argmax_or_null) {
     return gpb_acquisition(c, GPB_ACQ_EI, y_max, q, m, mode, out, grad_or_null, argmax_or_null);
+}
+
+// ---- incremental append (GpOptimiser.add_evaluation with fixed hyper-parameters) -----------------------------------------
+// The reference re-builds the regressor from scratch for every added evaluation (optimisation.py:177-186): O(N^3).  With
+// the hyper-parameters kept, adding one training point only appends a row to the factor:
+//     l = L^-1 k(x_new, X),   d = sqrt(k(x_new, x_new) + diagonal terms - l.l),   L <- [[L, 0], [l^T, d]]
+// one forward substitution (O(N^2)); the inverted 128-block of the diagonal gets its new row from the rows above it
+// (rows of a lower-triangular inverse depend only on earlier rows), and alpha is recomputed from the new factor because
+// the mean (x-bar of Linear / Quadratic means) and the residual change for every point.
+__global__ void __launch_bounds__(128) append_row_kernel(double* __restrict__ L, int64_t ld, double* __restrict__ dinv_blk,
+                                                         const double* __restrict__ l, int n, double diag_base,
+                                                         int* __restrict__ info) {
+    __shared__ double red[4];
+    __shared__ double dval;
+    const int tid = threadIdx.x, r = n % NB, b0 = (n / NB) * NB;
+    double acc = 0.0;
+    for (int k = tid; k < n; k += 128) acc = fma(l[k], l[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        const double d2 = diag_base - ((red[0] + red[1]) + (red[2] + red[3]));
+        if (!(d2 > 0.0)) {
+            *info = n + 1;
+            dval = 0.0;
+        } else {
+            dval = sqrt(d2);
+        }
+    }
+    __syncthreads();
+    const double d = dval;
+    if (d == 0.0) return;
+    double* row = L + (int64_t)n * ld;
+    for (int k = tid; k < n; k += 128) row[k] = l[k];
+    if (tid == 0) row[n] = d;
+    // new row r of inv(L_bb): W[r][c] = -(1/d) sum_{k=c}^{r-1} L[n][b0+k] W[k][c], W[r][r] = 1/d
+    if (tid < NB) {
+        double w = 0.0;
+        if (tid < r) {
+            for (int k = tid; k < r; ++k) w = fma(l[b0 + k], dinv_blk[k * NB + tid], w);
+            w = -w / d;
+        } else if (tid == r) {
+            w = 1.0 / d;
+        }
+        dinv_blk[r * NB + tid] = w;
+    }
+}
+
+// grows every per-point buffer of the context to a new padded size (the factor keeps its contents; new rows / columns are
+// the identity padding)
+static int grow_padding(gpb_ctx* c, int64_t npad_new) {
+    const int64_t np0 = c->npad, d = c->d;
+    linv_destroy(c);  // a linear-inversion problem attached to this context is padded to the old size
+    auto regrow = [&](double*& p, size_t new_doubles, size_t keep_doubles) -> int {
+        double* q = nullptr;
+        GPB_CUDA(cudaMalloc(&q, sizeof(double) * new_doubles));
+        GPB_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * new_doubles, c->s));
+        if (p) {
+            GPB_CUDA(cudaMemcpyAsync(q, p, sizeof(double) * keep_doubles, cudaMemcpyDeviceToDevice, c->s));
+            GPB_CUDA(cudaStreamSynchronize(c->s));
+            GPB_CUDA(cudaFree(p));
+        }
+        p = q;
+        return 0;
+    };
+    GPB_TRY(regrow(c->x, (size_t)npad_new * d, (size_t)np0 * d));
+    GPB_TRY(regrow(c->y, (size_t)npad_new, (size_t)np0));
+    if (c->has_noise) GPB_TRY(regrow(c->noise, (size_t)npad_new, (size_t)np0));
+    double* Lnew = nullptr;
+    GPB_CUDA(cudaMalloc(&Lnew, sizeof(double) * (size_t)npad_new * npad_new));
+    GPB_CUDA(cudaMemsetAsync(Lnew, 0, sizeof(double) * (size_t)npad_new * npad_new, c->s));
+    GPB_CUDA(cudaMemcpy2DAsync(Lnew, sizeof(double) * npad_new, c->Lfit, sizeof(double) * np0, sizeof(double) * np0, np0,
+                               cudaMemcpyDeviceToDevice, c->s));
+    std::vector<double> eye((size_t)NB * NB, 0.0);
+    for (int i = 0; i < NB; ++i) eye[(size_t)i * NB + i] = 1.0;
+    GPB_CUDA(cudaMemcpy2DAsync(Lnew + (size_t)np0 * npad_new + np0, sizeof(double) * npad_new, eye.data(), sizeof(double) * NB,
+                               sizeof(double) * NB, NB, cudaMemcpyHostToDevice, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    GPB_CUDA(cudaFree(c->Lfit));
+    c->Lfit = Lnew;
+    c->Lfit_cap = sizeof(double) * (size_t)npad_new * npad_new;
+    GPB_TRY(regrow(c->dinv_fit, (size_t)npad_new * NB, (size_t)np0 * NB));
+    c->dinv_fit_cap = sizeof(double) * (size_t)npad_new * NB;
+    GPB_CUDA(cudaMemcpyAsync(c->dinv_fit + (size_t)np0 * NB, eye.data(), sizeof(double) * NB * NB, cudaMemcpyHostToDevice, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    GPB_TRY(regrow(c->alpha, (size_t)npad_new, (size_t)np0));
+    c->alpha_cap = sizeof(double) * (size_t)npad_new;
+    GPB_TRY(regrow(c->mu, (size_t)npad_new, (size_t)np0));
+    c->mu_cap = sizeof(double) * (size_t)npad_new;
+    // objective / solve workspaces are re-created at their next use
+    for (double** p : {&c->dinv_work, &c->vec, &c->resid, &c->alpha_work, &c->tmp, &c->Kwork, &c->W, &c->Kinv})
+        if (*p) {
+            GPB_CUDA(cudaFree(*p));
+            *p = nullptr;
+        }
+    c->dinv_work_cap = c->vec_cap = c->resid_cap = c->alpha_work_cap = c->tmp_cap = c->Kwork_cap = c->W_cap = c->Kinv_cap = 0;
+    c->npad = npad_new;
+    return 0;
+}
+
+int gpb_append_point(gpb_ctx* c, const double* x_new, double y_new, double noise_var_new, int* info) {
+    GPB_TRY(use(c));
+    GPB_TRY(need_fit(c));
+    if (c->has_ycov) {
+        set_error("gpb_append_point: not available with a dense y_cov");
+        return -2;
+    }
+    for (int i = 0; i < c->ncomp; ++i)
+        if (c->kinds[i] == COV_HETERO) {
+            set_error("gpb_append_point: HeteroscedasticNoise has one hyper-parameter per point; re-fit instead");
+            return -2;
+        }
+    if (c->n_regions) {
+        set_error("gpb_append_point: ChangePoint kernels are not supported; re-fit instead");
+        return -2;
+    }
+    clear_graphs(c);            // captured sequences bake in pointers and sizes
+    c->pp.valid = false;        // cached digit planes of L
+    const int64_t n = c->n;
+    if (n == c->npad) GPB_TRY(grow_padding(c, c->npad + NB));
+    const int npad = (int)c->npad, d = c->d;
+    GPB_TRY(ensure_linalg_ws(c));
+    // the new point and its data
+    GPB_CUDA(cudaMemcpyAsync(c->x + (size_t)n * d, x_new, sizeof(double) * d, cudaMemcpyHostToDevice, c->s));
+    GPB_CUDA(cudaMemcpyAsync(c->y + n, &y_new, sizeof(double), cudaMemcpyHostToDevice, c->s));
+    if (c->has_noise) GPB_CUDA(cudaMemcpyAsync(c->noise + n, &noise_var_new, sizeof(double), cudaMemcpyHostToDevice, c->s));
+    for (int k = 0; k < d; ++k) c->xbar[k] = (c->xbar[k] * (double)n + x_new[k]) / (double)(n + 1);
+    for (int k = 0; k < d; ++k) c->mp_fit.xbar[k] = c->xbar[k];
+    // l = L^-1 k(x_new, X): cross-covariance row into the right-hand side half of `vec`, forward substitution
+    GPB_TRY(launch_cross_stack(c->cp_fit, c->x + (size_t)n * d, 1, 1, c->x, (int)n, npad, c->vec, npad, c->s));
+    GPB_TRY(trsv_lower_fwd(c->Lfit, npad, npad, c->dinv_fit, c->vec, c->s));
+    double diag = c->has_noise ? noise_var_new : 0.0;
+    for (int i = 0; i < c->ncomp; ++i) {
+        if (c->kinds[i] <= COV_RQ) diag += c->cp_fit.amp2[i] * (1.0 + c->cp_fit.jitter);
+        else if (c->kinds[i] == COV_WHITE) diag += c->cp_fit.amp2[i];
+    }
+    GPB_CUDA(cudaMemsetAsync(c->info_dev, 0, sizeof(int), c->s));
+    append_row_kernel<<<1, 128, 0, c->s>>>(c->Lfit, npad, c->dinv_fit + (size_t)(n / NB) * NB * NB, c->vec + npad, (int)n, diag,
+                                           c->info_dev);
+    GPB_CUDA(cudaGetLastError());
+    count_launch();
+    int info_h = 0;
+    GPB_CUDA(cudaMemcpyAsync(&info_h, c->info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    *info = info_h;
+    if (info_h != 0) {   // not positive definite with the new point: the fitted state of the old n points stays valid
+        return 0;
+    }
+    c->n = n + 1;
+    // alpha = K^-1 (y - mu) with the enlarged factor (every residual changes when x-bar moves)
+    GPB_TRY(launch_residual(c->mp_fit, c->x, c->y, (int)c->n, npad, c->vec, c->mu, c->s));
+    GPB_TRY(trsv_lower_fwd(c->Lfit, npad, npad, c->dinv_fit, c->vec, c->s));
+    GPB_CUDA(cudaMemcpyAsync(c->vec, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+    GPB_TRY(trsv_lower_bwd(c->Lfit, npad, npad, c->dinv_fit, c->vec, c->s));
+    GPB_CUDA(cudaMemcpyAsync(c->alpha, c->vec + npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, c->s));
+    GPB_CUDA(cudaStreamSynchronize(c->s));
+    return 0;
 }
 
 int gpb_posterior(gpb_ctx* c, const double* q, int64_t m, double* mu, double* sigma) {

@@ -43,6 +43,7 @@ struct OptionTable {
         v[OPT_I8_FALLBACK] = env("GPB200_I8_FALLBACK", 1);
         v[OPT_PREDICT_BLOCK] = env("GPB200_PREDICT_BLOCK", 2048);
         v[OPT_I8_GRAD_GUARD] = env("GPB200_I8_GRAD_GUARD", 1);
+        v[OPT_I8_GRAD_PHASES] = env("GPB200_I8_GRAD_PHASES", 7);
     }
 };
 OptionTable& table() {
@@ -51,7 +52,7 @@ OptionTable& table() {
 }
 
 const char* const kNames[OPT_COUNT] = {"gemm_i8",  "gemm_i8_min_k", "gemm_i8_pair", "gemm_i8_debug", "gemm_tile",
-                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block", "i8_grad_guard"};
+                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block", "i8_grad_guard", "i8_grad_phases"};
 
 int find_option(const char* name) {
     if (!name) return -1;

@@ -22,7 +22,8 @@ class GpOptimiser:
     """Gaussian-process (Bayesian) optimisation: maximise an expensive function from few evaluations.
 
     Arguments as in the reference (optimisation.py:80-93): ``x, y, bounds, y_err, hyperpars, kernel, mean,
-    cross_val, acquisition, optimizer, n_processes``; extra ``device``, ``sweep_candidates``, ``sweep_restarts``.
+    cross_val, acquisition, optimizer, n_processes``; extra ``device``, ``sweep_candidates``, ``sweep_restarts``,
+    ``refit_every`` (re-optimise the hyper-parameters only every k-th added evaluation, appending in between).
     """
 
     def __init__(
@@ -41,6 +42,7 @@ class GpOptimiser:
         device: int = None,
         sweep_candidates: int = 1 << 20,
         sweep_restarts: int = 64,
+        refit_every: int = 1,
     ):
         self.x = x if isinstance(x, np.ndarray) else np.array(x)
         if self.x.ndim == 1:
@@ -56,6 +58,8 @@ class GpOptimiser:
         self.device = device
         self.sweep_candidates = sweep_candidates
         self.sweep_restarts = sweep_restarts
+        self.refit_every = max(1, int(refit_every))
+        self._since_refit = 0
         self._fit_optimizer = optimizer if optimizer in ("bfgs", "diffev") else "bfgs"
 
         self.gp = self._build_gp(hyperpars)
@@ -101,7 +105,15 @@ class GpOptimiser:
                 )
             self.y_err = np.append(self.y_err, new_y_err)
 
-        self.gp = self._build_gp()
+        # The reference re-optimises the hyper-parameters and re-factors from scratch after every evaluation
+        # (optimisation.py:177-186).  refit_every = k > 1 (extension) does that only every k-th evaluation; in between the
+        # new point is appended to the existing factor at the current hyper-parameters: one O(N^2) row update on the GPU.
+        self._since_refit += 1
+        if self._since_refit < self.refit_every:
+            self.gp.append(new_x, new_y, new_y_err)
+        else:
+            self._since_refit = 0
+            self.gp = self._build_gp()
         self.mu_max = self.y.max()
         self.acquisition.update_gp(self.gp)
 

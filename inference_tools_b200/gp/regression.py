@@ -271,6 +271,31 @@ class GpRegressor:
                 self._engine.dist_init(*self._dist)
         self._factor(np.asarray(hyperpars, dtype=float))
 
+    def append(self, new_x, new_y, new_y_err=None):
+        """Extension: add ONE training point with the hyper-parameters kept.  The factor gets one new row from a single
+        forward substitution (O(N^2)) instead of the O(N^3) rebuild the reference performs for every added evaluation
+        (optimisation.py:177-186); afterwards the object is the regressor of the enlarged data set at the same theta."""
+        if self._dist is not None or self._y_cov is not None:
+            raise NotImplementedError("append() needs a single-GPU regressor without a dense y_cov")
+        new_x = np.asarray(new_x, dtype=float).reshape(1, self.n_dimensions)
+        if (self._noise_var is None) != (new_y_err is None):
+            raise ValueError("[ GpRegressor error ] 'new_y_err' must be given exactly when the regressor was built with 'y_err'")
+        nv = 0.0 if new_y_err is None else float(np.asarray(new_y_err).squeeze()) ** 2
+        info = self.engine.append_point(new_x, float(np.asarray(new_y).squeeze()), nv)
+        if info > 0:
+            raise LinAlgError("Matrix is not positive definite")
+        self.x = np.append(self.x, new_x, axis=0)
+        self.y = np.append(self.y, float(np.asarray(new_y).squeeze()))
+        if self._noise_var is not None:
+            self._noise_var = np.append(self._noise_var, nv)
+        self.n_points += 1
+        self.cov.pass_spatial_data(self.x)
+        self.mean.pass_spatial_data(self.x)
+        for eng in self._pool:
+            eng.close()
+        self._pool = []
+        self._cache = {}
+
     # dense attributes of the reference object, fetched from the device on demand
     def _fetch(self, which):
         if which not in self._cache:

@@ -375,6 +375,67 @@ def test_batched_objective_and_population_batched_diffev():
     assert de.marginal_likelihood(de.hyperpars) >= best - 1e-3 * abs(best)
 
 
+@pytest.mark.parametrize("mean,comps", [("const", ("SE",)), ("linear", ("RQ", "WHITE")), ("quadratic", ("SE",))])
+def test_incremental_append_equals_rebuild_at_fixed_hyperparameters(mean, comps):
+    """gpb_append_point: appending rows to the factor one evaluation at a time (crossing a 128-row padding boundary, so the
+    buffers are re-grown once) gives the regressor that a rebuild on the enlarged data gives -- and the oracle's."""
+    d, n0, n1 = 2, 250, 262
+    x, y, e = synth(91, n1, d)
+    tm = {"const": [0.3], "linear": [0.3, 0.1, -0.2], "quadratic": [0.3, 0.1, -0.2, 0.05, 0.02]}[mean]
+    tc = [0.1, np.log(0.3), np.log(0.4)] if comps == ("SE",) else [0.1, 0.7, np.log(0.3), np.log(0.4), np.log(0.05)]
+    theta = np.array(tm + tc)
+    kw = dict(kernel=make_kernel(gp, comps), mean=make_mean(gp, mean), hyperpars=theta)
+    m = gp.GpRegressor(x[:n0], y[:n0], y_err=e[:n0], **kw)
+    q = np.random.default_rng(0).uniform(0, 1, (50, d))
+    m(q)                                                   # warm the graph / plane caches that an append must invalidate
+    for i in range(n0, n1):
+        m.append(x[i], y[i], e[i])
+    full = gp.GpRegressor(x, y, y_err=e, kernel=make_kernel(gp, comps), mean=make_mean(gp, mean), hyperpars=theta)
+    ref = orc.Fit(x, y, comps, mean, theta, e**2)
+    assert m.n_points == n1 and m.x.shape == (n1, d)
+    assert rel_err(m.alpha, full.alpha) < 1e-10 and rel_err(m.alpha, ref.alpha) < TOL
+    assert rel_err(m.L, full.L) < 1e-11 and rel_err(m.mu, full.mu) < 1e-13
+    mu, sig = m(q)
+    mu_o, sig_o = ref.predict(q)
+    assert rel_err(mu, mu_o) < TOL and np.abs(sig / sig_o - 1).max() < TOL
+    lml_o = orc.marginal_likelihood(x, y, comps, mean, theta, e**2)
+    assert abs(m.marginal_likelihood(theta) - lml_o) <= TOL * abs(lml_o)
+    lml, grad = m.marginal_likelihood_gradient(theta)
+    lml_f, grad_f = full.marginal_likelihood_gradient(theta)
+    assert abs(lml - lml_f) <= 1e-12 * abs(lml_f) and rel_err(grad, grad_f) < 1e-10
+    # a duplicate of a training point without noise makes the enlarged matrix singular: refused, old state kept
+    nn = gp.GpRegressor(x[:40], y[:40], hyperpars=[0.3, 0.1, np.log(0.3), np.log(0.4)])
+    a0 = nn.alpha.copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            for _ in range(3):
+                nn.append(x[3], y[3])
+            refused = False
+        except LinAlgError:
+            refused = True
+    assert refused and nn.n_points < 43 and np.isfinite(nn(q[:5])[0]).all()
+    assert refused and (nn.n_points > 40 or np.array_equal(nn.alpha, a0))
+
+
+def test_gp_optimiser_with_incremental_appends():
+    """GpOptimiser(refit_every=k): hyper-parameters re-optimised every k-th evaluation, O(N^2) appends in between."""
+    rng = np.random.default_rng(3)
+    f = lambda t: np.sin(3 * t) + 0.5 * t
+    x0 = rng.uniform(0, 2, 8)
+    np.random.seed(5)
+    opt = gp.GpOptimiser(x0, f(x0), bounds=[(0.0, 2.0)], y_err=np.full(8, 1e-3), refit_every=3, optimizer="sweep",
+                         sweep_candidates=4096, sweep_restarts=4)
+    thetas = []
+    for _ in range(6):
+        p = opt.propose_evaluation()
+        opt.add_evaluation(p, f(p), 1e-3)
+        thetas.append(np.array(opt.gp.hyperpars, dtype=float))
+    assert opt.gp.n_points == 14 and opt.y.size == 14
+    assert np.array_equal(thetas[0], thetas[1]) and not np.array_equal(thetas[1], thetas[2])   # refit at the 3rd, 6th
+    assert abs(opt.x[np.argmax(opt.y)] - 0.583) < 0.2 or opt.y.max() > 1.25
+
+
 def test_pickle_round_trip_drops_device_handles():
     x, y, e = synth(12, 64, 2)
     m = gp.GpRegressor(x, y, y_err=e, hyperpars=[0.1, 0.0, -1.0, -1.0])

@@ -30,7 +30,12 @@ __global__ void __launch_bounds__(128, 1) peak_kernel(long long iters) {
     unsigned char* tiles = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     __shared__ unsigned long long bar;
     __shared__ unsigned slot;
-    for (int i = threadIdx.x; i < 112 * 1024 / 4; i += blockDim.x) ((unsigned*)tiles)[i] = 0x01010101u;
+    // pseudo-random digits: constant operands toggle no data lines and stay far below the power limit a real GEMM hits
+    for (int i = threadIdx.x; i < 112 * 1024 / 4; i += blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u + blockIdx.x * 40503u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        ((unsigned*)tiles)[i] = h;
+    }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;\n");

@@ -133,6 +133,30 @@ def run_cond(n=4096):
     return res
 
 
+def run_phases(n=16384):
+    """Which phase of marginal_likelihood_gradient is sensitive to the INT8 GEMM?  SE 3-D at size n: gradient error vs the
+    oracle with the INT8 path allowed in exactly the phases of the mask (1 potrf, 2 trtri, 4 lauum), guard off."""
+    d = 3
+    x, y, e = synth(2024 + n, n, d)
+    theta = np.array([0.3, 0.1] + [np.log(0.35)] * d)
+    lml_o, grad_o = orc.marginal_likelihood_gradient_blocked(x, y, ("SE",), "const", theta, e**2)
+    res = {"what": f"SE d=3 N={n}: gradient error vs oracle per INT8 phase mask (1 potrf, 2 trtri, 4 lauum), guard off",
+           "grad_oracle": grad_o.tolist(), "cases": []}
+    m = gp.GpRegressor(x, y, y_err=e, hyperpars=theta)
+    for mask in (0, 1, 2, 4, 3, 6, 7):
+        with _lib.options(i8_grad_guard=0, i8_grad_phases=mask):
+            lml, grad = m.marginal_likelihood_gradient(theta)
+        entry = {"mask": mask, "grad_rel": rel(grad, grad_o), "grad_abs": float(np.abs(grad - grad_o).max()),
+                 "lml_rel": abs(lml - lml_o) / abs(lml_o), "per_param_abs": np.abs(grad - grad_o).tolist()}
+        print(json.dumps(entry), flush=True)
+        res["cases"].append(entry)
+    with _lib.options(i8_grad_guard=1):
+        lml, grad = m.marginal_likelihood_gradient(theta)
+        res["guarded"] = {"grad_rel": rel(grad, grad_o), "retries": m.engine.stat("grad_guard_retries"), "est": m.engine.stat("grad_guard_est")}
+        print(json.dumps(res["guarded"]), flush=True)
+    json.dump(res, open(os.path.join(OUT, f"grad_phase_sensitivity_N{n}.json"), "w"), indent=1)
+
+
 def run_cfg1():
     """BASELINE config 1 shape: SE 1-D, N=200, predict at 1000 points; latency of the hot calls (the reference needs
     12.9 ms per marginal_likelihood_gradient on the survey host)."""
@@ -169,3 +193,5 @@ if __name__ == "__main__":
         run_cond(int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
     elif what == "cfg1":
         run_cfg1()
+    elif what == "phases":
+        run_phases(int(sys.argv[2]) if len(sys.argv) > 2 else 16384)
