@@ -90,6 +90,9 @@ enum Option : int {
     OPT_I8_FALLBACK,      // re-run a factorisation on the DMMA kernels when the INT8 path reports a non-PD pivot (default 1)
     OPT_PREDICT_BLOCK,    // block width of the left-looking predict solve against cached digit planes (0 = recursion)
     OPT_I8_GRAD_GUARD,    // a-posteriori error estimate of the INT8 inverse chain in marginal_likelihood_gradient (default 1)
+    OPT_GEMM_I8_MAX_K,    // longest k extent of one INT8 launch (<= 16384, the int32 exactness limit); longer ones are chunked,
+                          // each chunk with its own row scales, and accumulated in FP64
+    OPT_GEMM_I8_EPI,      // epilogue warps per CTA of the INT8 kernel: 16 (default) or 8
     OPT_I8_GRAD_PHASES,   // diagnostic bit mask: which phases of gpb_lml_grad may use the INT8 path (1 potrf, 2 trtri, 4 lauum; default 7)
     OPT_COUNT
 };

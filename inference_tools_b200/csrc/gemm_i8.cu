@@ -52,8 +52,9 @@ constexpr int HI_BYTES = S_HI * A_PLANE;                   // 24576 per operand 
 constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = SLOT_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers, tmem slot*/;
-constexpr int EPI_WARPS = 8;                   // two per TMEM lane quarter, 64 columns each
-constexpr int THREADS = 64 + 32 * EPI_WARPS;   // warp 0: TMA, warp 1: TMEM alloc + MMA issue, warps 2-9: epilogue
+// warp 0: TMA, warp 1: TMEM alloc + MMA issue, then EPI epilogue warps (EPI / 4 per TMEM lane quarter, 128 * 4 / EPI
+// columns each; template parameter: 16 by default, 8 = the round-1 configuration, option "gemm_i8_epi")
+constexpr int threads_for(int epi) { return 64 + 32 * epi; }
 constexpr int TMEM_COLS = 512;
 constexpr int RASTER = 8;                     // row-blocks per rasterisation group (B planes stay in L2 across them)
 constexpr int MAX_K = 16384;
@@ -265,8 +266,8 @@ __device__ __forceinline__ void issue_kblock(unsigned tmem_base, unsigned a_base
 // stages its own 128 rows of A and HALF of the B planes, the leader issues M = 256 MMAs that read both halves, and each
 // CTA's TMEM receives its 128 rows of the accumulators: per MMA a CTA reads 6 KB of shared memory instead of 8 KB and
 // fills 25 % less of it, which takes the kernel off the shared-memory bandwidth limit.
-template <int CTAS>
-__global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int CTAS, int EPI_WARPS>
+__global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmA_hi,
                                                              const __grid_constant__ CUtensorMap tmB_hi, const I8Args p,
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                 }
             }
         }
-    } else {  // ---- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; two warps per quarter split the columns
+    } else {  // ---- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; EPI_WARPS / 4 warps per quarter split the columns
         const int q = warp & 3, half = (warp - 2) >> 2;
         constexpr int COLS = BN / (EPI_WARPS / 4);  // columns per warp
         const int cbase = half * COLS;
@@ -445,7 +446,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < COLS; j += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + j));
             }
-            if (tr.nkb > 0) {  // first sweep: H = ((P_6 2^-8 + P_5) 2^-8 + P_4) 2^-8 + P_3 -> scratch
+            // The diagonal sums are combined as INTEGERS before the single conversion to FP64 per sweep (int32 -> FP64
+            // conversions are a quarter-rate instruction and the accumulators cannot be released before they are read):
+            //   first sweep   I1 = P_3 2^24 + P_4 2^16 + P_5 2^8 + P_6   (|I1| < 2^56, exact in int64) -> scratch as FP64
+            //   second sweep  I2 = P_0 2^16 + P_1 2^8 + P_2              (exact in FP64)
+            //   sum_g P_g 2^-8g = 2^-16 (I2 + 2^-32 I1)
+            if (tr.nkb > 0) {
                 mbar_wait(bar_ready, uses & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
@@ -458,22 +464,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
                     if (c == COLS / 16 - 1) release_tmem();
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
-                        double h0 = (double)r[S - S_HI - 1][j], h1 = (double)r[S - S_HI - 1][j + 1];
+                        long long i0 = r[0][j], i1 = r[0][j + 1];
 #pragma unroll
-                        for (int g = S - S_HI - 2; g >= 0; --g) {
-                            h0 = fma(h0, 0.00390625, (double)r[g][j]);
-                            h1 = fma(h1, 0.00390625, (double)r[g][j + 1]);
+                        for (int g = 1; g < S - S_HI; ++g) {
+                            i0 = i0 * 256 + r[g][j];
+                            i1 = i1 * 256 + r[g][j + 1];
                         }
-                        *reinterpret_cast<double2*>(scr + c * 16 + j) = make_double2(h0, h1);
+                        *reinterpret_cast<double2*>(scr + c * 16 + j) = make_double2((double)i0, (double)i1);
                     }
                 }
                 ++uses;
                 mbar_wait(bar_ready, uses & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
-            const double sa = p.sa[row] * p.alpha;
+            const double sa = p.sa[row] * p.alpha * (1.0 / 65536.0);
 #pragma unroll 1
-            for (int c = 0; c < COLS / 16; ++c) {  // second sweep: continue the Horner sum through P_2..P_0, scale, store
+            for (int c = 0; c < COLS / 16; ++c) {  // second sweep: add I2, scale, store
                 double v[16];
                 const int col = tr.col0 + cbase + c * 16;
                 if (tr.nkb > 0) {
@@ -489,12 +495,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_kernel(const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
                         const double2 h = *reinterpret_cast<const double2*>(scr + c * 16 + j);
-                        double h0 = h.x, h1 = h.y;
+                        long long i0 = r[0][j], i1 = r[0][j + 1];
 #pragma unroll
-                        for (int g = S_HI - 1; g >= 0; --g) {
-                            h0 = fma(h0, 0.00390625, (double)r[g][j]);
-                            h1 = fma(h1, 0.00390625, (double)r[g][j + 1]);
+                        for (int g = 1; g < S_HI; ++g) {
+                            i0 = i0 * 256 + r[g][j];
+                            i1 = i1 * 256 + r[g][j + 1];
                         }
+                        const double h0 = fma(h.x, 2.3283064365386963e-10, (double)i0);  // 2^-32
+                        const double h1 = fma(h.y, 2.3283064365386963e-10, (double)i1);
                         v[j] = h0 * sa * __ldg(p.sb + col + j);
                         v[j + 1] = h1 * sa * __ldg(p.sb + col + j + 1);
                     }
@@ -766,8 +774,10 @@ int get_workspace(cudaStream_t s, Workspace*& w) {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     w = &g_ws[{dev, s}];
     if (w->sm_count == 0) {  // once per (device, stream), under the lock: worker threads share nothing else here
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         int sms = 0;
         GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         w->sm_count = sms;
@@ -806,12 +816,14 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
     const int debug = (int)option(OPT_GEMM_I8_DEBUG);
     I8Args p{M, N, Kc, sa, sb, C, ldc, D, ldd, D2, ldd2, alpha, beta, flags | (debug << 20), tm, tn, w->scratch, k_off, k_total,
              a_row_off, b_row_off};
+    const int epi = option(OPT_GEMM_I8_EPI) == 8 ? 8 : 16;  // epilogue warps per CTA
     if (ctas == 1) {
-        gemm_i8_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
+        if (epi == 8) gemm_i8_kernel<1, 8><<<grid, threads_for(8), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
+        else gemm_i8_kernel<1, 16><<<grid, threads_for(16), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
     } else {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(THREADS);
+        cfg.blockDim = dim3(threads_for(epi));
         cfg.dynamicSmemBytes = SMEM_BYTES;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
@@ -822,7 +834,8 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const int nt = (int)tiles;
-        GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+        if (epi == 8) GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 8>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+        else GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 16>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
     }
     GPB_CUDA(cudaGetLastError());
     count_launch();
@@ -894,7 +907,8 @@ int i8_gemm_planes(const I8Planes& A, int a_row_off, const I8Planes& B, int b_ro
     Workspace* w;
     GPB_TRY(get_workspace(s, w));
     const int ctas = ctas_for(M);
-    const int chunks = (K + MAX_K - 1) / MAX_K;
+    const int max_k = (int)std::min<int64_t>(MAX_K, std::max<int64_t>(64, option(OPT_GEMM_I8_MAX_K) / 64 * 64));
+    const int chunks = (K + max_k - 1) / max_k;
     const int Kc_max = ((K / 64 + chunks - 1) / chunks) * 64;
     for (int k0 = 0, c = 0; k0 < K; k0 += Kc_max, ++c) {
         const int Kc = std::min(Kc_max, K - k0);
@@ -919,7 +933,8 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     if (!get_encode()) return 1;
     Workspace* w;
     GPB_TRY(get_workspace(s, w));
-    const int chunks = (a.K + MAX_K - 1) / MAX_K;
+    const int max_k = (int)std::min<int64_t>(MAX_K, std::max<int64_t>(64, option(OPT_GEMM_I8_MAX_K) / 64 * 64));
+    const int chunks = (a.K + max_k - 1) / max_k;
     const int Kc_max = ((a.K / 64 + chunks - 1) / chunks) * 64;  // balanced chunks, multiples of 64
     GPB_TRY(grow(w->qa, w->qa_cap, (size_t)S * a.M * Kc_max, w->retired));
     GPB_TRY(grow(w->qb, w->qb_cap, (size_t)S * a.N * Kc_max, w->retired));

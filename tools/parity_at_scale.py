@@ -150,6 +150,13 @@ def run_phases(n=16384):
                  "lml_rel": abs(lml - lml_o) / abs(lml_o), "per_param_abs": np.abs(grad - grad_o).tolist()}
         print(json.dumps(entry), flush=True)
         res["cases"].append(entry)
+    for max_k in (16384, 8192, 4096, 2048):     # lauum alone on the INT8 path, k extent chunked (per-chunk row scales)
+        with _lib.options(i8_grad_guard=0, i8_grad_phases=4, gemm_i8_max_k=max_k):
+            lml, grad = m.marginal_likelihood_gradient(theta)
+            ms = m.engine.timers().get("lauum")
+        entry = {"lauum_only_max_k": max_k, "grad_rel": rel(grad, grad_o), "grad_abs": float(np.abs(grad - grad_o).max()), "lauum_ms": ms}
+        print(json.dumps(entry), flush=True)
+        res["cases"].append(entry)
     with _lib.options(i8_grad_guard=1):
         lml, grad = m.marginal_likelihood_gradient(theta)
         res["guarded"] = {"grad_rel": rel(grad, grad_o), "retries": m.engine.stat("grad_guard_retries"), "est": m.engine.stat("grad_guard_est")}
