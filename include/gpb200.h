@@ -59,6 +59,8 @@ double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-cor
  *   "graphs"         CUDA-graph replay of launch sequences (1)
  *   "i8_fallback"    repeat a factorisation on DMMA when the INT8 path reports a non-PD pivot (1)
  *   "predict_block"  block width of the left-looking predict solve against cached digit planes (0 = recursion)
+ *   "gemm_i8_max_k"  longest k extent of one INT8 launch (16384 = the int32 exactness limit); longer extents are chunked
+ *   "gemm_i8_epi"    epilogue warps of the INT8 kernel (0 = by k extent, 8, 16)      "i8_grad_phases"  diagnostic mask
  *   "i8_grad_guard"  a-posteriori error estimate of the INT8 inverse chain in gpb_lml_grad, DMMA repeat when it is too
  *                    large relative to the gradient (1)
  * Changing an option drops every context's captured graphs at its next call. */

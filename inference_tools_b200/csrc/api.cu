@@ -555,15 +555,18 @@ static int lml_impl(gpb_ctx* c, const double* theta, double* lml, int* info) {
     return 0;
 }
 
-// Error guard of the INT8 inverse chain.  The digit-split GEMM is accurate normwise: every entry of K^-1 = W^T W comes
-// out with an absolute error of about 2^-56 sqrt(N) max|W|^2, however small the entry is, and the gradient trace
-// 1/2 sum (alpha alpha^T - K^-1) o dK_p sums those errors against a smooth dK_p while the exact terms largely cancel.  The
-// FP64 DMMA kernels are accurate componentwise and do not have this problem.  After the INT8 pass the estimate
-//     est = GUARD_C 2^-56 sqrt(N) (1 / min L_ii)^2 1/2 max_c sqrt(sum_ij max_p dK_p,ij^2)
-// (the Frobenius sum comes out of the trace kernel for free) is compared with GUARD_TOL max|grad|; when it is larger,
-// inverse, alpha and traces are recomputed on DMMA from the same factor.  GUARD_C = 20 and GUARD_TOL = 2e-10 are
-// calibrated on the conditioning sweep (profiles/conditioning_sweep_r2.md: measured error / est between 4 and 60 with
-// GUARD_C = 1; every case whose INT8 gradient error exceeded 1e-9 has est well above the threshold).
+// Error guard of the INT8 inverse chain.  The digit-split GEMM is accurate normwise: an entry of K^-1 = W^T W comes out
+// with an absolute error of about 2^-56 sqrt(k) max|W|^2 (k = the chunk length of the product, 4096), however small the
+// entry is, and the gradient trace 1/2 sum (alpha alpha^T - K^-1) o dK_p sums those errors against a smooth dK_p while the
+// exact terms largely cancel.  The FP64 DMMA kernels are accurate componentwise and do not have this problem.  After the
+// INT8 pass the estimate
+//     est = GUARD_C 2^-56 sqrt(min(N, 4096)) (1 / min L_ii)^2 1/2 max_c sqrt(sum_ij max_p dK_p,ij^2)
+// (the Frobenius sum comes out of the trace kernel for free) is compared with GUARD_TOL max(max|grad|, 1/2 |r.alpha|) --
+// the second term is the size of the two quantities whose difference the gradient is, so the test does not degenerate
+// where the gradient vanishes (the end of every L-BFGS run).  When est is larger, K^-1 and the traces are recomputed on
+// DMMA from the same W.  GUARD_C = 20 and GUARD_TOL = 2e-10 are calibrated on profiles/conditioning_sweep_r2.md and
+// profiles/grad_phase_sensitivity_r2.md (measured error / est between 4 and 94 with GUARD_C = 1 before the product was
+// chunked; every case whose INT8 gradient error exceeded 1e-9 has est far above the threshold).
 constexpr double GUARD_C = 20.0, GUARD_TOL = 2e-10;
 
 static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* grad, int* info) {
@@ -600,22 +603,24 @@ static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* g
         GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_NONE, nullptr, &info_h));
     }
     double sc[3], fro2[MAX_COMP];
-    auto inverse_and_traces = [&]() -> int {
-        c->timer.mark("trtri");
-        {
-            PhaseMode pm(phases, 2);
-            GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
-                GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
-                return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
-            }));
+    auto inverse_and_traces = [&](bool with_trtri) -> int {
+        if (with_trtri) {
+            c->timer.mark("trtri");
+            {
+                PhaseMode pm(phases, 2);
+                GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
+                    GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+                    return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
+                }));
+            }
+            // alpha = K^-1 r through the explicit inverse, as the reference does here (regression.py:556-559):
+            // v = W r, alpha = W^T v -- two fully parallel matrix-vector passes instead of 2 N/128 dependent block steps
+            c->timer.mark("alpha");
+            GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->resid, c->vec, c->s));
+            GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->partials, c->s));
+            // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
+            GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
         }
-        // alpha = K^-1 r through the explicit inverse, as the reference does here (regression.py:556-559):
-        // v = W r, alpha = W^T v -- two fully parallel matrix-vector passes instead of 2 N/128 dependent block steps
-        c->timer.mark("alpha");
-        GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->resid, c->vec, c->s));
-        GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->partials, c->s));
-        // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
-        GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
         c->timer.mark("lauum");
         {
             PhaseMode pm(phases, 4);
@@ -633,19 +638,22 @@ static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* g
         return 0;
     };
     const double i8_before = thread_gemm_flops_i8();
-    GPB_TRY(inverse_and_traces());
+    GPB_TRY(inverse_and_traces(true));
     c->grad_guard_est = 0.0;
     if (info_h == 0 && option(OPT_I8_GRAD_GUARD) && gemm_i8_override() < 0 && thread_gemm_flops_i8() > i8_before) {
         double fmax2 = 0.0, gmax = 0.0;
         for (int i = 0; i < c->ncomp; ++i) fmax2 = std::max(fmax2, fro2[i]);
         for (int i = 0; i < nt; ++i) gmax = std::max(gmax, std::fabs(grad[i]));
         const double wmax = 1.0 / sc[2];
-        const double est = GUARD_C * 1.3877787807814457e-17 * std::sqrt((double)n) * wmax * wmax * 0.5 * std::sqrt(fmax2);
-        c->grad_guard_est = gmax > 0.0 ? est / gmax : 0.0;
-        if (!(est <= GUARD_TOL * gmax)) {  // also taken when anything is NaN
+        const double est = GUARD_C * 1.3877787807814457e-17 * std::sqrt((double)std::min(n, 4096)) * wmax * wmax * 0.5 * std::sqrt(fmax2);
+        const double gscale = std::max(gmax, 0.5 * std::fabs(sc[1]));
+        c->grad_guard_est = gscale > 0.0 ? est / gscale : 0.0;
+        if (!(est <= GUARD_TOL * gscale)) {  // also taken when anything is NaN
             c->timer.unmark_last();        // the "end" mark: the repeated phases extend this call's timeline
+            // only K^-1 = W^T W is repeated: the phase-by-phase measurement (profiles/grad_phase_sensitivity_r2.md) puts
+            // the error in that product; potrf and the triangular inverse on the INT8 path stay within 1e-10
             set_gemm_i8_override(0);
-            const int rc = inverse_and_traces();
+            const int rc = inverse_and_traces(false);
             set_gemm_i8_override(-1);
             ++c->grad_guard_retries;
             GPB_TRY(rc);

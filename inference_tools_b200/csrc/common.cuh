@@ -62,6 +62,10 @@ struct GemmArgs {
     double* D2; int64_t ldd2;       // optional second copy of the output (nullptr = off)
     double alpha, beta;
     int flags;
+    // INT8 path only: longest k extent per launch (0 = the "gemm_i8_max_k" option, 16384).  Every chunk has its own row
+    // scales, so a short chunk keeps more bits of operand rows whose entries decay along k (columns of inv(L) in
+    // K^-1 = W^T W: profiles/grad_phase_sensitivity_r2.md); the chunks are accumulated in FP64.
+    int max_k = 0;
 };
 int gemm_nt(const GemmArgs& a, cudaStream_t s);
 void gemm_i8_release(cudaStream_t s);  // gemm_i8.cu: frees the digit-plane workspace tied to a stream

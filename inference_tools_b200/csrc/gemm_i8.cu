@@ -816,7 +816,10 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
     const int debug = (int)option(OPT_GEMM_I8_DEBUG);
     I8Args p{M, N, Kc, sa, sb, C, ldc, D, ldd, D2, ldd2, alpha, beta, flags | (debug << 20), tm, tn, w->scratch, k_off, k_total,
              a_row_off, b_row_off};
-    const int epi = option(OPT_GEMM_I8_EPI) == 8 ? 8 : 16;  // epilogue warps per CTA
+    // epilogue warps per CTA: 16 pay off on long k extents (+1.4 % on the predict shape), 8 on short ones (+3 % at
+    // k = 1024): profiles/i8_epilogue_ab_r2.json.  Option "gemm_i8_epi": 0 = by k extent, 8 or 16 = fixed.
+    const int epi_opt = (int)option(OPT_GEMM_I8_EPI);
+    const int epi = epi_opt == 8 ? 8 : (epi_opt == 16 ? 16 : (Kc >= 4096 ? 16 : 8));
     if (ctas == 1) {
         if (epi == 8) gemm_i8_kernel<1, 8><<<grid, threads_for(8), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
         else gemm_i8_kernel<1, 16><<<grid, threads_for(16), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
@@ -933,7 +936,8 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     if (!get_encode()) return 1;
     Workspace* w;
     GPB_TRY(get_workspace(s, w));
-    const int max_k = (int)std::min<int64_t>(MAX_K, std::max<int64_t>(64, option(OPT_GEMM_I8_MAX_K) / 64 * 64));
+    const int64_t want_k = a.max_k > 0 ? std::min<int64_t>(a.max_k, option(OPT_GEMM_I8_MAX_K)) : option(OPT_GEMM_I8_MAX_K);
+    const int max_k = (int)std::min<int64_t>(MAX_K, std::max<int64_t>(64, want_k / 64 * 64));
     const int chunks = (a.K + max_k - 1) / max_k;
     const int Kc_max = ((a.K / 64 + chunks - 1) / chunks) * 64;  // balanced chunks, multiples of 64
     GPB_TRY(grow(w->qa, w->qa_cap, (size_t)S * a.M * Kc_max, w->retired));

@@ -44,7 +44,7 @@ struct OptionTable {
         v[OPT_PREDICT_BLOCK] = env("GPB200_PREDICT_BLOCK", 4096);
         v[OPT_I8_GRAD_GUARD] = env("GPB200_I8_GRAD_GUARD", 1);
         v[OPT_GEMM_I8_MAX_K] = env("GPB200_GEMM_I8_MAX_K", 16384);
-        v[OPT_GEMM_I8_EPI] = env("GPB200_GEMM_I8_EPI", 16);
+        v[OPT_GEMM_I8_EPI] = env("GPB200_GEMM_I8_EPI", 0);
         v[OPT_I8_GRAD_PHASES] = env("GPB200_I8_GRAD_PHASES", 7);
     }
 };
