@@ -344,20 +344,34 @@ def main():
     # dominant kernel = gemm_i8_kernel: FP64 GEMMs executed as 28 exact int8 tensor-core products (csrc/gemm_i8.cu).
     # Roofline: int8 operations executed on the tcgen05 pipe / CUDA-event time of the GEMM-only phases, against twice
     # the MEASURED sustained bf16 rate (kind::i8 issues at twice the kind::f16 rate; MEASURED_PEAKS.json has no int8 entry).
-    gemm_phase_ms = sum(ph.get(k, 0) for k in ("grad.potrf", "fit.potrf", "grad.trtri", "grad.lauum", "predict.trsm"))
+    gemm_phase_ms = sum(ph.get(k, 0) for k in ("grad.potrf", "fit.potrf", "grad.trtri", "grad.lauum", "predict.planes", "predict.trsm"))
     gemm_tf = (flops / args.steps) / (gemm_phase_ms * 1e-3) / 1e12 if gemm_phase_ms else None
     int8_tops = 28.0 * (flops_i8 / args.steps) / (gemm_phase_ms * 1e-3) / 1e12 if gemm_phase_ms else None
     pred_tf = (m_loc * float(npad) ** 2) / (ph.get("predict.trsm", 1e30) * 1e-3) / 1e12
+    # Denominator: the MEASURED sustained full-chip rate of tcgen05.mma kind::i8 (tools/int8_peak.cu: every SM issuing
+    # back-to-back 128x128x32 MMAs on random digits for 4 s; the chip runs into its power limit there exactly as in this
+    # step, ~1.6 GHz).  MEASURED_PEAKS.json has no int8 entry; without the probe file fall back to 2 x its sustained bf16.
     int8_peak, int8_src = 2 * 1397.2, "fallback: 2 x 1397.2 (bf16 sustained of this pool when MEASURED_PEAKS.json was written)"
     try:
-        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        int8_peak = 2.0 * float(mp["bf16_tflops_sustained"])
-        int8_src = "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 runs at twice the bf16 rate on tcgen05; sustained figure: timed inside a long step)"
+        pk = json.load(open(os.path.join(ROOT, "profiles", "int8_peak_r2.json")))
+        int8_peak = float(pk["sustained_int8_tops"])
+        int8_src = (f"measured: tools/int8_peak.cu sustained {pk['sustained_seconds']:.1f} s on all SMs, SM clock {pk['clocks']['sm_mhz']} MHz "
+                    f"under {pk['clocks']['reasons']} (profiles/int8_peak_r2.json); MEASURED_PEAKS.json has no int8 entry "
+                    f"(2 x its sustained bf16 would be {2 * 1397.2:.0f})")
     except Exception:
-        pass
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            int8_peak = 2.0 * float(mp["bf16_tflops_sustained"])
+            int8_src = "2 x MEASURED_PEAKS.json bf16_tflops_sustained (profiles/int8_peak_r2.json missing)"
+        except Exception:
+            pass
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_i8_traffic_r1.json"))).get("dram_bytes_per_launch")
+        for name in ("gemm_i8_traffic_r2.json", "gemm_i8_traffic_r1.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                traffic = json.load(open(path)).get("dram_bytes_per_launch")
+                break
     except Exception:
         pass
     line = {
@@ -371,7 +385,7 @@ def main():
         "roofline": {"kernel": "gemm_i8_kernel (tcgen05.mma kind::i8 -> UTCIMMA; 28 exact int8 products per FP64 product)",
                      "bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TFLOP/s",
                      "frac": (int8_tops / int8_peak) if int8_tops else None, "traffic": traffic, "peak_source": int8_src,
-                     "how": "28 x algorithmic FP64 GEMM flops issued on the INT8 path in the step / CUDA-event time of the GEMM-only phases (potrf x2, trtri, lauum, predict trsm; these also hold the short-k DMMA GEMMs and the diagonal-block kernels) on the library stream; traffic = ncu dram bytes of one 8192^3 launch",
+                     "how": "28 x algorithmic FP64 GEMM flops issued on the INT8 path in the step / CUDA-event time of the GEMM-only phases (potrf x2, trtri, lauum, predict planes + solve; these also hold the operand splitting, the short-k DMMA GEMMs and the diagonal-block kernels) on the library stream; traffic = ncu dram bytes of one launch of the predict shape",
                      "fp64_equivalent": {"achieved": gemm_tf, "fp64_dmma_peak": peak, "ratio": (gemm_tf / peak) if gemm_tf else None,
                                          "int8_share_of_gemm_flops": (flops_i8 / flops) if flops else None, "fp64_peak_source": peak_src}},
         "cholesky": {"seconds": potrf_ms * 1e-3, "tflops": chol_tf, "frac_of_fp64_peak": chol_tf / peak if chol_tf else None, "flops": "N^3/3"},

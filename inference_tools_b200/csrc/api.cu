@@ -280,8 +280,7 @@ void gpb_ctx_destroy(gpb_ctx* c) {
                       reinterpret_cast<double*>(c->argws)};
     for (double* p : ptrs)
         if (p) cudaFree(p);
-    for (void* p : {(void*)c->pp.lbuf, (void*)c->pp.wbuf, (void*)c->pp.xbuf, (void*)c->pp.tbuf, (void*)c->pp.lscale,
-                    (void*)c->pp.wscale, (void*)c->pp.xscale, (void*)c->pp.tscale, (void*)c->pp.bound, (void*)c->pp.wtmp})
+    for (void* p : {(void*)c->pp.lbuf, (void*)c->pp.xbuf, (void*)c->pp.lscale, (void*)c->pp.xscale, (void*)c->pp.bound})
         if (p) cudaFree(p);
     dist_destroy(c);
     linv_destroy(c);
@@ -829,16 +828,21 @@ int64_t chunk_rows(const gpb_ctx* c) {
 // ---- blocked predict solve on cached digit planes --------------------------------------------------------------------------
 // X = S L^-T for a chunk of stacked cross-covariance rows, left-looking over block columns of width nb:
 //     T_j = S_j - X_{<j} L_{j,<j}^T        one INT8 GEMM, k = j nb, both operands already split
-//     X_j = T_j inv(L_jj)^T                 one INT8 GEMM, k = nb_j (triangular)
-// L's planes and the inverted diagonal blocks are split ONCE per fit; each block of X is split once, right after it is
-// solved.  A GEMM needs one scale per operand row over its whole k extent, while the blocks of a row of X appear one at a
-// time -- so X uses an a-priori bound instead of the measured row maximum: row 0 of a query's stack is v = L^-1 k_q with
-// |v|^2 <= k(q, q) (the posterior variance k(q,q) - |v|^2 is non-negative); rows a >= 1 (SquaredExponential gradient
-// terms) are L^-1 (A_a o k_q) with squared norm <= a^2 / l_a^2, the prior variance of df/dx_a.  HEADROOM = 8 covers
-// rounding in badly conditioned fits (values beyond it are clamped); it costs 3 of the 55 bits kept per element.
-// Replaces the recursion (trsm_right_lt), which re-split L for every chunk and level, dropped to DMMA for its k < 512
-// leaves and copied every leaf result (round-1 profile: 1108 split launches, 3584 copy2d launches per step).
-constexpr double X_BOUND_HEADROOM = 8.0;
+//     X_j = T_j L_jj^-T                     the recursive solve (trsm_right_lt) inside the nb x nb diagonal block
+// L's off-diagonal planes are split ONCE per fit; each block of X is split once, right after it is solved.  A GEMM needs
+// one scale per operand row over its whole k extent, while the blocks of a row of X appear one at a time -- so X uses an
+// a-priori bound instead of the measured row maximum: row 0 of a query's stack is v = L^-1 k_q with |v|^2 <= k(q, q)
+// (the posterior variance k(q,q) - |v|^2 is non-negative); rows a >= 1 (SquaredExponential gradient terms) are
+// L^-1 (A_a o k_q) with squared norm <= a^2 / l_a^2, the prior variance of df/dx_a.  Values a rounding error beyond the
+// bound are clamped by the split kernel.
+// The diagonal blocks are NOT solved by an INT8 product with an explicit inverse: the entries of inv(L_jj) grow like
+// 1 / sigma_noise, the digit-split product is accurate only normwise (relative to the row maxima), and sigma^2 =
+// k(q,q) - |v|^2 cancels -- measured on the conditioning sweep, that variant lost a factor 10 (cond 1e6) to 1e5 (cond 1e11)
+// against the FP64 path in sigma.  The recursion multiplies by inverted 128-blocks on the FP64 tensor pipe and uses the
+// INT8 path only for its benign X L21^T updates, and matches the FP64 path (profiles/conditioning_sweep_r2.md).
+// Replaces the full-width recursion, which re-split L for every chunk and level (round-1 profile: 1108 split launches
+// per step, 6.6 % of the GPU time) and ran 98 % of its flops at k <= N/2 GEMMs of decreasing size.
+constexpr double X_BOUND_HEADROOM = 1.0 + 1e-6;
 
 int predict_block_width(const gpb_ctx* c, int rows_pad) {
     const int mode = gemm_i8_override() >= 0 ? gemm_i8_override() : (int)option(OPT_GEMM_I8);
@@ -863,20 +867,12 @@ int build_predict_planes(gpb_ctx* c, int nb, int ns, int64_t rows_cap) {
     auto cols_of = [&](int j) { return std::min(nb, npad - j * nb); };
     if (!(pp.valid && pp.nb == nb)) {
         pp.valid = false;
-        size_t lbytes = 0, wbytes = 0;
-        for (int j = 0; j < nblk; ++j) {
-            lbytes += i8_plane_bytes(cols_of(j), (int64_t)j * nb);
-            wbytes += i8_plane_bytes(cols_of(j), cols_of(j));
-        }
+        size_t lbytes = 0;
+        for (int j = 0; j < nblk; ++j) lbytes += i8_plane_bytes(cols_of(j), (int64_t)j * nb);
         GPB_TRY(ensure(pp.lbuf, pp.lbuf_cap, std::max<size_t>(lbytes, 16)));
-        GPB_TRY(ensure(pp.wbuf, pp.wbuf_cap, wbytes));
         GPB_TRY(ensure(pp.lscale, pp.lscale_cap, sizeof(double) * npad));
-        GPB_TRY(ensure(pp.wscale, pp.wscale_cap, sizeof(double) * npad));
-        GPB_TRY(ensure(pp.wtmp, pp.wtmp_cap, sizeof(double) * 2 * (size_t)nb * nb));
         pp.Lp.assign(nblk, I8Planes());
-        pp.Wp.assign(nblk, I8Planes());
-        size_t lo = 0, wo = 0;
-        const LinalgWs ws = ws_of(c, c->dinv_fit);
+        size_t lo = 0;
         for (int j = 0; j < nblk; ++j) {
             const int k0 = j * nb, nbj = cols_of(j);
             I8Planes& L = pp.Lp[j];
@@ -887,39 +883,19 @@ int build_predict_planes(gpb_ctx* c, int nb, int ns, int64_t rows_cap) {
             L.plane = (int64_t)nbj * k0;
             lo += i8_plane_bytes(nbj, k0);
             if (j > 0) GPB_TRY(i8_split_rows(c->Lfit + (size_t)k0 * npad, npad, nbj, k0, false, nullptr, 1, L, 0, 0, c->s));
-            I8Planes& W = pp.Wp[j];
-            W.q = pp.wbuf + wo;
-            W.scale = pp.wscale + k0;
-            W.rows = nbj;
-            W.ld = nbj;
-            W.plane = (int64_t)nbj * nbj;
-            wo += i8_plane_bytes(nbj, nbj);
-            // inv(L_jj) in FP64 (recursion on the inverted 128-blocks), then its planes
-            double* Wd = pp.wtmp;
-            GPB_CUDA(cudaMemsetAsync(Wd, 0, sizeof(double) * (size_t)nbj * nbj, c->s));
-            GPB_TRY(trtri_lower(c->Lfit + (size_t)k0 * npad + k0, npad, Wd, nbj, nbj, k0 / NB, ws, pp.wtmp + (size_t)nb * nb, nb,
-                                c->s));
-            GPB_TRY(i8_split_rows(Wd, nbj, nbj, nbj, false, nullptr, 1, W, 0, 0, c->s));
         }
         pp.nb = nb;
         pp.nblk = nblk;
         pp.valid = true;
     }
-    // per-chunk planes
+    // per-chunk planes of the solved columns
     GPB_TRY(ensure(pp.xbuf, pp.xbuf_cap, i8_plane_bytes(rows_cap, npad)));
-    GPB_TRY(ensure(pp.tbuf, pp.tbuf_cap, i8_plane_bytes(rows_cap, nb)));
     GPB_TRY(ensure(pp.xscale, pp.xscale_cap, sizeof(double) * rows_cap));
-    GPB_TRY(ensure(pp.tscale, pp.tscale_cap, sizeof(double) * rows_cap));
     pp.Xp.q = pp.xbuf;
     pp.Xp.scale = pp.xscale;
     pp.Xp.rows = rows_cap;
     pp.Xp.ld = npad;
     pp.Xp.plane = rows_cap * (int64_t)npad;
-    pp.Tp.q = pp.tbuf;
-    pp.Tp.scale = pp.tscale;
-    pp.Tp.rows = rows_cap;
-    pp.Tp.ld = nb;
-    pp.Tp.plane = rows_cap * (int64_t)nb;
     if (pp.ns != ns || !pp.bound) {  // a-priori bounds of the rows of a query's stack
         GPB_TRY(ensure(pp.bound, pp.bound_cap, sizeof(double) * (MAX_DIM + 1)));
         double b[MAX_DIM + 1] = {0};
@@ -938,13 +914,13 @@ int build_predict_planes(gpb_ctx* c, int nb, int ns, int64_t rows_cap) {
 int predict_solve_blocked(gpb_ctx* c, int rows_pad, int ns) {
     PredictPlanes& pp = c->pp;
     const int npad = (int)c->npad, nb = pp.nb;
+    const LinalgWs ws = ws_of(c, c->dinv_fit);
     for (int j = 0; j < pp.nblk; ++j) {
         const int k0 = j * nb, nbj = std::min(nb, npad - k0);
         double* Sj = c->S + k0;
         if (j > 0)
             GPB_TRY(i8_gemm_planes(pp.Xp, 0, pp.Lp[j], 0, rows_pad, nbj, k0, Sj, npad, Sj, npad, -1.0, 1.0, GEMM_FULL, c->s));
-        GPB_TRY(i8_split_rows(Sj, npad, rows_pad, nbj, true, nullptr, 1, pp.Tp, 0, 0, c->s));
-        GPB_TRY(i8_gemm_planes(pp.Tp, 0, pp.Wp[j], 0, rows_pad, nbj, nbj, nullptr, 0, Sj, npad, 1.0, 0.0, GEMM_TRIL_B, c->s));
+        GPB_TRY(trsm_right_lt(Sj, npad, rows_pad, c->Lfit + (size_t)k0 * npad + k0, npad, nbj, k0 / NB, ws, c->s));
         if (j + 1 < pp.nblk) GPB_TRY(i8_split_rows(Sj, npad, rows_pad, nbj, true, pp.bound, ns, pp.Xp, 0, k0, c->s));
     }
     return 0;
@@ -1000,7 +976,7 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
         GPB_TRY(launch_row_dot(c->S, npad, rows, npad, c->alpha, c->dots, c->s));
         c->timer.mark("trsm");
         if (blocked) {
-            GPB_TRY(run_graphed(c, pkey("pblk", {c->S, c->pp.lbuf, c->pp.wbuf, c->pp.xbuf, c->pp.tbuf}, {npad, rows_pad, nb_solve, ns}),
+            GPB_TRY(run_graphed(c, pkey("pblk", {c->S, c->pp.lbuf, c->pp.xbuf, c->Lfit, c->dinv_fit, c->tmp}, {npad, rows_pad, nb_solve, ns}),
                                 [&]() { return predict_solve_blocked(c, rows_pad, ns); }));
         } else {
             GPB_TRY(run_graphed(c, pkey("ptrsm", {c->S, c->Lfit, c->dinv_fit, c->tmp}, {npad, rows_pad}),

@@ -1,0 +1,69 @@
+"""Turns the JSON results of tools/parity_at_scale.py (copied into profiles/) into the markdown tables DESIGN.md cites."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = lambda n: os.path.join(ROOT, "profiles", n)
+f = lambda v: "-" if v is None else (f"{v:.1e}" if isinstance(v, float) else str(v))
+
+
+def cond():
+    r = json.load(open(P("conditioning_sweep_r2.json")))
+    out = ["# Conditioning sweep (round 2): INT8 digit-split GEMM path vs FP64 DMMA path vs CPU oracle", "",
+           r["what"] + ".  `default` = the shipped dispatch (INT8 where it pays, chunked K^-1 product, gradient guard on);",
+           "`int8_forced` = INT8 wherever the kernel's shape rules allow (k >= 64); `dmma` = FP64 tensor pipe only.",
+           "Errors are relative to the oracle (grad: max-norm relative).  `retry` = the gradient guard repeated K^-1 on DMMA.", "",
+           "| l | sigma_n | cond(K) | mode | alpha | mu | sigma | LML | grad LML | retry |", "|---|---|---|---|---|---|---|---|---|---|"]
+    for c in r["cases"]:
+        for mode in ("default", "int8_forced", "dmma"):
+            e = c[mode]
+            if "failed" in e:
+                out.append(f"| {c['l']} | {c['sigma_n']} | {c['cond']:.1e} | {mode} | {e['failed']} |||||")
+                continue
+            out.append(f"| {c['l']} | {c['sigma_n']} | {c['cond']:.1e} | {mode} | {f(e['alpha'])} | {f(e['mu'])} | {f(e['sigma'])} | "
+                       f"{f(e['lml'])} | {f(e['grad'])} | {int(e.get('stats', {}).get('grad_guard_retries', 0))} |")
+    open(P("conditioning_sweep_r2.md"), "w").write("\n".join(out) + "\n")
+
+
+def scale():
+    r = json.load(open(P("parity_at_scale_r2.json")))
+    out = ["# Parity at the sizes the INT8 path runs (round 2)", "", r["what"] + ".",
+           "Oracle: oracle/gp_oracle.py (row-blocked; numpy.linalg.cholesky, scipy solve_triangular on the identity, iK.T @ iK) on the GPU box's 16 host cores.", "",
+           "| N | d | kernel | mode | alpha | mu | sigma | LML | grad LML | INT8 share of GEMM flops | guard retry | oracle s |",
+           "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    for c in r["cases"]:
+        for mode in ("default", "dmma"):
+            e = c[mode]
+            out.append(f"| {c['N']} | {c['d']} | {c['kernel']} | {mode} | {f(e['alpha'])} | {f(e['mu'])} | {f(e['sigma'])} | {f(e['lml'])} | "
+                       f"{f(e['grad'])} | {e['int8_share']:.2f} | {int(e.get('stats', {}).get('grad_guard_retries', 0))} | {c['oracle_seconds']:.0f} |")
+    open(P("parity_at_scale_r2.md"), "w").write("\n".join(out) + "\n")
+
+
+def phases():
+    out = ["# Which phase of marginal_likelihood_gradient is sensitive to the INT8 GEMM? (round 2)", "",
+           "SquaredExponential 3-D, l = 0.35, y_err = 0.05; gradient error vs the CPU oracle with the INT8 path allowed in exactly",
+           "the phases of the mask (1 potrf, 2 trtri, 4 lauum = K^-1 = W^T W), guard off; then K^-1 alone on INT8 with its k extent",
+           "cut into chunks (each chunk has its own row scales; FP64 accumulation across chunks).", ""]
+    for n in (8192, 16384):
+        try:
+            r = json.load(open(P(f"grad_phase_sensitivity_N{n}_r2.json")))
+        except Exception:
+            continue
+        out += [f"## N = {n}", "", "| case | grad rel. error | abs. error | lauum ms |", "|---|---|---|---|"]
+        names = {0: "all DMMA", 1: "potrf INT8", 2: "trtri INT8", 4: "lauum INT8", 3: "potrf+trtri INT8", 6: "trtri+lauum INT8", 7: "all INT8 (unchunked)"}
+        for c in r["cases"]:
+            if "mask" in c:
+                out.append(f"| {names[c['mask']]} | {f(c['grad_rel'])} | {f(c['grad_abs'])} | |")
+            else:
+                out.append(f"| lauum INT8, chunk {c['lauum_only_max_k']} | {f(c['grad_rel'])} | {f(c['grad_abs'])} | {c['lauum_ms']:.1f} |")
+        g = r.get("guarded")
+        if g:
+            out.append(f"| shipped dispatch (chunk 4096 + guard) | {f(g['grad_rel'])} | | retries {int(g['retries'])} |")
+        out.append("")
+    open(P("grad_phase_sensitivity_r2.md"), "w").write("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    for fn in (cond, scale, phases):
+        try:
+            fn()
+        except FileNotFoundError as e:
+            print("skip", e)

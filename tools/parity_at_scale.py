@@ -1,6 +1,6 @@
 """Parity of the CUDA engine against the CPU oracle at the sizes the INT8 tensor-core GEMM path runs (gpurun only).
 
-    python tools/parity_at_scale.py scale 8192 16384 32768      # alpha, mu/sigma (256 points), LML, grad LML vs oracle
+    python tools/parity_at_scale.py scale 8192 16384 32768      # alpha, mu/sigma (4096 points), LML, grad LML vs oracle
     python tools/parity_at_scale.py cond [N]                     # conditioning sweep: INT8 / DMMA / oracle, cond(K) 1e3 -> 1e12
     python tools/parity_at_scale.py cfg1                         # N = 200 latency of one LML-gradient evaluation
 
@@ -99,7 +99,7 @@ def run_scale(sizes):
     for n in sizes:
         for d, comps, kernel, theta in cases_for(n):
             x, y, e = synth(2024 + n, n, d)
-            q = np.random.default_rng(n).uniform(0, 1, (256, d))
+            q = np.random.default_rng(n).uniform(0, 1, (4096, d))      # enough rows for the blocked predict solve
             o = oracle_results(x, y, e, comps, theta, q)
             entry = {"N": n, "d": d, "kernel": "+".join(comps), "oracle_seconds": o["seconds_grad"] + o["seconds_fit_predict"],
                      "cond_lower_bound_from_L": float((o["L_diag"].max() / o["L_diag"].min()) ** 2), "lml": o["lml"]}
@@ -119,7 +119,7 @@ def run_cond(n=4096):
         for sn in (0.1, 0.03, 0.01, 0.003, 0.001, 0.0003, 0.0001):
             x, y, e = synth(7, n, d, sn)
             theta = np.array([0.3, 0.1] + [np.log(ls)] * d)
-            q = np.random.default_rng(1).uniform(0, 1, (256, d))
+            q = np.random.default_rng(1).uniform(0, 1, (4096, d))      # enough rows for the blocked predict solve
             tm, parts = orc.split_theta(theta, ("SE",), "const", n, d)
             w = np.linalg.eigvalsh(orc.train_cov(("SE",), parts, x, e**2))
             o = oracle_results(x, y, e, ("SE",), theta, q)
