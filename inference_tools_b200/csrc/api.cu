@@ -280,7 +280,8 @@ void gpb_ctx_destroy(gpb_ctx* c) {
                       reinterpret_cast<double*>(c->argws)};
     for (double* p : ptrs)
         if (p) cudaFree(p);
-    for (void* p : {(void*)c->pp.lbuf, (void*)c->pp.xbuf, (void*)c->pp.lscale, (void*)c->pp.xscale, (void*)c->pp.bound})
+    for (void* p : {(void*)c->pp.lbuf, (void*)c->pp.wbuf, (void*)c->pp.xbuf, (void*)c->pp.tbuf, (void*)c->pp.lscale,
+                    (void*)c->pp.wscale, (void*)c->pp.xscale, (void*)c->pp.tscale, (void*)c->pp.bound, (void*)c->pp.wtmp})
         if (p) cudaFree(p);
     dist_destroy(c);
     linv_destroy(c);
@@ -493,9 +494,14 @@ static int factor_impl(gpb_ctx* c, const double* theta, int* info) {
     make_mean_params(c, theta, c->mp_fit);
     int info_h = 0;
     GPB_TRY(assemble_and_factor(c, c->cp_fit, c->mp_fit, c->Lfit, c->dinv_fit, c->mu, SOLVE_BOTH, c->alpha, &info_h));
+    // smallest pivot of the factor: the conditioning measure behind the predict solve's choice of diagonal-block variant
+    GPB_TRY(launch_logdet_dot(c->Lfit, c->npad, c->alpha, c->alpha, (int)c->n, c->scal, c->s));
+    double sc3[3] = {0.0, 0.0, 0.0};
+    GPB_CUDA(cudaMemcpyAsync(sc3, c->scal, sizeof(sc3), cudaMemcpyDeviceToHost, c->s));
     c->timer.mark("end");
     GPB_CUDA(cudaStreamSynchronize(c->s));
     *info = info_h;
+    c->min_pivot_fit = sc3[2];
     if (info_h == 0) {
         c->theta_fit.assign(theta, theta + c->n_mean + c->n_cov);
         c->fitted = true;
@@ -835,18 +841,37 @@ int64_t chunk_rows(const gpb_ctx* c) {
 // (the posterior variance k(q,q) - |v|^2 is non-negative); rows a >= 1 (SquaredExponential gradient terms) are
 // L^-1 (A_a o k_q) with squared norm <= a^2 / l_a^2, the prior variance of df/dx_a.  Values a rounding error beyond the
 // bound are clamped by the split kernel.
-// The diagonal blocks are NOT solved by an INT8 product with an explicit inverse: the entries of inv(L_jj) grow like
-// 1 / sigma_noise, the digit-split product is accurate only normwise (relative to the row maxima), and sigma^2 =
-// k(q,q) - |v|^2 cancels -- measured on the conditioning sweep, that variant lost a factor 10 (cond 1e6) to 1e5 (cond 1e11)
-// against the FP64 path in sigma.  The recursion multiplies by inverted 128-blocks on the FP64 tensor pipe and uses the
-// INT8 path only for its benign X L21^T updates, and matches the FP64 path (profiles/conditioning_sweep_r2.md).
+// Two variants of the diagonal solve.  (fast) X_j = T_j inv(L_jj)^T as one INT8 product with the explicit inverse of the
+// block, split once per fit.  The entries of inv(L_jj) grow like w = 1 / min L_ii, the digit-split product is accurate
+// only normwise (relative to the row maxima), and sigma^2 = k(q,q) - |v|^2 cancels down to ~ k(q,q) / w^2 at the training
+// points, so the relative error of sigma^2 is about 2^-56 sqrt(nb) w^3 (w in units of the prior sigma): measured on the
+// conditioning sweep this variant lost a factor 5 (w = 10) to 1e5 (w = 1e4) against the FP64 path in sigma.  It is
+// used only while PREDICT_W_C w^3 <= PREDICT_W_TOL (w <~ 30: the benchmark's fit has w = 16).  (robust) otherwise: the
+// recursive solve inside the block, which multiplies by inverted 128-blocks on the FP64 tensor pipe and uses the INT8
+// path only for its benign X L21^T updates; it matches the FP64 path over the whole sweep
+// (profiles/conditioning_sweep_r2.md) and costs ~9 % more time in the solve.
 // Replaces the full-width recursion, which re-split L for every chunk and level (round-1 profile: 1108 split launches
 // per step, 6.6 % of the GPU time) and ran 98 % of its flops at k <= N/2 GEMMs of decreasing size.
 constexpr double X_BOUND_HEADROOM = 1.0 + 1e-6;
+constexpr double PREDICT_W_C = 2.0 * 1.3877787807814457e-17 * 64.0, PREDICT_W_TOL = 5e-11;
+
+bool predict_fast_diag(const gpb_ctx* c) {
+    if (option(OPT_PREDICT_DIAG) == 1) return false;   // 0 = by conditioning, 1 = always robust, 2 = always fast
+    if (option(OPT_PREDICT_DIAG) == 2) return true;
+    double amp2 = 0.0;
+    for (int i = 0; i < c->ncomp; ++i)
+        if (c->kinds[i] <= COV_RQ) amp2 += c->cp_fit.amp2[i];
+    if (!(c->min_pivot_fit > 0.0) || !(amp2 > 0.0)) return false;
+    const double w = std::sqrt(amp2) / c->min_pivot_fit;
+    return PREDICT_W_C * w * w * w <= PREDICT_W_TOL;
+}
 
 int predict_block_width(const gpb_ctx* c, int rows_pad) {
     const int mode = gemm_i8_override() >= 0 ? gemm_i8_override() : (int)option(OPT_GEMM_I8);
-    const int want = (int)option(OPT_PREDICT_BLOCK);
+    // option "predict_block": -1 = off (full-width recursion), 0 = by variant (measured on the benchmark step: 4096 is the
+    // fastest width with the INT8 diagonal solve, 1024 with the recursive one), else the width itself
+    int want = (int)option(OPT_PREDICT_BLOCK);
+    if (want == 0) want = predict_fast_diag(c) ? 4096 : 1024;
     if (mode == 0 || want < NB) return 0;
     const int npad = (int)c->npad;
     const int quarter = (npad / 4) / NB * NB;
@@ -865,14 +890,25 @@ int build_predict_planes(gpb_ctx* c, int nb, int ns, int64_t rows_cap) {
     const int npad = (int)c->npad;
     const int nblk = (npad + nb - 1) / nb;
     auto cols_of = [&](int j) { return std::min(nb, npad - j * nb); };
-    if (!(pp.valid && pp.nb == nb)) {
+    const bool use_w = predict_fast_diag(c);
+    if (!(pp.valid && pp.nb == nb && pp.use_w == use_w)) {
         pp.valid = false;
-        size_t lbytes = 0;
-        for (int j = 0; j < nblk; ++j) lbytes += i8_plane_bytes(cols_of(j), (int64_t)j * nb);
+        size_t lbytes = 0, wbytes = 0;
+        for (int j = 0; j < nblk; ++j) {
+            lbytes += i8_plane_bytes(cols_of(j), (int64_t)j * nb);
+            wbytes += i8_plane_bytes(cols_of(j), cols_of(j));
+        }
         GPB_TRY(ensure(pp.lbuf, pp.lbuf_cap, std::max<size_t>(lbytes, 16)));
         GPB_TRY(ensure(pp.lscale, pp.lscale_cap, sizeof(double) * npad));
         pp.Lp.assign(nblk, I8Planes());
-        size_t lo = 0;
+        pp.Wp.assign(nblk, I8Planes());
+        if (use_w) {
+            GPB_TRY(ensure(pp.wbuf, pp.wbuf_cap, wbytes));
+            GPB_TRY(ensure(pp.wscale, pp.wscale_cap, sizeof(double) * npad));
+            GPB_TRY(ensure(pp.wtmp, pp.wtmp_cap, sizeof(double) * 2 * (size_t)nb * nb));
+        }
+        size_t lo = 0, wo = 0;
+        const LinalgWs ws = ws_of(c, c->dinv_fit);
         for (int j = 0; j < nblk; ++j) {
             const int k0 = j * nb, nbj = cols_of(j);
             I8Planes& L = pp.Lp[j];
@@ -883,14 +919,38 @@ int build_predict_planes(gpb_ctx* c, int nb, int ns, int64_t rows_cap) {
             L.plane = (int64_t)nbj * k0;
             lo += i8_plane_bytes(nbj, k0);
             if (j > 0) GPB_TRY(i8_split_rows(c->Lfit + (size_t)k0 * npad, npad, nbj, k0, false, nullptr, 1, L, 0, 0, c->s));
+            if (!use_w) continue;
+            I8Planes& W = pp.Wp[j];
+            W.q = pp.wbuf + wo;
+            W.scale = pp.wscale + k0;
+            W.rows = nbj;
+            W.ld = nbj;
+            W.plane = (int64_t)nbj * nbj;
+            wo += i8_plane_bytes(nbj, nbj);
+            // inv(L_jj) in FP64 (recursion on the inverted 128-blocks), then its planes
+            double* Wd = pp.wtmp;
+            GPB_CUDA(cudaMemsetAsync(Wd, 0, sizeof(double) * (size_t)nbj * nbj, c->s));
+            GPB_TRY(trtri_lower(c->Lfit + (size_t)k0 * npad + k0, npad, Wd, nbj, nbj, k0 / NB, ws, pp.wtmp + (size_t)nb * nb, nb,
+                                c->s));
+            GPB_TRY(i8_split_rows(Wd, nbj, nbj, nbj, false, nullptr, 1, W, 0, 0, c->s));
         }
         pp.nb = nb;
         pp.nblk = nblk;
+        pp.use_w = use_w;
         pp.valid = true;
     }
-    // per-chunk planes of the solved columns
+    // per-chunk planes of the solved columns (and, fast variant, of the block before its diagonal solve)
     GPB_TRY(ensure(pp.xbuf, pp.xbuf_cap, i8_plane_bytes(rows_cap, npad)));
     GPB_TRY(ensure(pp.xscale, pp.xscale_cap, sizeof(double) * rows_cap));
+    if (use_w) {
+        GPB_TRY(ensure(pp.tbuf, pp.tbuf_cap, i8_plane_bytes(rows_cap, nb)));
+        GPB_TRY(ensure(pp.tscale, pp.tscale_cap, sizeof(double) * rows_cap));
+        pp.Tp.q = pp.tbuf;
+        pp.Tp.scale = pp.tscale;
+        pp.Tp.rows = rows_cap;
+        pp.Tp.ld = nb;
+        pp.Tp.plane = rows_cap * (int64_t)nb;
+    }
     pp.Xp.q = pp.xbuf;
     pp.Xp.scale = pp.xscale;
     pp.Xp.rows = rows_cap;
@@ -920,7 +980,12 @@ int predict_solve_blocked(gpb_ctx* c, int rows_pad, int ns) {
         double* Sj = c->S + k0;
         if (j > 0)
             GPB_TRY(i8_gemm_planes(pp.Xp, 0, pp.Lp[j], 0, rows_pad, nbj, k0, Sj, npad, Sj, npad, -1.0, 1.0, GEMM_FULL, c->s));
-        GPB_TRY(trsm_right_lt(Sj, npad, rows_pad, c->Lfit + (size_t)k0 * npad + k0, npad, nbj, k0 / NB, ws, c->s));
+        if (pp.use_w) {
+            GPB_TRY(i8_split_rows(Sj, npad, rows_pad, nbj, true, nullptr, 1, pp.Tp, 0, 0, c->s));
+            GPB_TRY(i8_gemm_planes(pp.Tp, 0, pp.Wp[j], 0, rows_pad, nbj, nbj, nullptr, 0, Sj, npad, 1.0, 0.0, GEMM_TRIL_B, c->s));
+        } else {
+            GPB_TRY(trsm_right_lt(Sj, npad, rows_pad, c->Lfit + (size_t)k0 * npad + k0, npad, nbj, k0 / NB, ws, c->s));
+        }
         if (j + 1 < pp.nblk) GPB_TRY(i8_split_rows(Sj, npad, rows_pad, nbj, true, pp.bound, ns, pp.Xp, 0, k0, c->s));
     }
     return 0;
@@ -976,7 +1041,8 @@ int predict_driver(gpb_ctx* c, const double* q_dev, int64_t m, PredMode mode, do
         GPB_TRY(launch_row_dot(c->S, npad, rows, npad, c->alpha, c->dots, c->s));
         c->timer.mark("trsm");
         if (blocked) {
-            GPB_TRY(run_graphed(c, pkey("pblk", {c->S, c->pp.lbuf, c->pp.xbuf, c->Lfit, c->dinv_fit, c->tmp}, {npad, rows_pad, nb_solve, ns}),
+            GPB_TRY(run_graphed(c, pkey("pblk", {c->S, c->pp.lbuf, c->pp.xbuf, c->pp.wbuf, c->pp.tbuf, c->Lfit, c->dinv_fit, c->tmp},
+                                     {npad, rows_pad, nb_solve, ns, c->pp.use_w}),
                                 [&]() { return predict_solve_blocked(c, rows_pad, ns); }));
         } else {
             GPB_TRY(run_graphed(c, pkey("ptrsm", {c->S, c->Lfit, c->dinv_fit, c->tmp}, {npad, rows_pad}),

@@ -56,15 +56,17 @@ int ensure(T*& p, size_t& cap, size_t bytes) {
 
 // Digit planes of the fitted factor for the blocked predict solve (api.cu: predict_solve_blocked), built once per fit:
 //   Lp[j]  rows of block row j of L left of its diagonal block (nb_j x j nb), the B operand of T_j = S_j - X_<j L_j,<j^T
-// and per query chunk: Xp, the solved columns (a-priori row scale).
+//   Wp[j]  inv(L_jj) (nb_j x nb_j, lower), only for well-conditioned fits (use_w): the B operand of X_j = T_j inv(L_jj)^T
+// and per query chunk: Xp, the solved columns (a-priori row scale), Tp, the current block before its diagonal solve.
 struct PredictPlanes {
-    bool valid = false;
+    bool valid = false, use_w = false;
     int nb = 0, nblk = 0, ns = 0;
-    std::vector<gpb::I8Planes> Lp;
-    gpb::I8Planes Xp;
-    signed char *lbuf = nullptr, *xbuf = nullptr;
-    double *lscale = nullptr, *xscale = nullptr, *bound = nullptr;
-    size_t lbuf_cap = 0, xbuf_cap = 0, lscale_cap = 0, xscale_cap = 0, bound_cap = 0;
+    std::vector<gpb::I8Planes> Lp, Wp;
+    gpb::I8Planes Xp, Tp;
+    signed char *lbuf = nullptr, *wbuf = nullptr, *xbuf = nullptr, *tbuf = nullptr;
+    double *lscale = nullptr, *wscale = nullptr, *xscale = nullptr, *tscale = nullptr, *bound = nullptr, *wtmp = nullptr;
+    size_t lbuf_cap = 0, wbuf_cap = 0, xbuf_cap = 0, tbuf_cap = 0, lscale_cap = 0, wscale_cap = 0, xscale_cap = 0,
+           tscale_cap = 0, bound_cap = 0, wtmp_cap = 0;
 };
 
 struct gpb_dist;  // dist.cu
@@ -90,6 +92,7 @@ struct gpb_ctx {
     size_t Lfit_cap = 0, dinv_fit_cap = 0, alpha_cap = 0, mu_cap = 0;
     std::vector<double> theta_fit;
     bool fitted = false;
+    double min_pivot_fit = 0.0;  // min_i L_ii of the fitted factor
     gpb::CovParams cp_fit;
     gpb::MeanParams mp_fit;
     // objective-evaluation workspace

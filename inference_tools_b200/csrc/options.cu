@@ -41,7 +41,8 @@ struct OptionTable {
         v[OPT_GEMM_TMA] = env("GPB200_GEMM_TMA", 1);
         v[OPT_GRAPHS] = getenv("GPB200_NO_GRAPHS") ? 0 : 1;
         v[OPT_I8_FALLBACK] = env("GPB200_I8_FALLBACK", 1);
-        v[OPT_PREDICT_BLOCK] = env("GPB200_PREDICT_BLOCK", 2048);
+        v[OPT_PREDICT_BLOCK] = env("GPB200_PREDICT_BLOCK", 0);
+        v[OPT_PREDICT_DIAG] = env("GPB200_PREDICT_DIAG", 0);
         v[OPT_I8_GRAD_GUARD] = env("GPB200_I8_GRAD_GUARD", 1);
         v[OPT_GEMM_I8_MAX_K] = env("GPB200_GEMM_I8_MAX_K", 16384);
         v[OPT_GEMM_I8_EPI] = env("GPB200_GEMM_I8_EPI", 0);
@@ -54,7 +55,7 @@ OptionTable& table() {
 }
 
 const char* const kNames[OPT_COUNT] = {"gemm_i8",  "gemm_i8_min_k", "gemm_i8_pair", "gemm_i8_debug", "gemm_tile",
-                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block", "i8_grad_guard", "gemm_i8_max_k", "gemm_i8_epi", "i8_grad_phases"};
+                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block", "predict_diag", "i8_grad_guard", "gemm_i8_max_k", "gemm_i8_epi", "i8_grad_phases"};
 
 int find_option(const char* name) {
     if (!name) return -1;

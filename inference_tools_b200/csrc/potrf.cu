@@ -301,10 +301,10 @@ int lauum_lower(const double* W, int64_t ldw, double* Kinv, int64_t ldk, int n, 
     GemmArgs g{n, n, n, W, ldw, W, ldw, nullptr, 0, Kinv, ldk, nullptr, 0, 1.0, 0.0,
                GEMM_A_MMAJOR | GEMM_B_NMAJOR | GEMM_TRIK_A | GEMM_TRIK_B | GEMM_LOWER};
     // The columns of W = inv(L) decay away from the diagonal while the INT8 path keeps 55 bits below each operand row's
-    // MAXIMUM over the k extent of a launch.  4096-long chunks (own scales each) cut the error of K^-1 -- which the
-    // gradient trace amplifies -- 24-fold at N = 16384 for 18 % more time in this product
+    // MAXIMUM over the k extent of a launch.  Chunks of N/4 (at most 4096, at least 1024; own scales each) cut the error
+    // of K^-1 -- which the gradient trace amplifies -- 24-fold at N = 16384 for 18 % more time in this product
     // (profiles/grad_phase_sensitivity_r2.md).
-    g.max_k = 4096;
+    g.max_k = std::min(4096, std::max(1024, (n / 4) / 64 * 64));
     return gemm_nt(g, s);
 }
 
