@@ -408,7 +408,13 @@ int dist_factor_impl(gpb_ctx* c, const double* theta, int block, int* info_out, 
             did_la[k] = 1;
             GPB_TRY(factor_panel(k + 1));
         }
-        // (3) trailing update of the other owned columns; v_k = the residual row of the panel, kept on every rank
+        // (3) trailing update of the other owned columns; v_k = the residual row of the panel, kept on every rank.
+        // On the owner of panel k+1 the trailing update waits until that panel is factored: the persistent INT8 GEMM
+        // occupies every SM for the whole launch, so stream priority cannot get the ~60 short dependent kernels of the
+        // panel chain in between trailing launches -- each would wait for a full trailing GEMM.  Ordering instead of
+        // priority keeps the chain (the sweep's critical path) undisturbed; the owner catches up on its trailing work
+        // while the panel travels.
+        if (k + 1 < nblk && d->owner(k + 1) == me && G > 1) GPB_CUDA(cudaStreamWaitEvent(s_main, d->ev(EV_PANEL(k + 1)), 0));
         GPB_CUDA(cudaStreamWaitEvent(s_main, d->ev(EV_BCAST(k)), 0));
         GPB_CUDA(cudaMemcpyAsync(d->v_full + (size_t)k * nbd, pb[k & 1] + (size_t)(npad - d->row_end(k)) * nbd,
                                  sizeof(double) * d->cols_of(k), cudaMemcpyDeviceToDevice, s_main));

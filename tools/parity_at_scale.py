@@ -164,6 +164,35 @@ def run_phases(n=16384):
     json.dump(res, open(os.path.join(OUT, f"grad_phase_sensitivity_N{n}.json"), "w"), indent=1)
 
 
+def run_predict(n=32768):
+    """Which predict-solve variant is accurate on a DENSE data set (SE 2-D, the config-5 model: sigma^2 cancels hard)?
+    mu / sigma at 4096 points vs the oracle for: the default dispatch, both diagonal-block variants, the full-width
+    recursion, and the DMMA path."""
+    d = 2
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 1, (n, d))
+    y = np.sin(3 * x).sum(axis=1) + rng.normal(0, 0.05, n)
+    e = np.full(n, 0.05)
+    theta = np.array([0.2, 0.1] + [np.log(0.3)] * d)
+    q = np.random.default_rng(6).uniform(0, 1, (4096, d))
+    t0 = time.perf_counter()
+    fit = orc.Fit(x, y, ("SE",), "const", theta, e**2)
+    mu_o, sig_o = fit.predict(q)
+    res = {"what": f"SE d=2 N={n}: predict variants vs oracle (mu max-norm relative, sigma elementwise relative)",
+           "oracle_seconds": time.perf_counter() - t0, "sigma_over_amp_min": float(sig_o.min() / np.exp(theta[1])), "cases": {}}
+    m = gp.GpRegressor(x, y, y_err=e, hyperpars=theta)
+    for name, opts in (("default", {}), ("diag_recursion", {"predict_diag": 1}), ("diag_int8_inverse", {"predict_diag": 2}),
+                       ("full_recursion", {"predict_block": -1}), ("dmma", {"gemm_i8": 0})):
+        with _lib.options(**opts):
+            m.set_hyperparameters(theta)
+            mu, sig = m(np.tile(q, (8, 1)))          # 32768 rows: the blocked path engages
+            mu, sig = mu[:4096], sig[:4096]
+            res["cases"][name] = {"mu": rel(mu, mu_o), "sigma": float(np.abs(sig / sig_o - 1).max()), "alpha": rel(m.alpha, fit.alpha),
+                                  "block": m.engine.stat("predict_block"), "trsm_ms": m.engine.timers().get("trsm")}
+        print(name, json.dumps(res["cases"][name]), flush=True)
+    json.dump(res, open(os.path.join(OUT, f"predict_variants_N{n}.json"), "w"), indent=1)
+
+
 def run_cfg1():
     """BASELINE config 1 shape: SE 1-D, N=200, predict at 1000 points; latency of the hot calls (the reference needs
     12.9 ms per marginal_likelihood_gradient on the survey host)."""
@@ -200,5 +229,7 @@ if __name__ == "__main__":
         run_cond(int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
     elif what == "cfg1":
         run_cfg1()
+    elif what == "predict":
+        run_predict(int(sys.argv[2]) if len(sys.argv) > 2 else 32768)
     elif what == "phases":
         run_phases(int(sys.argv[2]) if len(sys.argv) > 2 else 16384)
