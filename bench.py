@@ -180,7 +180,7 @@ def dist_cholesky_block(args, rank, world, local, gp_engine, barrier, max_over_r
     import torch.distributed as dist
     from inference_tools_b200 import _lib
     gp_engine.close()                      # release the headline workload's HBM before the 64 GiB factor
-    d, block = 2, int(os.environ.get("GPB_BENCH_DIST_BLOCK", 1024))
+    d, block = 2, int(os.environ.get("GPB_BENCH_DIST_BLOCK", 2048))
     rng = np.random.default_rng(5)
     x = rng.uniform(0, 1, (n, d))
     y = np.sin(3 * x).sum(axis=1) + rng.normal(0, 0.05, n)

@@ -60,7 +60,9 @@ double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-cor
  *   "i8_fallback"    repeat a factorisation on DMMA when the INT8 path reports a non-PD pivot (1)
  *   "predict_block"  block width of the left-looking predict solve against cached digit planes (0 = auto, -1 = the
  *                    full-width recursion)
- *   "predict_diag"   its diagonal blocks: 0 = by conditioning, 1 = recursion with FP64 leaf inverses, 2 = INT8 inverse
+ *   "predict_diag"   its diagonal blocks: 1 = recursion with FP64 leaf inverses (default), 2 = one INT8 product with the
+ *                    block's explicit inverse (9 % faster solve, sigma up to 4x above the FP64 floor on dense data),
+ *                    0 = the latter only for well-conditioned fits (amp / min L_ii <~ 30)
  *   "gemm_i8_max_k"  longest k extent of one INT8 launch (16384 = the int32 exactness limit); longer extents are chunked
  *   "gemm_i8_epi"    epilogue warps of the INT8 kernel (0 = by k extent, 8, 16)      "i8_grad_phases"  diagnostic mask
  *   "i8_grad_guard"  a-posteriori error estimate of the INT8 inverse chain in gpb_lml_grad, DMMA repeat when it is too

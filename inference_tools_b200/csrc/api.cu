@@ -845,11 +845,13 @@ int64_t chunk_rows(const gpb_ctx* c) {
 // block, split once per fit.  The entries of inv(L_jj) grow like w = 1 / min L_ii, the digit-split product is accurate
 // only normwise (relative to the row maxima), and sigma^2 = k(q,q) - |v|^2 cancels down to ~ k(q,q) / w^2 at the training
 // points, so the relative error of sigma^2 is about 2^-56 sqrt(nb) w^3 (w in units of the prior sigma): measured on the
-// conditioning sweep this variant lost a factor 5 (w = 10) to 1e5 (w = 1e4) against the FP64 path in sigma.  It is
-// used only while PREDICT_W_C w^3 <= PREDICT_W_TOL (w <~ 30: the benchmark's fit has w = 16).  (robust) otherwise: the
-// recursive solve inside the block, which multiplies by inverted 128-blocks on the FP64 tensor pipe and uses the INT8
-// path only for its benign X L21^T updates; it matches the FP64 path over the whole sweep
-// (profiles/conditioning_sweep_r2.md) and costs ~9 % more time in the solve.
+// conditioning sweep this variant lost a factor 5 (w = 10) to 1e5 (w = 1e4) against the FP64 path in sigma, and on a
+// dense data set (SE 2-D, N = 32768, sigma^2 / k(q,q) down to 2e-6) a factor 4 even at w = 22
+// (profiles/predict_variants_N32768_r2.json).  It is therefore NOT the default; option "predict_diag" = 2 selects it,
+// = 0 selects it only while PREDICT_W_C w^3 <= PREDICT_W_TOL (w <~ 30).  (robust, default) the recursive solve inside the
+// block, which multiplies by inverted 128-blocks on the FP64 tensor pipe and uses the INT8 path only for its benign
+// X L21^T updates; it matches the FP64 path over the whole sweep (profiles/conditioning_sweep_r2.md) and costs ~9 % more
+// time in the solve.
 // Replaces the full-width recursion, which re-split L for every chunk and level (round-1 profile: 1108 split launches
 // per step, 6.6 % of the GPU time) and ran 98 % of its flops at k <= N/2 GEMMs of decreasing size.
 constexpr double X_BOUND_HEADROOM = 1.0 + 1e-6;

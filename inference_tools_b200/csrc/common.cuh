@@ -93,7 +93,7 @@ enum Option : int {
     OPT_GRAPHS,           // CUDA-graph replay of pointer/shape-only launch sequences (default 1)
     OPT_I8_FALLBACK,      // re-run a factorisation on the DMMA kernels when the INT8 path reports a non-PD pivot (default 1)
     OPT_PREDICT_BLOCK,    // block width of the left-looking predict solve against cached digit planes (0 = auto, -1 = recursion)
-    OPT_PREDICT_DIAG,     // diagonal blocks of the blocked predict solve: 0 = by conditioning, 1 = recursion (robust), 2 = INT8 inverse
+    OPT_PREDICT_DIAG,     // diagonal blocks of the blocked predict solve: 1 = recursion (robust, default), 2 = INT8 inverse, 0 = by conditioning
     OPT_I8_GRAD_GUARD,    // a-posteriori error estimate of the INT8 inverse chain in marginal_likelihood_gradient (default 1)
     OPT_GEMM_I8_MAX_K,    // longest k extent of one INT8 launch (<= 16384, the int32 exactness limit); longer ones are chunked,
                           // each chunk with its own row scales, and accumulated in FP64

@@ -42,7 +42,7 @@ struct OptionTable {
         v[OPT_GRAPHS] = getenv("GPB200_NO_GRAPHS") ? 0 : 1;
         v[OPT_I8_FALLBACK] = env("GPB200_I8_FALLBACK", 1);
         v[OPT_PREDICT_BLOCK] = env("GPB200_PREDICT_BLOCK", 0);
-        v[OPT_PREDICT_DIAG] = env("GPB200_PREDICT_DIAG", 0);
+        v[OPT_PREDICT_DIAG] = env("GPB200_PREDICT_DIAG", 1);
         v[OPT_I8_GRAD_GUARD] = env("GPB200_I8_GRAD_GUARD", 1);
         v[OPT_GEMM_I8_MAX_K] = env("GPB200_GEMM_I8_MAX_K", 16384);
         v[OPT_GEMM_I8_EPI] = env("GPB200_GEMM_I8_EPI", 0);

@@ -105,7 +105,7 @@ def test_blocked_predict_solve_on_cached_planes_matches_recursion_and_oracle():
     q = np.random.default_rng(2).uniform(-0.05, 1.05, (mq, d))
     mu_b, sig_b = m(q)
     assert "planes" in m.engine.timers()                     # the blocked path built its planes
-    with _lib.options(predict_diag=1):                       # the other diagonal-block variant gives the same answer
+    with _lib.options(predict_diag=2):                       # the other diagonal-block variant gives the same answer
         mu_v, sig_v = m(q)
     assert rel_err(mu_v, mu_b) < 1e-12 and np.abs(sig_v / sig_b - 1).max() < 1e-10
     dm_b, dv_b = m.spatial_derivatives(q[:12000])

@@ -9,7 +9,14 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import inference_tools_b200.gp as gp
 from inference_tools_b200.sharding import round_robin, shard_range
-from oracle.cpu_reference import synth
+
+
+def synth(seed, n, d, sigma_n=0.05):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (n, d))
+    y = np.sin(3 * x).sum(axis=1) + rng.normal(0, sigma_n, n)
+    return x, y, np.full(n, sigma_n)
+
 from scipy.optimize import fmin_l_bfgs_b
 
 ap = argparse.ArgumentParser()

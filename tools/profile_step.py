@@ -4,7 +4,14 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from inference_tools_b200 import _lib
-from oracle.cpu_reference import synth
+
+
+def synth(seed, n, d, sigma_n=0.05):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (n, d))
+    y = np.sin(3 * x).sum(axis=1) + rng.normal(0, sigma_n, n)
+    return x, y, np.full(n, sigma_n)
+
 n, m = int(sys.argv[1]), int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 d = 5
