@@ -54,7 +54,9 @@ double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-cor
 /* Runtime options, process-wide (initial values come from the GPB200_* environment variables):
  *   "gemm_i8"        0 = every FP64 GEMM on the FP64 tensor pipe (DMMA), 1 = INT8 tensor-core digit-split GEMM where
  *                    it pays (k >= gemm_i8_min_k and >= 148 tiles; default), 2 = wherever it applies
- *   "gemm_i8_min_k"  shortest k extent sent to the INT8 path (512)      "gemm_i8_pair"  CTA-pair tiles (1)
+ *   "gemm_i8_min_k"  shortest k extent sent to the INT8 path (512)
+ *   "gemm_i8_pair"   INT8 kernel tiles: 0 = single CTA, 1 = CTA pairs with uniform shared-memory slots (default), 2 = CTA
+ *                    pairs with 3 A slots + 2 half-size B slots (measured equal)
  *   "gemm_tile", "gemm_tma", "gemm_i8_debug"  kernel-selection / probe switches of the GEMM dispatcher
  *   "graphs"         CUDA-graph replay of launch sequences (1)
  *   "i8_fallback"    repeat a factorisation on DMMA when the INT8 path reports a non-PD pivot (1)
@@ -64,6 +66,7 @@ double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-cor
  *                    block's explicit inverse (9 % faster solve, sigma up to 4x above the FP64 floor on dense data),
  *                    0 = the latter only for well-conditioned fits (amp / min L_ii <~ 30)
  *   "gemm_i8_max_k"  longest k extent of one INT8 launch (16384 = the int32 exactness limit); longer extents are chunked
+ *   "gemm_i8_prefetch"  INT8 kernel: k-blocks by which an L2 prefetch of the digit planes runs ahead of the loads (0 = off)
  *   "gemm_i8_epi"    epilogue warps of the INT8 kernel (0 = by k extent, 8, 16)      "i8_grad_phases"  diagnostic mask
  *   "i8_grad_guard"  a-posteriori error estimate of the INT8 inverse chain in gpb_lml_grad, DMMA repeat when it is too
  *                    large relative to the gradient (1)
@@ -154,6 +157,11 @@ int gpb_acquisition(gpb_ctx* ctx, int kind, double param, const double* q, int64
  *   gpb_dist_factor   set_hyperparameters (regression.py:218-244): assemble own columns, right-looking blocked Cholesky
  *                     with one-panel look-ahead; L stays sharded, v = L^-1 (y - mu) ends up on every rank
  *   gpb_dist_lml      marginal_likelihood (regression.py:528-542) = gpb_dist_factor + -1/2 v.v - sum log L_ii
+ *   gpb_dist_lml_grad marginal_likelihood_gradient (regression.py:544-567) = gpb_dist_factor + alpha + the rows of K^-1 this
+ *                     rank owns (identity rows solved against the streamed panels, then Y_a Y_b^T products with the
+ *                     streamed row blocks) + this rank's share of the traces + one all-reduce of the n_mean + n_cov
+ *                     gradient entries; grad on every rank; seconds_out4 = assemble, factor sweep, their sum, gradient part.
+ *                     No ChangePoint kernels, no dense y_cov.
  *   gpb_dist_alpha    alpha = L^-T v (regression.py:242-244), block back-substitution; alpha_out (n doubles, host) on
  *                     every rank
  *   gpb_dist_predict  __call__ (regression.py:188-216): each rank passes ITS OWN slab of query points (m may differ,
@@ -162,6 +170,7 @@ int gpb_dist_unique_id(char* out128);
 int gpb_dist_init(gpb_ctx* ctx, int rank, int world, const char* id128);
 int gpb_dist_factor(gpb_ctx* ctx, const double* theta, int block, int* info, double* seconds_out3);
 int gpb_dist_lml(gpb_ctx* ctx, const double* theta, int block, double* lml, int* info, double* seconds_out3);
+int gpb_dist_lml_grad(gpb_ctx* ctx, const double* theta, int block, double* lml, double* grad, int* info, double* seconds_out4);
 int gpb_dist_alpha(gpb_ctx* ctx, double* alpha_out);
 int gpb_dist_predict(gpb_ctx* ctx, const double* q, int64_t m, double* mu, double* sig);
 int gpb_dist_finalize(gpb_ctx* ctx);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "gpb_dist_init": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_char_p]),
     "gpb_dist_factor": (C.c_int, [_ctx_p, _dp, C.c_int, _ip, _dp]),
     "gpb_dist_lml": (C.c_int, [_ctx_p, _dp, C.c_int, _dp, _ip, _dp]),
+    "gpb_dist_lml_grad": (C.c_int, [_ctx_p, _dp, C.c_int, _dp, _dp, _ip, _dp]),
     "gpb_dist_alpha": (C.c_int, [_ctx_p, _dp]),
     "gpb_dist_predict": (C.c_int, [_ctx_p, _dp, C.c_int64, _dp, _dp]),
     "gpb_dist_finalize": (C.c_int, [_ctx_p]),
@@ -373,6 +374,15 @@ class Engine:
         secs = (C.c_double * 3)()
         self._check(self.lib.gpb_dist_factor(self._ctx, _ptr(th), block, C.byref(info), secs))
         return info.value, {"assemble_s": secs[0], "factor_s": secs[1], "total_s": secs[2]}
+
+    def dist_lml_grad(self, theta, block: int = 1024):
+        """collective: log marginal likelihood and its gradient on the block-column-cyclic layout"""
+        th = _f64(theta)
+        val, info = C.c_double(0), C.c_int(0)
+        grad = np.zeros(self.n_mean + self.n_cov)
+        secs = (C.c_double * 4)()
+        self._check(self.lib.gpb_dist_lml_grad(self._ctx, _ptr(th), block, C.byref(val), _ptr(grad), C.byref(info), secs))
+        return val.value, grad, info.value, {"assemble_s": secs[0], "factor_s": secs[1], "total_s": secs[2], "gradient_s": secs[3]}
 
     def dist_alpha(self):
         out = np.empty(self.n)

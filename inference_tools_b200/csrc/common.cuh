@@ -86,7 +86,7 @@ double thread_gemm_flops_i8();
 enum Option : int {
     OPT_GEMM_I8 = 0,      // 0 = FP64 DMMA kernels only, 1 = INT8 tensor-core path where it pays (default), 2 = wherever it applies
     OPT_GEMM_I8_MIN_K,    // shortest k extent sent to the INT8 path (default 512)
-    OPT_GEMM_I8_PAIR,     // CTA-pair (cta_group::2) tiles on the INT8 path (default 1)
+    OPT_GEMM_I8_PAIR,     // INT8 path tiles: 0 single CTA, 1 CTA pairs (cta_group::2) with uniform slots, 2 pairs with the wide slot layout; default 1
     OPT_GEMM_I8_DEBUG,    // timing probes of the INT8 kernel (results meaningless)
     OPT_GEMM_TILE,        // DMMA tile override: 0 auto, 2 small, 3 wide, 6 previous default
     OPT_GEMM_TMA,         // TMA-staged DMMA kernel for k-major operands (default 1)
@@ -99,6 +99,7 @@ enum Option : int {
                           // each chunk with its own row scales, and accumulated in FP64
     OPT_GEMM_I8_EPI,      // epilogue warps per CTA of the INT8 kernel: 16 (default) or 8
     OPT_I8_GRAD_PHASES,   // diagnostic bit mask: which phases of gpb_lml_grad may use the INT8 path (1 potrf, 2 trtri, 4 lauum; default 7)
+    OPT_GEMM_I8_PREFETCH, // INT8 kernel: k-blocks by which an L2 prefetch of the digit planes runs ahead of the loads (0 = off)
     OPT_COUNT
 };
 int64_t option(Option o);

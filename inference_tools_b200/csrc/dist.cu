@@ -139,6 +139,14 @@ __global__ void __launch_bounds__(256) bwd_update_kernel(const double* __restric
     if (half == 0) out[col] += part[0][threadIdx.x] + part[1][threadIdx.x];
 }
 
+// Y[idx * nbd + i][a * nbd + i] = 1 for the owned row blocks a = me + G idx: the rows of the identity this rank
+// carries through the streamed forward solve (inverse rows for the gradient)
+__global__ void unit_rows_kernel(double* __restrict__ Y, int64_t ld, int nbd, int me, int G, int64_t npad) {
+    const int idx = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t col = (int64_t)(me + G * idx) * nbd + i;
+    if (i < nbd && col < npad) Y[((int64_t)idx * nbd + i) * ld + col] = 1.0;
+}
+
 // rhs[c] = v[c] - acc[c]
 __global__ void sub_kernel(const double* __restrict__ v, const double* __restrict__ acc, double* __restrict__ rhs, int n) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,6 +176,10 @@ struct gpb_dist {
            *v_full = nullptr, *alpha_full = nullptr, *bacc = nullptr, *bvec = nullptr, *pscale = nullptr;
     size_t panels_cap = 0, pbuf_cap = 0, tmp_cap = 0, acc_cap = 0, resid_cap = 0, winv_cap = 0, v_cap = 0, alpha_cap = 0,
            bacc_cap = 0, bvec_cap = 0, pscale_cap = 0, pplanes_cap = 0;
+    // gradient workspace: rows of L^-T (then of Kinv, left of the diagonal block) for the owned row blocks, stacked;
+    // the diagonal blocks of Kinv; per-tile partial sums; this rank's share of the gradient
+    double *ystack = nullptr, *kdiag = nullptr, *gpart = nullptr, *ggrad = nullptr;
+    size_t ystack_cap = 0, kdiag_cap = 0, gpart_cap = 0, ggrad_cap = 0;
     signed char* pplanes = nullptr;  // digit planes of the two broadcast buffers (split once per step, used by every update)
     int64_t tmp_rows = 0;
     bool have_alpha = false;
@@ -197,7 +209,7 @@ void dist_destroy(gpb_ctx* c) {
     gpb_dist* d = c->dist;
     if (!d) return;
     for (double* p : {d->panels, d->pbuf, d->tmp, d->acc, d->resid, d->winv, d->v_full, d->alpha_full, d->bacc, d->bvec,
-                      d->pscale, reinterpret_cast<double*>(d->pplanes)})
+                      d->pscale, d->ystack, d->kdiag, d->gpart, d->ggrad, reinterpret_cast<double*>(d->pplanes)})
         if (p) cudaFree(p);
     if (d->info) cudaFree(d->info);
     for (auto e : d->events) cudaEventDestroy(e);
@@ -483,6 +495,185 @@ int check_dist(gpb_ctx* c, const char* who, bool need_factor) {
     return 0;
 }
 
+// alpha = L^-T v on every rank (device: d->alpha_full, npad entries); computed once per factorisation
+int dist_alpha_impl(gpb_ctx* c) {
+    gpb_dist* d = c->dist;
+    const int nbd = d->nbd, nblk = d->nblk, me = d->rank;
+    const int64_t npad = d->npad;
+    cudaStream_t s = c->s;
+    GPB_TRY(ensure(d->alpha_full, d->alpha_cap, sizeof(double) * (size_t)npad));
+    GPB_TRY(ensure(d->bacc, d->bacc_cap, sizeof(double) * (size_t)npad));
+    GPB_TRY(ensure(d->bvec, d->bvec_cap, sizeof(double) * 2 * (size_t)nbd));
+    if (d->have_alpha) return 0;
+    GPB_CUDA(cudaMemsetAsync(d->bacc, 0, sizeof(double) * (size_t)npad, s));
+    for (int i = nblk - 1; i >= 0; --i) {
+        const int ci = d->cols_of(i);
+        double* ai = d->alpha_full + (size_t)i * nbd;
+        if (d->owner(i) == me) {
+            sub_kernel<<<(ci + 255) / 256, 256, 0, s>>>(d->v_full + (size_t)i * nbd, d->bacc + (size_t)i * nbd, d->bvec, ci);
+            GPB_CUDA(cudaGetLastError());
+            count_launch();
+            GPB_TRY(trsv_lower_bwd(d->panel(i), nbd, ci, d->dinv_of(i), d->bvec, s));
+            GPB_CUDA(cudaMemcpyAsync(ai, d->bvec + ci, sizeof(double) * ci, cudaMemcpyDeviceToDevice, s));
+        }
+        GPB_TRY(bcast(d, ai, ai, ci, d->owner(i), s));
+        for (int j = me; j < i; j += d->world) {  // owned block columns left of i
+            const double* Lij = d->panel(j) + (size_t)((int64_t)(i - j) * nbd) * nbd;
+            bwd_update_kernel<<<d->cols_of(j) / NB, 256, 0, s>>>(Lij, nbd, ci, ai, d->bacc + (size_t)j * nbd);
+            GPB_CUDA(cudaGetLastError());
+            count_launch();
+        }
+    }
+    d->have_alpha = true;
+    return 0;
+}
+
+// Rows of K^-1 for the gradient traces (the reference forms the whole inverse on one host: regression.py:556-557).
+// Rank `me` owns the row blocks a = me + G idx (the same cyclic rule as the column panels), stacked in d->ystack.
+//   Phase 1  Y = E L^-T for the owned rows E of the identity: the column panels of L are streamed through all ranks as in
+//            gpb_dist_predict (one broadcast per panel, double-buffered); row block a of Y is (columns a of L^-1)^T and is
+//            zero left of column a nbd, so step j only touches the row blocks a <= j.
+//   Phase 2  K^-1[a, b] = Y_a Y_b^T for b <= a (k runs over the columns >= a nbd): the owner of row block b broadcasts it,
+//            packed from its first non-zero column, and every rank multiplies its row blocks a >= b with it.  K^-1[a, b] for
+//            b < a is written over the zero part of Y's row block a (column block b -- never read again as an operand),
+//            the diagonal blocks go to d->kdiag.  The products run in k-chunks with their own row scales on the INT8 path
+//            for the reason given at lauum_lower (potrf.cu).
+// Flops: N^3 / 3 (phase 1) + ~2 N^3 / 3 (phase 2: the stacked row blocks share one k range) over all ranks;
+// NVLink: 2 x N^2 / 2 x 8 bytes received per rank.
+int dist_inverse_rows(gpb_ctx* c, int* na_out) {
+    gpb_dist* d = c->dist;
+    const int G = d->world, me = d->rank, nbd = d->nbd, nblk = d->nblk, npad = (int)d->npad;
+    const int na = nblk > me ? (nblk - 1 - me) / G + 1 : 0;
+    *na_out = na;
+    const int64_t stack_rows = (int64_t)na * nbd;
+    cudaStream_t s = c->s, s_comm = d->s_comm;
+    GPB_TRY(ensure(d->ystack, d->ystack_cap, sizeof(double) * (size_t)std::max<int64_t>(stack_rows, 1) * npad));
+    GPB_TRY(ensure(d->kdiag, d->kdiag_cap, sizeof(double) * (size_t)std::max(na, 1) * nbd * nbd));
+    if (stack_rows > d->tmp_rows) {
+        d->tmp_rows = stack_rows;
+        GPB_TRY(ensure(d->tmp, d->tmp_cap, sizeof(double) * (size_t)d->tmp_rows * NB));
+    }
+    auto yrow = [&](int idx) { return d->ystack + (size_t)idx * nbd * npad; };
+    if (na > 0) {
+        GPB_CUDA(cudaMemsetAsync(d->ystack, 0, sizeof(double) * (size_t)stack_rows * npad, s));
+        GPB_CUDA(cudaMemsetAsync(d->kdiag, 0, sizeof(double) * (size_t)na * nbd * nbd, s));
+        unit_rows_kernel<<<dim3((nbd + 255) / 256, na), 256, 0, s>>>(d->ystack, npad, nbd, me, G, npad);
+        GPB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    const size_t pb_doubles = (size_t)d->rows_aug() * nbd + (size_t)nbd * NB;
+    double* pb[2] = {d->pbuf, d->pbuf + pb_doubles};
+    size_t ev = 0;
+    std::vector<cudaEvent_t> used(2, nullptr);
+    cudaEvent_t ev_ready = d->ev(ev++);
+    GPB_CUDA(cudaEventRecord(ev_ready, s));  // earlier work on s (factor, alpha) is complete before s_comm reads the panels
+    GPB_CUDA(cudaStreamWaitEvent(s_comm, ev_ready, 0));
+    int64_t step = 0;
+    // ---- phase 1: forward solve with the streamed panels
+    for (int j = 0; j < nblk; ++j, ++step) {
+        const int cj = d->cols_of(j), oj = d->owner(j);
+        double* P = pb[step & 1];
+        if (used[step & 1]) GPB_CUDA(cudaStreamWaitEvent(s_comm, used[step & 1], 0));
+        const size_t count = (size_t)d->panel_rows(j) * nbd + (size_t)nbd * NB;  // panel + inverted diagonal blocks
+        if (oj == me && G == 1) {
+            GPB_CUDA(cudaMemcpyAsync(P, d->panel(j), sizeof(double) * count, cudaMemcpyDeviceToDevice, s_comm));
+        } else {
+            GPB_TRY(bcast(d, oj == me ? d->panel(j) : P, P, count, oj, s_comm));
+        }
+        cudaEvent_t eb = d->ev(ev++);
+        GPB_CUDA(cudaEventRecord(eb, s_comm));
+        GPB_CUDA(cudaStreamWaitEvent(s, eb, 0));
+        const int cnt = j >= me ? (j - me) / G + 1 : 0;  // owned row blocks a <= j
+        const int rows_act = cnt * nbd;
+        if (rows_act > 0) {
+            LinalgWs ws{P + (size_t)d->panel_rows(j) * nbd, d->tmp, d->tmp_rows, d->info + nblk};
+            GPB_TRY(trsm_right_lt(d->ystack + (size_t)j * nbd, npad, rows_act, P, nbd, cj, 0, ws, s));
+            const int rest = npad - (int)d->row_end(j);
+            if (rest > 0) {
+                GemmArgs g{rows_act, rest, cj, d->ystack + (size_t)j * nbd, npad, P + (size_t)cj * nbd, nbd,
+                           d->ystack + d->row_end(j), npad, d->ystack + d->row_end(j), npad, nullptr, 0, -1.0, 1.0, GEMM_FULL};
+                GPB_TRY(gemm_nt(g, s));
+            }
+        }
+        cudaEvent_t eu = d->ev(ev++);
+        GPB_CUDA(cudaEventRecord(eu, s));
+        used[step & 1] = eu;
+    }
+    // ---- phase 2: K^-1 blocks from the streamed row blocks of Y
+    cudaEvent_t ev_fwd = d->ev(ev++);
+    GPB_CUDA(cudaEventRecord(ev_fwd, s));
+    GPB_CUDA(cudaStreamWaitEvent(s_comm, ev_fwd, 0));
+    const int chunk = std::min(4096, std::max(1024, (npad / 4) / 64 * 64));
+    for (int b = 0; b < nblk; ++b, ++step) {
+        const int cb = d->cols_of(b), ob = d->owner(b);
+        const int64_t ldb = (int64_t)npad - (int64_t)b * nbd;  // packed row length: columns b nbd .. npad
+        double* P = pb[step & 1];
+        if (used[step & 1]) GPB_CUDA(cudaStreamWaitEvent(s_comm, used[step & 1], 0));
+        if (ob == me)
+            GPB_CUDA(cudaMemcpy2DAsync(P, sizeof(double) * ldb, yrow((b - me) / G) + (size_t)b * nbd, sizeof(double) * npad,
+                                       sizeof(double) * ldb, cb, cudaMemcpyDeviceToDevice, s_comm));
+        GPB_TRY(bcast(d, P, P, (size_t)cb * ldb, ob, s_comm));
+        cudaEvent_t eb = d->ev(ev++);
+        GPB_CUDA(cudaEventRecord(eb, s_comm));
+        GPB_CUDA(cudaStreamWaitEvent(s, eb, 0));
+        int idx = b <= me ? 0 : (b - me + G - 1) / G;  // first owned row block with a >= b
+        if (idx < na && me + G * idx == b) {             // diagonal block (lower tiles): k >= b nbd
+            GemmArgs g{cb, cb, (int)ldb, yrow(idx) + (size_t)b * nbd, npad, P, ldb, nullptr, 0,
+                       d->kdiag + (size_t)idx * nbd * nbd, nbd, nullptr, 0, 1.0, 0.0, GEMM_LOWER};
+            g.max_k = chunk;
+            GPB_TRY(gemm_nt(g, s));
+            ++idx;
+        }
+        if (idx < na) {  // row blocks a > b, stacked: both operands are zero left of column a1 nbd
+            const int64_t k0 = (int64_t)(me + G * idx) * nbd;
+            GemmArgs g{(na - idx) * nbd, cb, (int)(npad - k0), yrow(idx) + k0, npad, P + (k0 - (int64_t)b * nbd), ldb, nullptr, 0,
+                       yrow(idx) + (size_t)b * nbd, npad, nullptr, 0, 1.0, 0.0, GEMM_FULL};
+            g.max_k = chunk;
+            GPB_TRY(gemm_nt(g, s));
+        }
+        cudaEvent_t eu = d->ev(ev++);
+        GPB_CUDA(cudaEventRecord(eu, s));
+        used[step & 1] = eu;
+    }
+    return 0;
+}
+
+// marginal_likelihood_gradient (regression.py:544-567) on the distributed layout: factor, alpha, the owned rows of K^-1,
+// then every rank's share of the traces 1/2 sum (alpha alpha^T - K^-1) o dK_p over its row blocks (lml.cu, stacked
+// variant) and one all-reduce of the p gradient entries.
+int dist_lml_grad_impl(gpb_ctx* c, const double* theta, int block, double* lml, double* grad, int* info_out,
+                       double* seconds_out) {
+    gpb_dist* d = c->dist;
+    if (seconds_out) seconds_out[3] = 0.0;
+    GPB_TRY(dist_factor_impl(c, theta, block, info_out, seconds_out));
+    *lml = d->lml;
+    if (*info_out != 0) return 0;
+    cudaStream_t s = c->s;
+    EventGuard t;
+    GPB_TRY(t.create());
+    GPB_CUDA(cudaEventRecord(t.e[0], s));
+    GPB_TRY(dist_alpha_impl(c));
+    int na = 0;
+    GPB_TRY(dist_inverse_rows(c, &na));
+    const int p = c->n_mean + c->n_cov, npad = (int)d->npad;
+    GPB_TRY(ensure(d->ggrad, d->ggrad_cap, sizeof(double) * (size_t)std::max(p, 1)));
+    GPB_TRY(ensure(d->gpart, d->gpart_cap, std::max<size_t>(trace_partials_size_stacked(na, d->nbd, npad), 16)));
+    GPB_CUDA(cudaMemsetAsync(d->ggrad, 0, sizeof(double) * (size_t)p, s));
+    GPB_TRY(launch_lml_grad_stacked(d->cp, d->mp, c->n_mean, c->x, (int)c->n, npad, d->alpha_full, d->ystack, npad, d->kdiag,
+                                    d->nbd, d->rank, d->world, na, d->rank == 0, d->gpart, d->ggrad, s));
+    if (d->world > 1) GPB_NCCL(g_nccl.AllReduce(d->ggrad, d->ggrad, (size_t)p, ncclDouble, ncclSum, d->comm, s));
+    GPB_CUDA(cudaEventRecord(t.e[1], s));
+    GPB_CUDA(cudaMemcpyAsync(grad, d->ggrad, sizeof(double) * (size_t)p, cudaMemcpyDeviceToHost, s));
+    GPB_CUDA(cudaStreamSynchronize(s));
+    GPB_CUDA(cudaStreamSynchronize(d->s_comm));
+    if (seconds_out) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.e[0], t.e[1]);
+        seconds_out[3] = ms * 1e-3;
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -583,39 +774,34 @@ int gpb_dist_alpha(gpb_ctx* c, double* alpha_out) {
     GPB_TRY(check_dist(c, "gpb_dist_alpha", true));
     gpb_dist* d = c->dist;
     auto body = [&]() -> int {
-        const int nbd = d->nbd, nblk = d->nblk, me = d->rank;
-        const int64_t npad = d->npad;
-        cudaStream_t s = c->s;
-        GPB_TRY(ensure(d->alpha_full, d->alpha_cap, sizeof(double) * (size_t)npad));
-        GPB_TRY(ensure(d->bacc, d->bacc_cap, sizeof(double) * (size_t)npad));
-        GPB_TRY(ensure(d->bvec, d->bvec_cap, sizeof(double) * 2 * (size_t)nbd));
-        if (!d->have_alpha) {
-            GPB_CUDA(cudaMemsetAsync(d->bacc, 0, sizeof(double) * (size_t)npad, s));
-            for (int i = nblk - 1; i >= 0; --i) {
-                const int ci = d->cols_of(i);
-                double* ai = d->alpha_full + (size_t)i * nbd;
-                if (d->owner(i) == me) {
-                    sub_kernel<<<(ci + 255) / 256, 256, 0, s>>>(d->v_full + (size_t)i * nbd, d->bacc + (size_t)i * nbd, d->bvec, ci);
-                    GPB_CUDA(cudaGetLastError());
-                    count_launch();
-                    GPB_TRY(trsv_lower_bwd(d->panel(i), nbd, ci, d->dinv_of(i), d->bvec, s));
-                    GPB_CUDA(cudaMemcpyAsync(ai, d->bvec + ci, sizeof(double) * ci, cudaMemcpyDeviceToDevice, s));
-                }
-                GPB_TRY(bcast(d, ai, ai, ci, d->owner(i), s));
-                for (int j = me; j < i; j += d->world) {  // owned block columns left of i
-                    const double* Lij = d->panel(j) + (size_t)((int64_t)(i - j) * nbd) * nbd;
-                    bwd_update_kernel<<<d->cols_of(j) / NB, 256, 0, s>>>(Lij, nbd, ci, ai, d->bacc + (size_t)j * nbd);
-                    GPB_CUDA(cudaGetLastError());
-                    count_launch();
-                }
-            }
-            d->have_alpha = true;
-        }
-        if (alpha_out) GPB_CUDA(cudaMemcpyAsync(alpha_out, d->alpha_full, sizeof(double) * c->n, cudaMemcpyDeviceToHost, s));
-        GPB_CUDA(cudaStreamSynchronize(s));
+        GPB_TRY(dist_alpha_impl(c));
+        if (alpha_out)
+            GPB_CUDA(cudaMemcpyAsync(alpha_out, d->alpha_full, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->s));
+        GPB_CUDA(cudaStreamSynchronize(c->s));
         return 0;
     };
     return dist_fail(d, body());
+}
+
+// Distributed marginal_likelihood_gradient(theta) (regression.py:544-567).  COLLECTIVE.  grad receives the
+// n_mean + n_cov entries on every rank; seconds_out[0..3] = assemble, factor sweep, their sum, alpha + inverse rows +
+// traces (device time on this rank).  The factorisation stays valid for gpb_dist_alpha / gpb_dist_predict.
+int gpb_dist_lml_grad(gpb_ctx* c, const double* theta, int block, double* lml, double* grad, int* info_out,
+                      double* seconds_out) {
+    GPB_TRY(check_dist(c, "gpb_dist_lml_grad", false));
+    if (c->has_ycov) {
+        set_error("gpb_dist_lml_grad: dense y_cov is not supported on the distributed path");
+        return -2;
+    }
+    if (c->n_regions > 0) {
+        set_error("gpb_dist_lml_grad: ChangePoint kernels are not supported on the distributed path");
+        return -2;
+    }
+    if (block < NB || block % NB) {
+        set_error("gpb_dist_lml_grad: block must be a positive multiple of 128");
+        return -2;
+    }
+    return dist_fail(c->dist, dist_lml_grad_impl(c, theta, block, lml, grad, info_out, seconds_out));
 }
 
 // GpRegressor.__call__ (regression.py:188-216) against the distributed factor.  COLLECTIVE: every rank calls it with its

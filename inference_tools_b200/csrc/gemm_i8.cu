@@ -43,15 +43,25 @@ constexpr int S_HI = 3;                       // second sweep: diagonals 0..2 ne
 constexpr int BM = 128, BN = 128, KB = I8_KB;  // tile of D; k-block in int8 elements (= bytes, one swizzle row)
 constexpr int A_PLANE = BM * KB, B_PLANE = BN * KB;       // 8192, 8192
 constexpr int A_BYTES = S * A_PLANE, B_BYTES = S * B_PLANE;  // 57344, 57344
-// Shared memory is 4 slots of 56 KB, each with a full / empty barrier.  A k-block of the first sweep takes two
-// consecutive slots (7 A planes | 7 B planes); a k-block of the second sweep takes one (3 A planes, 3 B planes at
-// +28 KB), so the short second-sweep stages run four deep.
+// Shared memory is 224 KB of operand slots in two rings, each slot with a full / empty barrier: an A ring of 56 KB slots
+// (7 planes of 128 rows) and a B ring.  A k-block of the first sweep takes one slot of each ring; a k-block of the
+// second sweep takes one slot (3 A planes, 3 B planes at +28 KB).
+//   uniform layout (single-CTA tiles; CTA pairs with option "gemm_i8_pair" = 1): 2 + 2 slots of 56 KB, the second sweep
+//     alternates between the rings (four k-blocks deep);
+//   wide layout (CTA pairs, option "gemm_i8_pair" = 2): a CTA of a pair stages only HALF of the B planes (28 KB), so the same 224 KB hold
+//     3 A slots + 2 B slots of 28 KB.  Measured equal to the uniform layout within 1 % on every shape
+//     (profiles/gemm_i8_load_path_r2.md: the B ring is still two k-blocks deep and sets the pace); kept as an option.
+//     The second sweep (36 KB per k-block) runs in the A ring, three deep.
 constexpr int SLOT_BYTES = A_BYTES;                        // 57344
 constexpr int SLOT_B_OFF = SLOT_BYTES / 2;                 // 28672
 constexpr int HI_BYTES = S_HI * A_PLANE;                   // 24576 per operand in the second sweep
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;                                  // 56 KB slots' worth of shared memory
 constexpr int STAGE_BYTES = SLOT_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers, tmem slot*/;
+constexpr int RING_MAX = 4;                                // most slots per ring (I8_KB = 32 probe build: 4 + 4 slots of 28 KB)
+constexpr int NBS = KB == 64 ? 2 : 4;                      // B ring slots
+constexpr int BAR_FULL_A = 0, BAR_EMPTY_A = RING_MAX, BAR_FULL_B = 2 * RING_MAX, BAR_EMPTY_B = 3 * RING_MAX,
+              BAR_READY = 4 * RING_MAX, BAR_DRAINED = 4 * RING_MAX + 1, BAR_COUNT = 4 * RING_MAX + 2;
+constexpr int SMEM_BYTES = (KB == 64 ? STAGES : 2 * STAGES) * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers, tmem slot*/;
 // warp 0: TMA, warp 1: TMEM alloc + MMA issue, then EPI epilogue warps (EPI / 4 per TMEM lane quarter, 128 * 4 / EPI
 // columns each; template parameter: 16 by default, 8 = the round-1 configuration, option "gemm_i8_epi")
 constexpr int threads_for(int epi) { return 64 + 32 * epi; }
@@ -74,6 +84,7 @@ struct I8Args {
     double* scratch;     // gridDim.x * 128 * 128 doubles: first-sweep partial sums, private to each thread
     int k_off, k_total;  // this launch covers [k_off, k_off + K) of the full k extent (int32 sums stay exact)
     int a_row_off, b_row_off;  // first row of the operands inside their digit-plane buffers (cached planes hold more rows)
+    int prefetch;              // k-blocks by which an L2 prefetch of the planes runs ahead of the shared-memory loads (0 = off)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -112,6 +123,11 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
             "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar & 0xFEFFFFFFu)
             : "memory");
     }
+}
+// the box of `map` at these coordinates towards L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 // shared-memory matrix descriptor: k-major tile of 64-byte rows, 64-byte swizzle (8-row atoms of 512 bytes)
 __device__ __forceinline__ uint64_t smem_desc(unsigned addr) {
@@ -266,7 +282,7 @@ __device__ __forceinline__ void issue_kblock(unsigned tmem_base, unsigned a_base
 // stages its own 128 rows of A and HALF of the B planes, the leader issues M = 256 MMAs that read both halves, and each
 // CTA's TMEM receives its 128 rows of the accumulators: per MMA a CTA reads 6 KB of shared memory instead of 8 KB and
 // fills 25 % less of it, which takes the kernel off the shared-memory bandwidth limit.
-template <int CTAS, int EPI_WARPS>
+template <int CTAS, int EPI_WARPS, bool WIDE>
 __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmA_hi,
@@ -274,9 +290,17 @@ __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(cons
                                                              const int n_tiles) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + STAGES * STAGE_BYTES);
-    // bars[0..STAGES) slot full, [STAGES..2 STAGES) slot empty, then accumulators ready, accumulators drained
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 12);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + (KB == 64 ? STAGES : 2 * STAGES) * STAGE_BYTES);
+    // bars[BAR_FULL_A + i] / [BAR_EMPTY_A + i]: A ring slot i; [BAR_FULL_B + j] / [BAR_EMPTY_B + j]: B ring slot j;
+    // then accumulators ready, accumulators drained
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + BAR_COUNT);
+    static_assert(!WIDE || CTAS == 2, "the wide layout needs the half-size B slots of a CTA pair");
+    constexpr int NA = KB == 64 ? (WIDE ? 3 : 2) : 4;                  // A ring slots
+    constexpr int B_SLOT = WIDE ? SLOT_BYTES / 2 : SLOT_BYTES;         // bytes per B ring slot
+    constexpr bool ALT = !WIDE;  // second sweep alternates between the rings (a B slot holds 56 KB) or stays in the A ring
+    auto a_slot = [&](int u) { return smem_u32(tiles + (u % NA) * SLOT_BYTES); };
+    auto b_slot = [&](int u) { return smem_u32(tiles + NA * SLOT_BYTES + (u % NBS) * B_SLOT); };
+    auto bar_of = [&](int first, int i) { return smem_u32(&bars[first + i]); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned rank = 0;  // CTA within the pair; the leader (0) owns the full / drained barriers and issues the MMAs
@@ -287,10 +311,8 @@ __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(cons
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);  // the leader's arrive.expect_tx
-#pragma unroll
-        for (int i = STAGES; i < 2 * STAGES + 1; ++i) mbar_init(smem_u32(&bars[i]), 1);
-        mbar_init(smem_u32(&bars[2 * STAGES + 1]), CTAS * EPI_WARPS);  // one arrival per epilogue warp of the pair
+        for (int i = 0; i < BAR_DRAINED; ++i) mbar_init(smem_u32(&bars[i]), 1);  // full: the leader's arrive.expect_tx; empty / ready: one commit
+        mbar_init(smem_u32(&bars[BAR_DRAINED]), CTAS * EPI_WARPS);  // one arrival per epilogue warp of the pair
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (CTAS == 2) cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
@@ -313,10 +335,10 @@ __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(cons
     const unsigned tmem_base = *tmem_slot;
 
     if (warp == 0) {  // ---- TMA producer (both CTAs of a pair): converged warp, one elected lane issues
-        int it = 0;  // slots handed out so far
-        auto acquire = [&](int i) {  // wait until the MMAs that read slot use i - STAGES have completed
-            if (i >= STAGES) mbar_wait(smem_u32(&bars[STAGES + i % STAGES]), ((i / STAGES) - 1) & 1);
-        };
+        int ia = 0, ib = 0;  // slots of the A ring / B ring handed out so far
+        // wait until the MMAs that read the slot's previous contents have completed
+        auto acquire_a = [&](int u) { if (u >= NA) mbar_wait(bar_of(BAR_EMPTY_A, u % NA), ((u / NA) - 1) & 1); };
+        auto acquire_b = [&](int u) { if (u >= NBS) mbar_wait(bar_of(BAR_EMPTY_B, u % NBS), ((u / NBS) - 1) & 1); };
         // The leader announces the bytes of the whole pair on its barrier; the other CTA's TMA is credited to the same
         // barrier and needs no arrival of its own (a remote mbarrier.arrive costs more than the load it would announce).
         // Early bytes are harmless: the phase cannot complete before the leader's arrival, and the other CTA cannot be a
@@ -327,47 +349,61 @@ __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(cons
         for (int t = unit; t < n_tiles; t += n_units) {
             const TileRange tr = tile_range<CTAS>(p, t);
             const int arow = p.a_row_off + tr.row0 + (int)rank * BM, brow = p.b_row_off + tr.col0 + (int)rank * B_ROWS;
-            for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: A planes -> slot it, B planes -> slot it + 1
-                acquire(it);
-                acquire(it + 1);
+            for (int kb = 0; kb < tr.nkb; ++kb, ++ia, ++ib) {  // first sweep: B planes -> B ring, A planes -> A ring
+                acquire_b(ib);
+                acquire_a(ia);
                 if (elect_one()) {
                     const int k = tr.k_begin + kb * KB;
-                    const unsigned bar_a = smem_u32(&bars[it % STAGES]), bar_b = smem_u32(&bars[(it + 1) % STAGES]);
-                    if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {  // timing probe: MMA rate without the loads
+                    const unsigned bar_a = bar_of(BAR_FULL_A, ia % NA), bar_b = bar_of(BAR_FULL_B, ib % NBS);
+                    if ((p.flags & DEBUG_NO_LOAD) && ia >= NA && ib >= NBS) {  // timing probe: MMA rate without the loads
                         if (rank == 0) { mbar_arrive(bar_a); mbar_arrive(bar_b); }
-                    } else {
-                        announce(bar_a, A_BYTES);
-                        tma_load_3d<CTAS>(smem_u32(tiles + (it % STAGES) * SLOT_BYTES), &tmA, k, arow, 0, bar_a);
+                    } else {  // the smaller box first: it is the one with the shorter deadline in the wide layout
                         announce(bar_b, B_BYTES_CTA);
-                        tma_load_3d<CTAS>(smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), &tmB, k, brow, 0, bar_b);
+                        tma_load_3d<CTAS>(b_slot(ib), &tmB, k, brow, 0, bar_b);
+                        announce(bar_a, A_BYTES);
+                        tma_load_3d<CTAS>(a_slot(ia), &tmA, k, arow, 0, bar_a);
+                        // The loads complete at the latency of their slowest sector: the CTA that leads its row / column
+                        // block through k takes every L2 miss.  An L2 prefetch a few k-blocks ahead (no shared memory
+                        // needed) turns those into hits.
+                        if (p.prefetch > 0 && kb + p.prefetch < tr.nkb) {
+                            tma_prefetch_3d(&tmB, k + p.prefetch * KB, brow, 0);
+                            tma_prefetch_3d(&tmA, k + p.prefetch * KB, arow, 0);
+                        }
                     }
                 }
                 __syncwarp();
             }
-            for (int kb = 0; kb < tr.nkb; ++kb, ++it) {  // second sweep: one slot per k-block
-                acquire(it);
+            for (int kb = 0; kb < tr.nkb; ++kb) {  // second sweep: one slot per k-block
+                const bool in_b = ALT && (kb & 1);
+                if (in_b) acquire_b(ib); else acquire_a(ia);
                 if (elect_one()) {
                     const int k = tr.k_begin + kb * KB;
-                    const unsigned bar = smem_u32(&bars[it % STAGES]);
-                    if ((p.flags & DEBUG_NO_LOAD) && it >= STAGES) {
+                    const unsigned bar = in_b ? bar_of(BAR_FULL_B, ib % NBS) : bar_of(BAR_FULL_A, ia % NA);
+                    if ((p.flags & DEBUG_NO_LOAD) && ia >= NA && ib >= NBS) {
                         if (rank == 0) mbar_arrive(bar);
                     } else {
-                        const unsigned dst = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
+                        const unsigned dst = in_b ? b_slot(ib) : a_slot(ia);
                         announce(bar, HI_BYTES + HI_B_BYTES);
                         tma_load_3d<CTAS>(dst, &tmA_hi, k, arow, 0, bar);
                         tma_load_3d<CTAS>(dst + SLOT_B_OFF, &tmB_hi, k, brow, 0, bar);
+                        if (p.prefetch > 0 && kb + 2 * p.prefetch < tr.nkb) {  // these k-blocks are shorter: twice as far ahead
+                            tma_prefetch_3d(&tmB_hi, k + 2 * p.prefetch * KB, brow, 0);
+                            tma_prefetch_3d(&tmA_hi, k + 2 * p.prefetch * KB, arow, 0);
+                        }
                     }
                 }
                 __syncwarp();
+                if (in_b) ++ib; else ++ia;
             }
         }
     } else if (warp == 1) {  // ---- MMA issuer (leader CTA): the whole warp walks the pipeline, one elected lane issues
         if (rank == 0) {
-            int it = 0, uses = 0;
-            auto filled = [&](int i) { mbar_wait(smem_u32(&bars[i % STAGES]), (i / STAGES) & 1); };
+            int ia = 0, ib = 0, uses = 0;
+            auto filled_a = [&](int u) { mbar_wait(bar_of(BAR_FULL_A, u % NA), (u / NA) & 1); };
+            auto filled_b = [&](int u) { mbar_wait(bar_of(BAR_FULL_B, u % NBS), (u / NBS) & 1); };
             auto drained = [&]() {  // the epilogue warps (of both CTAs) have read the previous sweep's accumulators
                 if (uses >= 1) {
-                    mbar_wait(smem_u32(&bars[2 * STAGES + 1]), (uses - 1) & 1);
+                    mbar_wait(smem_u32(&bars[BAR_DRAINED]), (uses - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
                 ++uses;
@@ -377,47 +413,49 @@ __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(cons
                 mbar_arrive(bar);
                 if (CTAS == 2) mbar_arrive_cluster(bar, 1);
             };
+            const unsigned bar_ready = smem_u32(&bars[BAR_READY]);
             for (int t = unit; t < n_tiles; t += n_units) {
                 const TileRange tr = tile_range<CTAS>(p, t);
                 if (tr.nkb == 0) continue;
                 drained();
-                for (int kb = 0; kb < tr.nkb; ++kb, it += 2) {  // first sweep: diagonals S_HI..6, accumulator g - S_HI
-                    filled(it);
-                    filled(it + 1);
+                for (int kb = 0; kb < tr.nkb; ++kb, ++ia, ++ib) {  // first sweep: diagonals S_HI..6, accumulator g - S_HI
+                    filled_b(ib);
+                    filled_a(ia);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const unsigned bar_a = smem_u32(&bars[STAGES + it % STAGES]), bar_b = smem_u32(&bars[STAGES + (it + 1) % STAGES]);
+                    const unsigned bar_a = bar_of(BAR_EMPTY_A, ia % NA), bar_b = bar_of(BAR_EMPTY_B, ib % NBS);
                     if (elect_one()) {
                         if (no_mma) {
                             release(bar_a);
                             release(bar_b);
-                            if (kb == tr.nkb - 1) release(smem_u32(&bars[2 * STAGES]));
+                            if (kb == tr.nkb - 1) release(bar_ready);
                         } else {
-                            issue_kblock<CTAS, S_HI, S - 1>(tmem_base, smem_u32(tiles + (it % STAGES) * SLOT_BYTES),
-                                                            smem_u32(tiles + ((it + 1) % STAGES) * SLOT_BYTES), kb);
+                            issue_kblock<CTAS, S_HI, S - 1>(tmem_base, a_slot(ia), b_slot(ib), kb);
                             mma_commit<CTAS>(bar_a);  // both slots are free once these MMAs have read them
                             mma_commit<CTAS>(bar_b);
-                            if (kb == tr.nkb - 1) mma_commit<CTAS>(smem_u32(&bars[2 * STAGES]));
+                            if (kb == tr.nkb - 1) mma_commit<CTAS>(bar_ready);
                         }
                     }
                     __syncwarp();
                 }
                 drained();
-                for (int kb = 0; kb < tr.nkb; ++kb, ++it) {  // second sweep: diagonals 0..S_HI-1
-                    filled(it);
+                for (int kb = 0; kb < tr.nkb; ++kb) {  // second sweep: diagonals 0..S_HI-1
+                    const bool in_b = ALT && (kb & 1);
+                    if (in_b) filled_b(ib); else filled_a(ia);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const unsigned bar = smem_u32(&bars[STAGES + it % STAGES]);
+                    const unsigned bar = in_b ? bar_of(BAR_EMPTY_B, ib % NBS) : bar_of(BAR_EMPTY_A, ia % NA);
+                    const unsigned base = in_b ? b_slot(ib) : a_slot(ia);
                     if (elect_one()) {
                         if (no_mma) {
                             release(bar);
-                            if (kb == tr.nkb - 1) release(smem_u32(&bars[2 * STAGES]));
+                            if (kb == tr.nkb - 1) release(bar_ready);
                         } else {
-                            const unsigned base = smem_u32(tiles + (it % STAGES) * SLOT_BYTES);
                             issue_kblock<CTAS, 0, S_HI - 1>(tmem_base, base, base + SLOT_B_OFF, kb);
                             mma_commit<CTAS>(bar);
-                            if (kb == tr.nkb - 1) mma_commit<CTAS>(smem_u32(&bars[2 * STAGES]));
+                            if (kb == tr.nkb - 1) mma_commit<CTAS>(bar_ready);
                         }
                     }
                     __syncwarp();
+                    if (in_b) ++ib; else ++ia;
                 }
             }
         }
@@ -428,7 +466,7 @@ __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(cons
         const unsigned lane_base = (unsigned)(q * 32) << 16;
         double* scr = p.scratch + ((size_t)blockIdx.x * BM + q * 32 + lane) * BN + cbase;
         const double beta = p.beta;
-        const unsigned bar_ready = smem_u32(&bars[2 * STAGES]), bar_drained = smem_u32(&bars[2 * STAGES + 1]);
+        const unsigned bar_ready = smem_u32(&bars[BAR_READY]), bar_drained = smem_u32(&bars[BAR_DRAINED]);
         auto release_tmem = [&]() {  // this warp's accumulator columns are in registers
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
@@ -774,10 +812,12 @@ int get_workspace(cudaStream_t s, Workspace*& w) {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     w = &g_ws[{dev, s}];
     if (w->sm_count == 0) {  // once per (device, stream), under the lock: worker threads share nothing else here
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<1, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<2, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         int sms = 0;
         GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         w->sm_count = sms;
@@ -785,7 +825,8 @@ int get_workspace(cudaStream_t s, Workspace*& w) {
     return 0;
 }
 
-// tile height: CTA pairs (256 x 128 tiles) whenever the rows allow it; option "gemm_i8_pair" = 0 forces single-CTA tiles.
+// tile height: CTA pairs (256 x 128 tiles) whenever the rows allow it; option "gemm_i8_pair" = 0 forces single-CTA tiles,
+// 1 (default) = pairs with the uniform shared-memory layout, 2 = pairs with the wide layout (see SLOT_BYTES above).
 // Measured on B200 at 8192^3: 9.65 ms against 10.44 ms -- the pair reads 6 KB instead of 8 KB of shared memory per
 // MMA; its loads have a longer round trip (credited to the leader's barrier) and now set the pace.
 int ctas_for(int M) { return (option(OPT_GEMM_I8_PAIR) && M % (2 * BM) == 0) ? 2 : 1; }
@@ -815,14 +856,14 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
     }
     const int debug = (int)option(OPT_GEMM_I8_DEBUG);
     I8Args p{M, N, Kc, sa, sb, C, ldc, D, ldd, D2, ldd2, alpha, beta, flags | (debug << 20), tm, tn, w->scratch, k_off, k_total,
-             a_row_off, b_row_off};
+             a_row_off, b_row_off, (int)std::min<int64_t>(64, std::max<int64_t>(0, option(OPT_GEMM_I8_PREFETCH)))};
     // epilogue warps per CTA: 16 pay off on long k extents (+1.4 % on the predict shape), 8 on short ones (+3 % at
     // k = 1024): profiles/i8_epilogue_ab_r2.json.  Option "gemm_i8_epi": 0 = by k extent, 8 or 16 = fixed.
     const int epi_opt = (int)option(OPT_GEMM_I8_EPI);
     const int epi = epi_opt == 8 ? 8 : (epi_opt == 16 ? 16 : (Kc >= 4096 ? 16 : 8));
     if (ctas == 1) {
-        if (epi == 8) gemm_i8_kernel<1, 8><<<grid, threads_for(8), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
-        else gemm_i8_kernel<1, 16><<<grid, threads_for(16), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
+        if (epi == 8) gemm_i8_kernel<1, 8, false><<<grid, threads_for(8), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
+        else gemm_i8_kernel<1, 16, false><<<grid, threads_for(16), SMEM_BYTES, s>>>(tmA, tmB, tmA_hi, tmB_hi, p, (int)tiles);
     } else {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
@@ -837,8 +878,14 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const int nt = (int)tiles;
-        if (epi == 8) GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 8>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
-        else GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 16>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+        const bool wide = option(OPT_GEMM_I8_PAIR) == 2;  // 2: 3 A slots + 2 half-size B slots; 1 (default): uniform slots
+        if (wide) {
+            if (epi == 8) GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 8, true>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+            else GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 16, true>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+        } else {
+            if (epi == 8) GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 8, false>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+            else GPB_CUDA(cudaLaunchKernelEx(&cfg, gemm_i8_kernel<2, 16, false>, tmA, tmB, tmA_hi, tmB_hi, p, nt));
+        }
     }
     GPB_CUDA(cudaGetLastError());
     count_launch();

@@ -84,6 +84,12 @@ int launch_logdet_dot(const double* L, int64_t ld, const double* a, const double
 size_t trace_partials_size(int npad);
 int launch_lml_grad(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad, const double* alpha, const double* Kinv, int64_t ld,
                     double* partials, double* grad_dev, double* fro2_dev, cudaStream_t s);
+// distributed layout (dist.cu): row blocks me + G idx (idx < na, width nbd) of Kinv in a row stack + diagonal blocks;
+// every rank writes its share into grad_dev (zero on entry), the sum over ranks is the gradient
+size_t trace_partials_size_stacked(int na, int nbd, int npad);
+int launch_lml_grad_stacked(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad,
+                            const double* alpha, const double* Kst, int64_t ldst, const double* Kdiag, int nbd, int me, int G,
+                            int na, bool with_mean, double* partials, double* grad_dev, cudaStream_t s);
 
 // ---- loo.cu : leave-one-out objective (regression.py:451-526)
 int launch_symmetrize(double* A, int64_t ld, int n, cudaStream_t s);

@@ -23,18 +23,16 @@ __device__ __forceinline__ void lower_tile(int t, int& bi, int& bj) {
     bj = t - r * (r + 1) / 2;
 }
 
-// one smooth component `c`; partials[tile][NACC]
-__global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, int c, const double* __restrict__ x,
-                                                           int n, const double* __restrict__ alpha,
-                                                           const double* __restrict__ Kinv, int64_t ld,
-                                                           double* __restrict__ partials) {
+// One 128 x 128 tile (global rows row0.., columns col0..) of the trace of smooth component `c`; `kinv_at(i, gj)` returns
+// Kinv at tile row i, global column gj.  out[NACC] receives the tile's partial sums.
+template <class Fetch>
+__device__ __forceinline__ void trace_smooth_tile(const CovParams& cp, int c, const double* __restrict__ x, int n,
+                                                  const double* __restrict__ alpha, int row0, int col0, Fetch kinv_at,
+                                                  double* __restrict__ out) {
     __shared__ double xs[TILE * MAX_DIM];
     __shared__ double as[TILE];
     __shared__ double ws[TILE];   // ChangePoint weight of this leaf's region at the row points
     __shared__ double red[8][NACC];
-    int bi, bj;
-    lower_tile(blockIdx.x, bi, bj);
-    const int row0 = bi * TILE, col0 = bj * TILE;
     const int tid = threadIdx.x, col = tid & (TILE - 1), half = tid >> 7;
     const int d = cp.d;
     for (int idx = tid; idx < TILE * d; idx += 256) xs[idx] = x[(int64_t)row0 * d + idx];
@@ -71,7 +69,7 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
         if (gi < gj || gi >= n || gj >= n) continue;
         const double w = (gi == gj) ? 1.0 : 2.0;  // symmetry: strict lower counted twice
         // dK of a leaf under a ChangePoint carries the region coefficient g_r(x_i) g_r(x_j) (covariance.py:570-572)
-        const double Q = w * (ws[i] * wcol) * (as[i] * aj - Kinv[(int64_t)gi * ld + gj]);
+        const double Q = w * (ws[i] * wcol) * (as[i] * aj - kinv_at(i, gj));
         double s[MAX_DIM];  // 0.5 dx^2 / l^2 per dimension
         double z = 0.0;
 #pragma unroll
@@ -125,8 +123,46 @@ __global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, i
     if (tid < NACC) {
         double v = 0.0;
         for (int w = 0; w < 8; ++w) v += red[w][tid];
-        partials[(int64_t)blockIdx.x * NACC + tid] = v;
+        out[tid] = v;
     }
+}
+
+// one smooth component `c`, dense Kinv (lower tiles); partials[tile][NACC]
+__global__ void __launch_bounds__(256) trace_smooth_kernel(const CovParams cp, int c, const double* __restrict__ x,
+                                                           int n, const double* __restrict__ alpha,
+                                                           const double* __restrict__ Kinv, int64_t ld,
+                                                           double* __restrict__ partials) {
+    int bi, bj;
+    lower_tile(blockIdx.x, bi, bj);
+    const int row0 = bi * TILE, col0 = bj * TILE;
+    const double* base = Kinv + (int64_t)row0 * ld;
+    trace_smooth_tile(cp, c, x, n, alpha, row0, col0,
+                      [=](int i, int gj) { return base[(int64_t)i * ld + gj]; }, partials + (int64_t)blockIdx.x * NACC);
+}
+
+// Distributed layout (dist.cu): this rank holds the row blocks a = me + G * idx (width nbd) of Kinv.  Row i of block a is
+// row idx * nbd + i of the stack `Kst` (leading dimension ldst, column = global column, valid LEFT of the diagonal block);
+// the diagonal blocks are in Kdiag[idx] (nbd x nbd, lower tiles valid).  grid = stack row tiles x column tiles; tiles right
+// of the diagonal block write zero partials.
+__global__ void __launch_bounds__(256) trace_smooth_stacked_kernel(const CovParams cp, int c, const double* __restrict__ x,
+                                                                   int n, const double* __restrict__ alpha,
+                                                                   const double* __restrict__ Kst, int64_t ldst,
+                                                                   const double* __restrict__ Kdiag, int nbd, int me, int G,
+                                                                   int tiles_n, double* __restrict__ partials) {
+    const int ti = blockIdx.x / tiles_n, tj = blockIdx.x - ti * tiles_n;
+    const int per_blk = nbd / TILE, idx = ti / per_blk, a = me + G * idx;
+    const int lrow0 = (ti - idx * per_blk) * TILE;             // first row of the tile inside its row block
+    const int row0 = a * nbd + lrow0, col0 = tj * TILE;
+    double* out = partials + (int64_t)blockIdx.x * NACC;
+    if (col0 > row0) {                                          // uniform per CTA
+        if (threadIdx.x < NACC) out[threadIdx.x] = 0.0;
+        return;
+    }
+    const bool diag = col0 >= a * nbd;  // inside the diagonal block: columns are local to Kdiag[idx]
+    const double* base = diag ? Kdiag + (int64_t)idx * nbd * nbd + (int64_t)lrow0 * nbd - (int64_t)a * nbd
+                              : Kst + ((int64_t)idx * nbd + lrow0) * ldst;
+    const int64_t ldk = diag ? nbd : ldst;
+    trace_smooth_tile(cp, c, x, n, alpha, row0, col0, [=](int i, int gj) { return base[(int64_t)i * ldk + gj]; }, out);
 }
 
 // grad[off + map(p)] = sum over tiles of partials[tile][p]; one CTA per accumulator slot
@@ -326,7 +362,94 @@ __global__ void __launch_bounds__(1024) diag_terms_kernel(const CovParams cp, co
     }
 }
 
+// Distributed variant of diag_terms_kernel: this rank adds the terms of the diagonal entries it owns (Kdiag blocks);
+// the mean-parameter gradients (alpha is replicated) are written by the rank with with_mean != 0 only, so that the sum
+// over ranks is the gradient.  grad must be zero on entry.
+__global__ void __launch_bounds__(1024) diag_terms_stacked_kernel(const CovParams cp, const MeanParams mp, int n_theta_mean,
+                                                                  const double* __restrict__ x, int n,
+                                                                  const double* __restrict__ alpha,
+                                                                  const double* __restrict__ Kdiag, int nbd, int me, int G,
+                                                                  int na, int with_mean, double* __restrict__ grad) {
+    __shared__ double sm[1024];
+    const int tid = threadIdx.x;
+    auto block_sum = [&](double v) -> double {
+        sm[tid] = v;
+        __syncthreads();
+        for (int o = 512; o > 0; o >>= 1) {
+            if (tid < o) sm[tid] += sm[tid + o];
+            __syncthreads();
+        }
+        const double r = sm[0];
+        __syncthreads();
+        return r;
+    };
+    const int d = mp.d;
+    const int n_mean = (mp.kind == MEAN_CONST) ? 1 : (mp.kind == MEAN_LINEAR ? 1 + d : 1 + 2 * d);
+    if (with_mean) {
+        for (int p = 0; p < n_mean; ++p) {
+            double v = 0.0;
+            for (int i = tid; i < n; i += 1024) {
+                double g = 1.0;
+                if (p >= 1) {
+                    const int k = (p - 1) % d;
+                    const double dx = x[(int64_t)i * d + k] - mp.xbar[k];
+                    g = (p <= d) ? dx : dx * dx;
+                }
+                v = fma(alpha[i], g, v);
+            }
+            v = block_sum(v);
+            if (tid == 0) grad[p] = v;
+        }
+    }
+    const int owned = na * nbd;  // stack rows; row r is global point (me + G (r / nbd)) nbd + r % nbd
+    for (int c = 0; c < cp.ncomp; ++c) {
+        if (cp.kind[c] != COV_WHITE && cp.kind[c] != COV_HETERO) continue;
+        double v = 0.0;
+        for (int r = tid; r < owned; r += 1024) {
+            const int idx = r / nbd, l = r - idx * nbd;
+            const int i = (me + G * idx) * nbd + l;
+            if (i >= n) continue;
+            const double qii = alpha[i] * alpha[i] - Kdiag[(int64_t)idx * nbd * nbd + (int64_t)l * nbd + l];
+            if (cp.kind[c] == COV_WHITE) v += qii;
+            else grad[n_theta_mean + cp.theta_off[c] + i] = exp(2.0 * cp.hetero_log_sigma[i]) * qii;
+        }
+        if (cp.kind[c] == COV_WHITE) {
+            v = block_sum(v);
+            if (tid == 0) grad[n_theta_mean + cp.theta_off[c]] = cp.amp2[c] * v;
+        }
+    }
+}
+
 }  // namespace
+
+size_t trace_partials_size_stacked(int na, int nbd, int npad) {
+    return (size_t)na * (nbd / TILE) * (npad / TILE) * NACC * sizeof(double);
+}
+
+int launch_lml_grad_stacked(const CovParams& cp, const MeanParams& mp, int n_theta_mean, const double* x, int n, int npad,
+                            const double* alpha, const double* Kst, int64_t ldst, const double* Kdiag, int nbd, int me, int G,
+                            int na, bool with_mean, double* partials, double* grad_dev, cudaStream_t s) {
+    if (cp.n_regions > 0) {
+        set_error("the distributed gradient does not support ChangePoint kernels");
+        return -2;
+    }
+    const int tiles_n = npad / TILE;
+    const int ntiles = na * (nbd / TILE) * tiles_n;
+    for (int c = 0; c < cp.ncomp && ntiles > 0; ++c) {
+        if (cp.kind[c] > COV_RQ) continue;
+        trace_smooth_stacked_kernel<<<ntiles, 256, 0, s>>>(cp, c, x, n, alpha, Kst, ldst, Kdiag, nbd, me, G, tiles_n, partials);
+        GPB_CUDA(cudaGetLastError());
+        reduce_partials_kernel<<<NACC, 256, 0, s>>>(partials, ntiles, cp.d, cp.kind[c] == COV_RQ,
+                                                    n_theta_mean + cp.theta_off[c], grad_dev, nullptr);
+        GPB_CUDA(cudaGetLastError());
+        count_launch(2);
+    }
+    diag_terms_stacked_kernel<<<1, 1024, 0, s>>>(cp, mp, n_theta_mean, x, n, alpha, Kdiag, nbd, me, G, na, with_mean ? 1 : 0,
+                                                 grad_dev);
+    GPB_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
 
 size_t trace_partials_size(int npad) {
     const int64_t nb = npad / TILE;

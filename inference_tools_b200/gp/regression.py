@@ -48,9 +48,11 @@ class GpRegressor:
         ``(rank, world, nccl_unique_id_bytes)`` when another channel shares the id.  Every rank constructs the
         regressor with the same data; the covariance matrix is then assembled, factored and solved in a
         block-column-cyclic layout over the ranks (NCCL panel broadcasts, ``csrc/dist.cu``).  In this mode
-        ``set_hyperparameters``, ``marginal_likelihood``, ``alpha`` and ``__call__`` are COLLECTIVE calls (every
-        rank makes them in the same order; ``__call__`` takes this rank's own slab of query points);
-        ``hyperpars`` must be given (the distributed path has the likelihood value but not its gradient).
+        ``set_hyperparameters``, ``marginal_likelihood``, ``marginal_likelihood_gradient``, ``alpha`` and
+        ``__call__`` are COLLECTIVE calls (every rank makes them in the same order; ``__call__`` takes this rank's
+        own slab of query points).  Without ``hyperpars`` the ranks run the optimiser in lockstep: the start points
+        (and differential-evolution populations) come from a generator seeded by the replicated data instead of
+        numpy's global one, and every evaluation returns the same all-reduced value and gradient on every rank.
     :param int dist_block: panel width of the distributed layout (multiple of 128, default 1024).
     """
 
@@ -140,14 +142,13 @@ class GpRegressor:
             self.model_selector = self.marginal_likelihood
             self.model_selector_gradient = self.marginal_likelihood_gradient
 
-        if hyperpars is None and self._dist is not None:
+        if hyperpars is None and self._dist is not None and (cross_val or n_processes != 1):
             raise ValueError(
                 """\n
                 [ GpRegressor error ]
-                >> distributed=True needs the 'hyperpars' argument: the block-cyclic path evaluates
-                >> the marginal likelihood (collectively) but not its gradient; optimise the
-                >> hyper-parameters on a subsample, or drive 'marginal_likelihood' from an optimiser
-                >> that takes identical steps on every rank.
+                >> distributed=True optimises the marginal likelihood collectively: every rank runs the
+                >> same optimiser on the same (all-reduced) values, so 'cross_val' and 'n_processes' > 1
+                >> are not available; pass 'hyperpars' to skip the optimisation.
                 """
             )
         if hyperpars is None:
@@ -483,9 +484,13 @@ class GpRegressor:
     def marginal_likelihood_gradient(self, theta: np.ndarray):
         """Log-marginal likelihood and its gradient (regression.py:544-567); a failed factorisation raises
         ``LinAlgError`` as numpy.linalg.cholesky does at regression.py:555."""
-        if self._dist is not None:
-            raise NotImplementedError("the distributed path provides marginal_likelihood but not its gradient "
-                                      "(the explicit inverse is not built in the block-cyclic layout)")
+        if self._dist is not None:      # collective: this rank's rows of K^-1, its share of the traces, one all-reduce
+            self._dist_theta = None
+            val, grad, info, _ = self.engine.dist_lml_grad(np.asarray(theta, dtype=float), self._dist_block)
+            if info > 0:
+                raise LinAlgError("Matrix is not positive definite")
+            self._dist_theta = np.asarray(theta, dtype=float).copy()
+            return np.float64(val), grad
         val, grad, info = self.engine.lml_grad(np.asarray(theta, dtype=float))
         if info > 0:
             raise LinAlgError("Matrix is not positive definite")
@@ -518,8 +523,15 @@ class GpRegressor:
 
             res = differential_evolution(func=population_cost, bounds=self.hp_bounds, vectorized=True, updating="deferred")
             return res.x
-        res = differential_evolution(func=lambda t: -self.model_selector(t), bounds=self.hp_bounds)
+        # distributed: every rank must propose the same populations (the evaluations are collective calls)
+        seed = self._lockstep_seed() if self._dist is not None else None
+        res = differential_evolution(func=lambda t: -self.model_selector(t), bounds=self.hp_bounds, seed=seed)
         return res.x
+
+    def _lockstep_seed(self) -> int:
+        """Seed shared by all ranks of a distributed fit without communication: a checksum of the (replicated) targets."""
+        import zlib
+        return zlib.crc32(np.ascontiguousarray(self.y).tobytes()) & 0x7FFFFFFF
 
     def bfgs_cost_func(self, theta: np.ndarray):
         val, grad = self.model_selector_gradient(theta)
@@ -534,7 +546,10 @@ class GpRegressor:
         if starts is None:
             starts = int(2 * np.sqrt(len(self.hp_bounds))) + 1
         lwr, upr = (np.array([b[i] for b in self.hp_bounds]) for i in (0, 1))
-        x0s = [lwr + (upr - lwr) * np.random.random(size=len(self.hp_bounds)) for _ in range(starts - 1)]
+        # distributed: the ranks run this optimiser in lockstep (every evaluation is a collective call), so they must draw
+        # the same start points -- from a generator seeded by the replicated data instead of the process-global one
+        draw = np.random.RandomState(self._lockstep_seed()).random_sample if self._dist is not None else np.random.random
+        x0s = [lwr + (upr - lwr) * draw(size=len(self.hp_bounds)) for _ in range(starts - 1)]
         x0s.append(0.5 * (lwr + upr))
 
         if n_processes == 1 or len(x0s) == 1:

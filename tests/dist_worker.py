@@ -37,6 +37,7 @@ def main():
     alpha = m.alpha
     theta2 = theta + 0.1
     lml2 = m.marginal_likelihood(theta2)          # re-factors at theta2 ...
+    lml_g, grad = m.marginal_likelihood_gradient(theta2)   # collective: row blocks of K^-1 per rank, traces, all-reduce
     mu_b, sig_b = m(q_all[lo:hi])                 # ... and predicting must bring the fit's own factor back
     out = {"rank": rank, "ok": True}
     if rank == 0:
@@ -47,6 +48,8 @@ def main():
         out.update(lml=float(lml), lml_single=float(s.marginal_likelihood(theta)), lml2=float(lml2),
                    lml2_single=float(s.marginal_likelihood(theta2)), alpha_err=rel(alpha, s.alpha), mu_err=rel(mu, mu_s),
                    sig_err=float(np.abs(sig / sig_s - 1).max()), repeat_mu_err=rel(mu_b, mu), repeat_sig_err=rel(sig_b, sig))
+        lml_gs, grad_s = s.marginal_likelihood_gradient(theta2)
+        out.update(grad_err=rel(grad, grad_s), lml_grad_err=abs(float(lml_g) - float(lml_gs)) / abs(float(lml_gs)))
         if n <= 4096:
             ref = orc.Fit(x, y, ("SE",), "const", theta, e**2)
             mu_o, sig_o = ref.predict(q_all[lo:hi])

@@ -20,6 +20,7 @@ ap.add_argument("--dim", type=int, default=2)
 ap.add_argument("--block", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--grad", action="store_true", help="also time gpb_dist_lml_grad (and compare with the single-GPU gradient under --check)")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 
@@ -61,6 +62,27 @@ if rank == 0:
         ref, info = eng.lml(theta)
         out["single_gpu_lml"] = ref
         out["rel_diff"] = abs(best[0] - ref) / abs(ref)
+if a.grad:          # collective: every rank takes part
+    gres = []
+    for r in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lml_g, grad, info, t = eng.dist_lml_grad(theta, a.block)
+        tt = torch.tensor([t["factor_s"], t["gradient_s"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        gres.append((lml_g, grad, tt.tolist()))
+    if rank == 0:
+        out["grad"] = {"lml": gres[-1][0], "grad": gres[-1][1].tolist(), "factor_s": gres[-1][2][0], "gradient_s": gres[-1][2][1],
+                       "gradient_over_factor": gres[-1][2][1] / gres[-1][2][0]}
+        if a.check:
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            eng.lml_grad(theta)
+            t0.record(); lml_s, grad_s, info = eng.lml_grad(theta); eng.sync(); t1.record(); torch.cuda.synchronize()
+            out["grad"]["single_gpu_s"] = t0.elapsed_time(t1) * 1e-3
+            out["grad"]["rel_diff_vs_single_gpu"] = float(np.abs(gres[-1][1] - grad_s).max() / np.abs(grad_s).max())
+if rank == 0:
     print(json.dumps(out))
     if a.out:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
