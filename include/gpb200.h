@@ -66,6 +66,10 @@ double gpb_gemm_flops_int8(void);         /* ... of which on the INT8 tensor-cor
  *                    block's explicit inverse (9 % faster solve, sigma up to 4x above the FP64 floor on dense data),
  *                    0 = the latter only for well-conditioned fits (amp / min L_ii <~ 30)
  *   "gemm_i8_max_k"  longest k extent of one INT8 launch (16384 = the int32 exactness limit); longer extents are chunked
+ *   "grad_inverse"   K^-1 of gpb_lml_grad: 0 = recursive triangular inverse W, then W^T W (default); 1 = rows of L^-T by blocked
+ *                    substitution, then Y Y^T (equal in time and accuracy)
+ *   "gemm_i8_epi2"   INT8 kernel, second-sweep epilogue in two passes (TMEM released before global memory is touched):
+ *                    0 = off, 1 = on, 2 = for k extents >= 2048 with 8 epilogue warps (default)
  *   "gemm_i8_prefetch"  INT8 kernel: k-blocks by which an L2 prefetch of the digit planes runs ahead of the loads (0 = off)
  *   "gemm_i8_epi"    epilogue warps of the INT8 kernel (0 = by k extent, 8, 16)      "i8_grad_phases"  diagnostic mask
  *   "i8_grad_guard"  a-posteriori error estimate of the INT8 inverse chain in gpb_lml_grad, DMMA repeat when it is too

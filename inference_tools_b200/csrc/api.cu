@@ -608,28 +608,43 @@ static int lml_grad_impl(gpb_ctx* c, const double* theta, double* lml, double* g
         GPB_TRY(assemble_and_factor(c, cp, mp, c->Kwork, c->dinv_work, nullptr, SOLVE_NONE, nullptr, &info_h));
     }
     double sc[3], fro2[MAX_COMP];
+    // The triangular inverse: c->W receives W = inv(L) (lower) from the recursion, or Y = W^T (upper) from the blocked
+    // substitution -- option "grad_inverse"; the substitution form keeps every product at the scale of L (potrf.cu)
+    const bool by_rows = option(OPT_GRAD_INVERSE) != 0;
     auto inverse_and_traces = [&](bool with_trtri) -> int {
         if (with_trtri) {
             c->timer.mark("trtri");
             {
                 PhaseMode pm(phases, 2);
-                GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
-                    GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
-                    return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
-                }));
+                if (by_rows) {
+                    GPB_TRY(run_graphed(c, pkey("trtri_rows", {c->Kwork, c->W, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
+                        return trtri_rows_lower(c->Kwork, npad, c->W, npad, npad, ws_of(c, c->dinv_work), c->s);
+                    }));
+                } else {
+                    GPB_TRY(run_graphed(c, pkey("trtri", {c->Kwork, c->W, c->Kinv, c->dinv_work, c->tmp}, {npad}), [&]() -> int {
+                        GPB_CUDA(cudaMemsetAsync(c->W, 0, sizeof(double) * np * np, c->s));
+                        return trtri_lower(c->Kwork, npad, c->W, npad, npad, 0, ws_of(c, c->dinv_work), c->Kinv, npad, c->s);
+                    }));
+                }
             }
             // alpha = K^-1 r through the explicit inverse, as the reference does here (regression.py:556-559):
             // v = W r, alpha = W^T v -- two fully parallel matrix-vector passes instead of 2 N/128 dependent block steps
             c->timer.mark("alpha");
-            GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->resid, c->vec, c->s));
-            GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->partials, c->s));
+            if (by_rows) {  // c->W holds W^T
+                GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->resid, c->vec, c->partials, c->s));
+                GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->s));
+            } else {
+                GPB_TRY(launch_row_dot(c->W, npad, npad, npad, c->resid, c->vec, c->s));
+                GPB_TRY(launch_col_dot(c->W, npad, npad, npad, c->vec, c->alpha_work, c->partials, c->s));
+            }
             // LML = -0.5 r.alpha - sum log L_ii   (regression.py:559-560)
             GPB_TRY(launch_logdet_dot(c->Kwork, npad, c->resid, c->alpha_work, n, c->scal, c->s));
         }
         c->timer.mark("lauum");
         {
             PhaseMode pm(phases, 4);
-            GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+            if (by_rows) GPB_TRY(lauum_rows_lower(c->W, npad, c->Kinv, npad, npad, c->s));
+            else GPB_TRY(lauum_lower(c->W, npad, c->Kinv, npad, npad, c->s));
         }
         c->timer.mark("trace");
         GPB_CUDA(cudaMemsetAsync(c->grad_dev, 0, sizeof(double) * (nt + 2 + MAX_COMP), c->s));

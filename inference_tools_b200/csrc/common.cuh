@@ -99,6 +99,9 @@ enum Option : int {
                           // each chunk with its own row scales, and accumulated in FP64
     OPT_GEMM_I8_EPI,      // epilogue warps per CTA of the INT8 kernel: 16 (default) or 8
     OPT_I8_GRAD_PHASES,   // diagnostic bit mask: which phases of gpb_lml_grad may use the INT8 path (1 potrf, 2 trtri, 4 lauum; default 7)
+    OPT_GRAD_INVERSE,     // K^-1 of marginal_likelihood_gradient: 0 = recursive triangular inverse, W^T W (default); 1 = rows of L^-T by
+                          // blocked substitution, Y Y^T (measured equal in time and accuracy: profiles/dist_grad_parity_r2.json)
+    OPT_GEMM_I8_EPI2,     // INT8 kernel, second-sweep epilogue in two passes (accumulators to registers, release, then global memory)
     OPT_GEMM_I8_PREFETCH, // INT8 kernel: k-blocks by which an L2 prefetch of the digit planes runs ahead of the loads (0 = off)
     OPT_COUNT
 };

@@ -69,6 +69,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int RASTER = 8;                     // row-blocks per rasterisation group (B planes stay in L2 across them)
 constexpr int MAX_K = 16384;
 constexpr int DEBUG_NO_MMA = 1 << 20, DEBUG_NO_LOAD = 1 << 21;  // timing probes (results are meaningless)
+constexpr int EPI_TWO_PASS = 1 << 22;                           // second-sweep epilogue: release TMEM before touching global memory
 
 struct I8Args {
     int M, N, K;
@@ -516,6 +517,58 @@ __global__ void __launch_bounds__(threads_for(EPI_WARPS), 1) gemm_i8_kernel(cons
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
             const double sa = p.sa[row] * p.alpha * (1.0 / 65536.0);
+            if (EPI_WARPS == 8 && (p.flags & EPI_TWO_PASS) && tr.nkb > 0) {  // 8 warps: 204 registers per thread to spend
+                // Two passes: first the whole accumulator row goes to registers (I2 is exact in FP64) and the TMEM columns
+                // are released -- the MMA warp starts the next tile's first sweep -- then the partial sums of the first
+                // sweep and C are fetched from global memory, off the critical path (one L2 round trip per chunk there).
+                double i2[COLS];
+#pragma unroll
+                for (int c = 0; c < COLS / 16; ++c) {
+                    int r[S_HI][16];
+#pragma unroll
+                    for (int g = 0; g < S_HI; ++g)
+                        tmem_ld16(tmem_base + lane_base + (unsigned)(g * BN + cbase + c * 16), r[g]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        long long v = r[0][j];
+#pragma unroll
+                        for (int g = 1; g < S_HI; ++g) v = v * 256 + r[g][j];
+                        i2[c * 16 + j] = (double)v;
+                    }
+                }
+                release_tmem();
+                ++uses;
+#pragma unroll
+                for (int c = 0; c < COLS / 16; ++c) {
+                    const int col = tr.col0 + cbase + c * 16;
+                    double v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const double2 h = *reinterpret_cast<const double2*>(scr + c * 16 + j);
+                        v[j] = fma(h.x, 2.3283064365386963e-10, i2[c * 16 + j]) * sa * __ldg(p.sb + col + j);
+                        v[j + 1] = fma(h.y, 2.3283064365386963e-10, i2[c * 16 + j + 1]) * sa * __ldg(p.sb + col + j + 1);
+                    }
+                    if (beta != 0.0) {
+                        const double2* src = reinterpret_cast<const double2*>(p.C + (int64_t)row * p.ldc + col);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const double2 w = src[j];
+                            v[2 * j] = fma(beta, w.x, v[2 * j]);
+                            v[2 * j + 1] = fma(beta, w.y, v[2 * j + 1]);
+                        }
+                    }
+                    double2* dst = reinterpret_cast<double2*>(p.D + (int64_t)row * p.ldd + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_double2(v[2 * j], v[2 * j + 1]);
+                    if (p.D2 != nullptr) {
+                        double2* dst2 = reinterpret_cast<double2*>(p.D2 + (int64_t)row * p.ldd2 + col);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst2[j] = make_double2(v[2 * j], v[2 * j + 1]);
+                    }
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < COLS / 16; ++c) {  // second sweep: add I2, scale, store
                 double v[16];
@@ -855,7 +908,11 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
         return -3;
     }
     const int debug = (int)option(OPT_GEMM_I8_DEBUG);
-    I8Args p{M, N, Kc, sa, sb, C, ldc, D, ldd, D2, ldd2, alpha, beta, flags | (debug << 20), tm, tn, w->scratch, k_off, k_total,
+    // second-sweep epilogue in two passes (8 epilogue warps only): +2-3 % for 2048 <= k < 4096, -1 % at k = 1024
+    // (profiles/i8_epi2_ab_r2.json).  Option "gemm_i8_epi2": 0 = off, 1 = on, 2 = by k extent (default).
+    const int64_t epi2 = option(OPT_GEMM_I8_EPI2);
+    const int two_pass = (epi2 == 1 || (epi2 == 2 && Kc >= 2048)) ? EPI_TWO_PASS : 0;
+    I8Args p{M, N, Kc, sa, sb, C, ldc, D, ldd, D2, ldd2, alpha, beta, flags | ((debug & 3) << 20) | two_pass, tm, tn, w->scratch, k_off, k_total,
              a_row_off, b_row_off, (int)std::min<int64_t>(64, std::max<int64_t>(0, option(OPT_GEMM_I8_PREFETCH)))};
     // epilogue warps per CTA: 16 pay off on long k extents (+1.4 % on the predict shape), 8 on short ones (+3 % at
     // k = 1024): profiles/i8_epilogue_ab_r2.json.  Option "gemm_i8_epi": 0 = by k extent, 8 or 16 = fixed.

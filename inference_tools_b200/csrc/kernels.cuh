@@ -68,6 +68,9 @@ int trtri_lower(const double* L, int64_t ldl, double* W, int64_t ldw, int n, int
                 double* scratch, int64_t lds, cudaStream_t s);
 // Kinv(lower tiles) = W^T W
 int lauum_lower(const double* W, int64_t ldw, double* Kinv, int64_t ldk, int n, cudaStream_t s);
+// the same inverse by substitution: Y = L^-T (upper, row-major; n x n overwritten), then Kinv(lower tiles) = Y Y^T
+int trtri_rows_lower(const double* L, int64_t ldl, double* Y, int64_t ldy, int n, const LinalgWs& ws, cudaStream_t s);
+int lauum_rows_lower(const double* Y, int64_t ldy, double* Kinv, int64_t ldk, int n, cudaStream_t s);
 
 // ---- solve.cu : vector solves and reductions
 // v = L^-1 r (fwd) ; a = L^-T v (bwd).  vec holds 2*npad doubles: [0,npad) = right-hand side (destroyed),

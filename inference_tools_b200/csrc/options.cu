@@ -47,6 +47,8 @@ struct OptionTable {
         v[OPT_GEMM_I8_MAX_K] = env("GPB200_GEMM_I8_MAX_K", 16384);
         v[OPT_GEMM_I8_EPI] = env("GPB200_GEMM_I8_EPI", 0);
         v[OPT_I8_GRAD_PHASES] = env("GPB200_I8_GRAD_PHASES", 7);
+        v[OPT_GRAD_INVERSE] = env("GPB200_GRAD_INVERSE", 0);
+        v[OPT_GEMM_I8_EPI2] = env("GPB200_GEMM_I8_EPI2", 2);
         v[OPT_GEMM_I8_PREFETCH] = env("GPB200_GEMM_I8_PREFETCH", 0);
     }
 };
@@ -56,7 +58,7 @@ OptionTable& table() {
 }
 
 const char* const kNames[OPT_COUNT] = {"gemm_i8",  "gemm_i8_min_k", "gemm_i8_pair", "gemm_i8_debug", "gemm_tile",
-                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block", "predict_diag", "i8_grad_guard", "gemm_i8_max_k", "gemm_i8_epi", "i8_grad_phases", "gemm_i8_prefetch"};
+                                       "gemm_tma", "graphs",        "i8_fallback",  "predict_block", "predict_diag", "i8_grad_guard", "gemm_i8_max_k", "gemm_i8_epi", "i8_grad_phases", "grad_inverse", "gemm_i8_epi2", "gemm_i8_prefetch"};
 
 int find_option(const char* name) {
     if (!name) return -1;

@@ -127,3 +127,20 @@ def test_blocked_predict_solve_on_cached_planes_matches_recursion_and_oracle():
     ref2 = orc.Fit(x, y, ("SE",), "const", theta2, e**2)
     mu2_o, sig2_o = ref2.predict(q[:128])
     assert rel_err(mu2[:128], mu2_o) < TOL and np.abs(sig2[:128] / sig2_o - 1).max() < TOL
+
+
+def test_gradient_with_the_substitution_inverse_matches_the_oracle():
+    """Option "grad_inverse" = 1: K^-1 from the rows of L^-T (blocked substitution, potrf.cu: trtri_rows_lower) instead of
+    the recursive triangular inverse -- same gradient, same alpha / LML, on the INT8 path and on DMMA."""
+    n, d = 4096, 3
+    x, y, e = synth(91, n, d)
+    theta = np.array([0.3, 0.1] + [np.log(0.35)] * d)
+    lml_o, grad_o = orc.marginal_likelihood_gradient_blocked(x, y, ("SE",), "const", theta, e**2)
+    m = gp.GpRegressor(x, y, y_err=e, hyperpars=theta)
+    lml0, grad0 = m.marginal_likelihood_gradient(theta)
+    for opts in ({"grad_inverse": 1}, {"grad_inverse": 1, "gemm_i8": 0}, {"grad_inverse": 1, "gemm_i8": 2, "gemm_i8_min_k": 64}):
+        with _lib.options(**opts):
+            lml, grad = m.marginal_likelihood_gradient(theta)
+        assert abs(lml - lml_o) <= TOL * abs(lml_o)
+        assert np.abs(grad - grad_o).max() <= TOL * np.abs(grad_o).max()
+        assert np.abs(grad - grad0).max() <= 1e-10 * np.abs(grad0).max()

@@ -8,7 +8,7 @@ from inference_tools_b200 import _lib
 from oracle import gp_oracle as orc
 
 out = {"cases": []}
-for n, d, block in [(8192, 2, 1024), (8192, 3, 512), (16384, 2, 1024)]:
+for n, d, block in [(2048, 2, 256), (8192, 2, 1024), (16384, 2, 1024), (16384, 3, 1024)]:
     rng = np.random.default_rng(5)
     x = rng.uniform(0, 1, (n, d))
     y = np.sin(3 * x).sum(axis=1) + rng.normal(0, 0.05, n)
@@ -26,9 +26,17 @@ for n, d, block in [(8192, 2, 1024), (8192, 3, 512), (16384, 2, 1024)]:
             eng.dist_init(0, 1, None)
             lml_d, grad_d, info, t = eng.dist_lml_grad(theta, block)
             lml_d, grad_d, info, t = eng.dist_lml_grad(theta, block)
-            lml_s, grad_s, info_s = eng.lml_grad(theta)
-            case[mode] = {"dist_grad_rel_err": rel(grad_d), "single_grad_rel_err": rel(grad_s), "dist_lml_rel_err": abs(lml_d - lml_o) / abs(lml_o),
-                          "factor_s": t["factor_s"], "gradient_s": t["gradient_s"], "guard_retries": eng.stat("grad_guard_retries") if hasattr(eng, "stat") else None}
+            single = {}
+            for inv in (1, 0):      # K^-1 from the rows of L^-T (substitution) / from the recursive triangular inverse
+                with _lib.options(grad_inverse=inv):
+                    eng.lml_grad(theta)
+                    lml_s, grad_s, info_s = eng.lml_grad(theta)
+                    tm = eng.timers()
+                    single[f"grad_inverse{inv}"] = {"grad_rel_err": rel(grad_s), "lml_rel_err": abs(lml_s - lml_o) / abs(lml_o),
+                                                    "trtri_ms": tm.get("trtri"), "lauum_ms": tm.get("lauum"), "total_ms": sum(tm.values()),
+                                                    "guard_retries": eng.stat("grad_guard_retries")}
+            case[mode] = {"dist_grad_rel_err": rel(grad_d), "single": single, "dist_lml_rel_err": abs(lml_d - lml_o) / abs(lml_o),
+                          "factor_s": t["factor_s"], "gradient_s": t["gradient_s"]}
             eng.dist_finalize()
             eng.close()
     out["cases"].append(case)
