@@ -60,8 +60,16 @@ def _worker(rank, world, port, m, out):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     cnt = torch.tensor([hi - lo], dtype=torch.int64)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    # distributed fit without hyperpars (gp/regression.py): every rank derives the optimiser's start points from the
+    # replicated targets alone, so the ranks -- whose numpy global generators differ -- take identical steps
+    from inference_tools_b200.gp import GpRegressor
+    np.random.seed(1000 + rank)
+    holder = type("Replica", (), {"y": np.sin(np.arange(50.0))})()
+    starts = np.random.RandomState(GpRegressor._lockstep_seed(holder)).random_sample(size=6)
+    gathered_starts = [None] * world
+    dist.all_gather_object(gathered_starts, starts.tolist())
     if rank == 0:
-        out.put((float(t), int(cnt), [b.tolist() for b in bufs] if len({b.numel() for b in bufs}) == 1 else None))
+        out.put((float(t), int(cnt), [b.tolist() for b in bufs] if len({b.numel() for b in bufs}) == 1 else None, gathered_starts))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,8 +84,9 @@ def test_two_rank_gloo_sharded_predict_bookkeeping():
     m = 64
     procs = [ctx.Process(target=_worker, args=(r, 2, port, m, out)) for r in range(2)]
     [p.start() for p in procs]
-    tmax, total, gathered = out.get(timeout=120)
+    tmax, total, gathered, starts = out.get(timeout=120)
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert tmax == 1.5 and total == m
     assert np.allclose(np.concatenate(gathered), np.arange(m) * 2.0)
+    assert starts[0] == starts[1] and len(starts[0]) == 6              # lockstep start points agree across ranks
