@@ -197,6 +197,18 @@ def dist_cholesky_block(args, rank, world, local, gp_engine, barrier, max_over_r
         barrier()
         lml, info, t = eng.dist_lml(theta, block)
         runs.append((lml, info, max_over_ranks(t["factor_s"]), max_over_ranks(t["assemble_s"])))
+    grad_block = None
+    if world >= 4 and os.environ.get("GPB_BENCH_DIST_GRAD", "1") != "0":
+        # the gradient of the same likelihood on the same layout (gpb_dist_lml_grad): N^2 / world doubles of inverse rows per
+        # rank, so only from 4 ranks up at this N.  Reported, never part of the headline value; a failure is reported too.
+        try:
+            barrier()
+            lml_g, grad, info_g, tg = eng.dist_lml_grad(theta, block)
+            grad_block = {"lml": lml_g, "info": info_g, "grad": [float(v) for v in grad], "factor_seconds": max_over_ranks(tg["factor_s"]),
+                          "gradient_seconds": max_over_ranks(tg["gradient_s"]),
+                          "what": "alpha + rows of K^-1 (streamed solves, Y_a Y_b^T products) + traces + all-reduce, after the factor"}
+        except Exception as exc:  # noqa: BLE001 -- the bench line must still be printed
+            grad_block = {"error": str(exc)[:300]}
     eng.dist_finalize()
     eng.close()
     lml, info, factor_s, assemble_s = runs[-1]
@@ -205,6 +217,8 @@ def dist_cholesky_block(args, rank, world, local, gp_engine, barrier, max_over_r
            "factor_seconds": factor_s, "assemble_seconds": assemble_s, "info": info, "lml": lml,
            "fp64_equiv_tflops_aggregate": npad**3 / 3 / factor_s / 1e12, "fp64_equiv_tflops_per_gpu": npad**3 / 3 / factor_s / 1e12 / world,
            "collective": "ncclBroadcast per panel (N^2/2 x 8 B received per rank in total) + one 2-double ncclAllReduce"}
+    if grad_block is not None:
+        out["gradient"] = grad_block
     try:
         ref = json.load(open(os.path.join(ROOT, "profiles", "dist_cholesky_1gpu_ref_r2.json")))
         if ref.get("n") == n and ref.get("block") == block:

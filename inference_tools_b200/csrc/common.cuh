@@ -66,7 +66,13 @@ struct GemmArgs {
     // scales, so a short chunk keeps more bits of operand rows whose entries decay along k (columns of inv(L) in
     // K^-1 = W^T W: profiles/grad_phase_sensitivity_r2.md); the chunks are accumulated in FP64.
     int max_k = 0;
+    // GEMM_TRIK_A with a block structure instead of the tile's own: A(m, k) == 0 for k < (m / trik_a_blk) * trik_a_step
+    // (0 = the plain rule, k < m).  The stacked row blocks of the distributed inverse (dist.cu) are block-cyclic: row
+    // block i of the stack starts its non-zeros world * nbd columns after row block i - 1.
+    int trik_a_blk = 0, trik_a_step = 0;
 };
+// first k of a tile whose first row is row0 under GEMM_TRIK_A
+__host__ __device__ inline int trik_a_begin(int row0, int blk, int step) { return blk > 0 ? (row0 / blk) * step : row0; }
 int gemm_nt(const GemmArgs& a, cudaStream_t s);
 void gemm_i8_release(cudaStream_t s);  // gemm_i8.cu: frees the digit-plane workspace tied to a stream
 

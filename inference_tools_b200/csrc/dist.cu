@@ -538,7 +538,8 @@ int dist_alpha_impl(gpb_ctx* c) {
 //            b < a is written over the zero part of Y's row block a (column block b -- never read again as an operand),
 //            the diagonal blocks go to d->kdiag.  The products run in k-chunks with their own row scales on the INT8 path
 //            for the reason given at lauum_lower (potrf.cu).
-// Flops: N^3 / 3 (phase 1) + ~2 N^3 / 3 (phase 2: the stacked row blocks share one k range) over all ranks;
+// Flops: N^3 / 3 (phase 1) + N^3 / 3 (phase 2: the k range of every tile starts at its row block's first non-zero column)
+// over all ranks;
 // NVLink: 2 x N^2 / 2 x 8 bytes received per rank.
 int dist_inverse_rows(gpb_ctx* c, int* na_out) {
     gpb_dist* d = c->dist;
@@ -624,10 +625,13 @@ int dist_inverse_rows(gpb_ctx* c, int* na_out) {
             GPB_TRY(gemm_nt(g, s));
             ++idx;
         }
-        if (idx < na) {  // row blocks a > b, stacked: both operands are zero left of column a1 nbd
+        if (idx < na) {  // row blocks a > b, stacked: both operands are zero left of column a1 nbd, and row block i of
+                         // the stack is zero for another i G nbd columns (block-structured GEMM_TRIK_A: N^3/3 flops in all)
             const int64_t k0 = (int64_t)(me + G * idx) * nbd;
             GemmArgs g{(na - idx) * nbd, cb, (int)(npad - k0), yrow(idx) + k0, npad, P + (k0 - (int64_t)b * nbd), ldb, nullptr, 0,
-                       yrow(idx) + (size_t)b * nbd, npad, nullptr, 0, 1.0, 0.0, GEMM_FULL};
+                       yrow(idx) + (size_t)b * nbd, npad, nullptr, 0, 1.0, 0.0, GEMM_TRIK_A};
+            g.trik_a_blk = nbd;
+            g.trik_a_step = G * nbd;
             g.max_k = chunk;
             GPB_TRY(gemm_nt(g, s));
         }

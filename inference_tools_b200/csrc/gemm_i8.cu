@@ -86,6 +86,7 @@ struct I8Args {
     int k_off, k_total;  // this launch covers [k_off, k_off + K) of the full k extent (int32 sums stay exact)
     int a_row_off, b_row_off;  // first row of the operands inside their digit-plane buffers (cached planes hold more rows)
     int prefetch;              // k-blocks by which an L2 prefetch of the planes runs ahead of the shared-memory loads (0 = off)
+    int trik_a_blk, trik_a_step;  // GemmArgs: block structure of GEMM_TRIK_A (0 = the tile's own rows)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -248,7 +249,7 @@ __device__ __forceinline__ TileRange tile_range(const I8Args& p, int t) {
     tr.row0 = bi * BMT;
     tr.col0 = bj * BN;
     int k_begin = 0, k_end = p.k_total;  // in the full k extent, then clipped to this launch's chunk
-    if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, tr.row0);
+    if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, trik_a_begin(tr.row0, p.trik_a_blk, p.trik_a_step));
     if (p.flags & GEMM_TRIK_B) k_begin = max(k_begin, tr.col0);
     if (p.flags & GEMM_TRIL_B) k_end = min(k_end, tr.col0 + BN);
     if (p.flags & GEMM_TRIL_A) k_end = min(k_end, tr.row0 + BMT);
@@ -891,7 +892,7 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
                   int a_row_off, const double* sa, const signed char* qb, int64_t ldb_q, int64_t pb, int64_t rows_b,
                   int b_row_off, const double* sb, int M, int N, int Kc, int k_off, int map_k_off, int k_total, const double* C,
                   int64_t ldc, double* D, int64_t ldd, double* D2, int64_t ldd2, double alpha, double beta, int flags,
-                  int ctas) {
+                  int ctas, int trik_blk = 0, int trik_step = 0) {
     const int bmt = BM * ctas;
     const int tm = M / bmt, tn = N / BN;
     const int64_t tiles = (flags & GEMM_LOWER) ? (ctas == 2 ? (int64_t)tm * (tm + 1) : (int64_t)tm * (tm + 1) / 2)
@@ -913,7 +914,7 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
     const int64_t epi2 = option(OPT_GEMM_I8_EPI2);
     const int two_pass = (epi2 == 1 || (epi2 == 2 && Kc >= 2048)) ? EPI_TWO_PASS : 0;
     I8Args p{M, N, Kc, sa, sb, C, ldc, D, ldd, D2, ldd2, alpha, beta, flags | ((debug & 3) << 20) | two_pass, tm, tn, w->scratch, k_off, k_total,
-             a_row_off, b_row_off, (int)std::min<int64_t>(64, std::max<int64_t>(0, option(OPT_GEMM_I8_PREFETCH)))};
+             a_row_off, b_row_off, (int)std::min<int64_t>(64, std::max<int64_t>(0, option(OPT_GEMM_I8_PREFETCH))), trik_blk, trik_step};
     // epilogue warps per CTA: 16 pay off on long k extents (+1.4 % on the predict shape), 8 on short ones (+3 % at
     // k = 1024): profiles/i8_epilogue_ab_r2.json.  Option "gemm_i8_epi": 0 = by k extent, 8 or 16 = fixed.
     const int epi_opt = (int)option(OPT_GEMM_I8_EPI);
@@ -949,7 +950,7 @@ int launch_planes(Workspace* w, cudaStream_t s, const signed char* qa, int64_t l
     return 0;
 }
 
-double algorithmic_flops(int M, int N, int K, int flags, int ctas) {
+double algorithmic_flops(int M, int N, int K, int flags, int ctas, int trik_blk = 0, int trik_step = 0) {
     const int bmt = BM * ctas, tm = M / bmt, tn = N / BN;
     const int64_t tiles = (flags & GEMM_LOWER) ? (ctas == 2 ? (int64_t)tm * (tm + 1) : (int64_t)tm * (tm + 1) / 2)
                                                : (int64_t)tm * tn;
@@ -959,7 +960,7 @@ double algorithmic_flops(int M, int N, int K, int flags, int ctas) {
         const int ntile = (flags & GEMM_LOWER) ? (ctas == 2 ? 2 * bi + 2 : bi + 1) : tn;
         for (int bj = 0; bj < ntile; ++bj) {
             int kb = 0, ke = K;
-            if (flags & GEMM_TRIK_A) kb = std::max(kb, bi * bmt);
+            if (flags & GEMM_TRIK_A) kb = std::max(kb, trik_a_begin(bi * bmt, trik_blk, trik_step));
             if (flags & GEMM_TRIK_B) kb = std::max(kb, bj * BN);
             if (flags & GEMM_TRIL_B) ke = std::min(ke, bj * BN + BN);
             if (flags & GEMM_TRIL_A) ke = std::min(ke, bi * bmt + bmt);
@@ -1050,15 +1051,18 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
     GPB_TRY(grow(w->sb, w->sb_cap, sizeof(double) * 2 * a.N, w->retired));
     const int ctas = ctas_for(a.M);
     const int bmt = BM * ctas;
+    // block-structured GEMM_TRIK_A: the splitting pass treats A as full (the skipped part holds zeros, which split to zero
+    // digits and do not move a row maximum); only the kernel's k ranges use the structure
+    const int a_flags = a.trik_a_blk > 0 ? (a.flags & ~GEMM_TRIK_A) : a.flags;
     for (int k0 = 0, c = 0; k0 < a.K; k0 += Kc_max, ++c) {
         const int Kc = std::min(Kc_max, a.K - k0);
         if (a_t) {
             const double* X = a.A + (int64_t)k0 * a.lda;
-            split_cols_max_kernel<<<a.M / 64, 256, 0, s>>>(X, a.lda, Kc, k0, w->sa, w->sa + a.M, 1.0 / 16384.0, a.flags, bmt);
+            split_cols_max_kernel<<<a.M / 64, 256, 0, s>>>(X, a.lda, Kc, k0, w->sa, w->sa + a.M, 1.0 / 16384.0, a_flags, bmt);
             split_cols_digits_kernel<<<dim3(a.M / 64, Kc / 64), 256, 0, s>>>(X, a.lda, Kc, k0, a.M, w->qa, w->sa + a.M,
-                                                                             a.flags, bmt);
+                                                                             a_flags, bmt);
         } else {
-            split_rows_kernel<<<a.M, 256, 0, s>>>(a.A + k0, a.lda, Kc, k0, a.M, w->qa, w->sa, 1.0 / 16384.0, a.flags, bmt,
+            split_rows_kernel<<<a.M, 256, 0, s>>>(a.A + k0, a.lda, Kc, k0, a.M, w->qa, w->sa, 1.0 / 16384.0, a_flags, bmt,
                                                   nullptr, 1, Kc, (int64_t)a.M * Kc);
         }
         GPB_CUDA(cudaGetLastError());
@@ -1076,9 +1080,9 @@ int gemm_nt_i8(const GemmArgs& a, cudaStream_t s, double* flops_out) {
         // the chunk's planes are compact (k local to the chunk); k_off / k_total only steer the triangular k ranges
         GPB_TRY(launch_planes(w, s, w->qa, Kc, (int64_t)a.M * Kc, a.M, 0, w->sa, w->qb, Kc, (int64_t)a.N * Kc, a.N, 0, w->sb, a.M,
                               a.N, Kc, k0, 0, a.K, c == 0 ? a.C : a.D, c == 0 ? a.ldc : a.ldd, a.D, a.ldd, a.D2, a.ldd2, a.alpha,
-                              c == 0 ? a.beta : 1.0, a.flags, ctas));
+                              c == 0 ? a.beta : 1.0, a.flags, ctas, a.trik_a_blk, a.trik_a_step));
     }
-    if (flops_out) *flops_out = algorithmic_flops(a.M, a.N, a.K, a.flags, ctas);
+    if (flops_out) *flops_out = algorithmic_flops(a.M, a.N, a.K, a.flags, ctas, a.trik_a_blk, a.trik_a_step);
     return 0;
 }
 

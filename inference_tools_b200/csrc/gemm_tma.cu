@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(THREADS, 3) dgemm_tma_kernel(const __grid_cons
     }
     const int row0 = bi * BM, col0 = bj * BN;
     int k_begin = 0, k_end = p.K;
-    if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, row0);
+    if (p.flags & GEMM_TRIK_A) k_begin = max(k_begin, trik_a_begin(row0, p.trik_a_blk, p.trik_a_step));
     if (p.flags & GEMM_TRIK_B) k_begin = max(k_begin, col0);
     if (p.flags & GEMM_TRIL_B) k_end = min(k_end, col0 + BN);
     if (p.flags & GEMM_TRIL_A) k_end = min(k_end, row0 + BM);
@@ -233,7 +233,7 @@ int gemm_nt_tma(const GemmArgs& a, cudaStream_t s, double* flops_out) {
                 const int ntile = (a.flags & GEMM_LOWER) ? 2 * (bi + 1) : tn;
                 for (int bj = 0; bj < ntile; ++bj) {
                     int kb = 0, ke = a.K;
-                    if (a.flags & GEMM_TRIK_A) kb = std::max(kb, bi * BM);
+                    if (a.flags & GEMM_TRIK_A) kb = std::max(kb, trik_a_begin(bi * BM, a.trik_a_blk, a.trik_a_step));
                     if (a.flags & GEMM_TRIK_B) kb = std::max(kb, bj * BN);
                     if (a.flags & GEMM_TRIL_B) ke = std::min(ke, bj * BN + BN);
                     if (a.flags & GEMM_TRIL_A) ke = std::min(ke, bi * BM + BM);
