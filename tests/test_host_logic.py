@@ -165,3 +165,21 @@ def test_linear_inverter_host_side():
     assert inv.cov.bounds == [(None, None)] * inv.cov.n_params and inv.mean.bounds == [(None, None)] * inv.mean.n_params
     with pytest.raises(ValueError, match="hyper-parameters"):
         inv.optimize_hyperparameters(np.ones(inv.n_hyperpars + 1))
+
+
+def test_distributed_fit_rejects_options_that_cannot_run_in_lockstep():
+    """GpRegressor(distributed=...) without hyperpars runs the optimiser on every rank in lockstep (collective likelihood /
+    gradient calls): leave-one-out selection and worker threads are refused before any engine is created."""
+    x = np.linspace(0, 1, 20)
+    y = np.sin(x)
+    for kw in ({"n_processes": 2}, {"cross_val": True}):
+        with pytest.raises(ValueError, match="distributed=True optimises"):
+            gp.GpRegressor(x, y, distributed=(0, 1, None), **kw)
+    # the start points of the lockstep optimiser depend on the replicated targets only
+    holder = type("Replica", (), {})()
+    holder.y = y
+    seed = gp.GpRegressor._lockstep_seed(holder)
+    holder.y = y.copy()
+    assert gp.GpRegressor._lockstep_seed(holder) == seed and 0 <= seed < 2**31
+    holder.y = y + 1e-12
+    assert gp.GpRegressor._lockstep_seed(holder) != seed
