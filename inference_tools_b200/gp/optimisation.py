@@ -16,6 +16,7 @@ from inference_tools_b200.gp.acquisition import AcquisitionFunction, ExpectedImp
 from inference_tools_b200.gp.covariance import CovarianceFunction, SquaredExponential
 from inference_tools_b200.gp.mean import ConstantMean, MeanFunction
 from inference_tools_b200.gp.regression import GpRegressor
+from inference_tools_b200.gp._lockstep import lockstep_lbfgs
 
 
 class GpOptimiser:
@@ -127,9 +128,17 @@ class GpOptimiser:
         return fmin_l_bfgs_b(self.acquisition.opt_func_gradient, x0, approx_grad=False, bounds=self.bounds, pgtol=1e-10)
 
     def multistart_bfgs(self, starting_positions=None):
+        """optimisation.py:211-223.  The restarts run scipy's L-BFGS-B as in the reference, but in lockstep: their
+        evaluation requests are answered by ONE batched device call per round (``_lockstep.py``) instead of one
+        single-point prediction each; every restart follows the trajectory it would follow alone."""
         if starting_positions is None:
             starting_positions = self.acquisition.starting_positions(self.bounds)
-        results = [self.launch_bfgs(x0) for x0 in starting_positions]
+        starts = list(starting_positions)
+        batch = getattr(self.acquisition, "opt_func_gradient_batch", None)
+        if batch is not None and len(starts) > 1:
+            results = lockstep_lbfgs(batch, starts, self.bounds, pgtol=1e-10)
+        else:
+            results = [self.launch_bfgs(x0) for x0 in starts]
         best = sorted(results, key=lambda r: float(r[1]))[0]
         return best[0], float(best[1])
 
