@@ -14,9 +14,10 @@
 //      two sweeps over k: first P_3..P_6 (22 products, all 7 + 7 planes per k-block), then P_0..P_2 (6 products,
 //      planes 0..2).  Every k-block of planes is fetched by ONE 3-D TMA box per operand and feeds 22 (6) MMA pairs:
 //      ~45 bytes of L2->shared traffic per MMA clock instead of ~190 for a plain int8 GEMM of this tile.
-//      Warp 0 is the TMA producer (four 56 KB slots), warp 1 issues the MMAs (one elected lane), warps 2-9 drain
-//      the accumulators (tcgen05.ld), combine them smallest-first in FP64 (Horner in 2^-8; the first sweep's
-//      partial sum waits in a per-CTA scratch row) and apply the row / column scales, alpha and beta.
+//      Warp 0 is the TMA producer (224 KB of operand slots in an A ring and a B ring), warp 1 issues the MMAs (one
+//      elected lane), 8 or 16 epilogue warps drain the accumulators (tcgen05.ld), combine the diagonals of a sweep as
+//      integers (the first sweep's sum waits in a per-CTA scratch row) and apply the row / column scales, alpha, beta.
+//      What paces the kernel and what was tried against it: profiles/gemm_i8_load_path_r2.md.
 //
 // Error per product: the two splitting errors (2^-55 of the row maxima) plus the dropped terms (s + t >= 7), at most
 // 2^-51 of rowmax(A) * rowmax(B) with worst-case digits and ~2^-56 with real ones (tests/test_int8_split_model.py) -- a
