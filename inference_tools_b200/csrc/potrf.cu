@@ -310,7 +310,8 @@ __global__ void unit_diag_kernel(double* __restrict__ Y, int64_t ld, int n) {
 // with blocks of L (entries of the size of the data, k extent nb) -- never with blocks of inv(L), whose rows span many
 // decades and which the INT8 path resolves only relative to their maxima.  Measured (profiles/dist_grad_parity_r2.json):
 // the gradient built on this inverse is as accurate as the recursion's, no better -- the error of the INT8 gradient sits
-// in the product K^-1 = W^T W (row scales of a chunk that holds the row's diagonal), not in W; same time too.  Kept as
+// in the product K^-1 = W^T W (normwise in the rows' maxima over the chunk that holds their diagonals), not in W; same time
+// too.  Kept as
 // option "grad_inverse" = 1; the distributed path (dist.cu) uses the same substitution on its row blocks.
 // Both operands of every product are k-contiguous.  Y (n x n) is overwritten entirely.
 int trtri_rows_lower(const double* L, int64_t ldl, double* Y, int64_t ldy, int n, const LinalgWs& ws, cudaStream_t s) {

@@ -1,0 +1,114 @@
+"""CPU model (numpy, no GPU): where does the INT8 digit-split path lose accuracy in K^-1 = W^T W, and which row-scale rule
+would fix it?
+
+The digit split keeps 55 bits below a row's MAXIMUM over the k range it is split for.  Rows of Y = W^T = L^-T carry their
+largest entries at and next to the diagonal, so when the scale of an operand row is taken over a k range that contains
+its diagonal, the small entries far from the diagonal keep fewer bits -- and those are the entries every off-diagonal
+block of K^-1 is built from.  This script quantises Y row by row under different scale rules (no int8 arithmetic is
+needed: the products of the quantised values are exact in the kernel), forms the first-order error of K^-1 and reports the
+error it causes in the gradient traces 1/2 sum K^-1 o dK_p that the marginal-likelihood gradient is made of:
+
+  full      one scale per row over the whole k extent (round 1)
+  chunked   scales per k-chunk of N/4 (shipped: lauum_lower, potrf.cu)
+  chunk/2   chunks of N/8
+  columns   block columns of width nb: the B operand's scale starts AFTER its own diagonal block (what the distributed
+            gradient does, dist.cu phase 2); the diagonal blocks themselves use chunked scales
+  tiles     as chunked, but a B row's scale in the chunk that holds its diagonal skips its own 128-wide tile; diagonal tiles
+            in FP64 (a possible single-GPU variant)
+
+Result (profiles/kinv_split_model_N4096_r2.json): every rule gives gradient errors of 1e-16 .. 5e-14 -- the 55-bit
+quantisation is NOT what limits the INT8 gradient (1e-11 .. 6e-10 measured on the GPU); the other normwise term is, the
+digit pairs s + t >= 7 the kernel drops (2^-56 of the product of the two rows' chunk maxima each).
+
+    python tools/kinv_split_model.py [N]        (default 1536; dense SquaredExponential 2-D, sigma_n = 0.05, l = 0.3)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1536
+TILE = 128
+rng = np.random.default_rng(5)
+x = rng.uniform(0, 1, (N, 2))
+y = np.sin(3 * x).sum(axis=1) + rng.normal(0, 0.05, N)
+amp2, l = np.exp(2 * 0.1), 0.3
+d2 = ((x[:, None, :] - x[None, :, :]) ** 2)
+Ks = amp2 * np.exp(-0.5 * d2.sum(-1) / l**2)
+K = Ks + (0.05**2 + amp2 * 1e-12) * np.eye(N)
+L = np.linalg.cholesky(K)
+Y = np.linalg.solve(L, np.eye(N)).T.copy()            # Y = L^-T, upper triangular: row a = column a of inv(L)
+Kinv = np.tril(Y @ Y.T)
+dK = [2 * Ks] + [(d2[:, :, k] / l**2) * Ks for k in range(2)]      # SE gradient planes (ln a, ln l_k)
+alpha = np.linalg.solve(K, y - y.mean())
+grad = [0.5 * float(((np.outer(alpha, alpha) - Kinv) * np.tril(p, -1)).sum() * 2 + ((alpha**2 - np.diag(Kinv)) * np.diag(p)).sum())
+        for p in dK]
+gscale = max(abs(g) for g in grad)
+tile_of = (np.arange(N) // TILE) * TILE
+
+
+def quant_error(rows, c0, c1, skip_tile):
+    """q(Y[rows, c0:c1]) - Y[rows, c0:c1]: each row rounded to 55 bits below its maximum over the chunk (the digit split: 7
+    base-256 digits, top digit |.| <= 127); with skip_tile the maximum skips the row's own 128-wide diagonal tile"""
+    Yc = Y[rows, c0:c1]
+    ref = np.abs(Yc)
+    if skip_tile:
+        k = np.arange(c0, c1)[None, :]
+        ref = np.where(k >= (tile_of[rows] + TILE)[:, None], ref, 0.0)
+    m = ref.max(axis=1)
+    ok = m > 0
+    e = np.frexp(np.where(ok, m, 1.0) * 128.0 / 127.0)[1]
+    sc = np.ldexp(1.0, 55 - e)[:, None]
+    q = np.rint(Yc * sc) / sc
+    if skip_tile:   # values above the skipped-range maximum are clamped by the kernel's a-priori-bound mode; here: keep them exact
+        q = np.where(np.abs(Yc) > m[:, None] * (128.0 / 127.0), Yc, q)
+    return np.where(ok[:, None], q - Yc, 0.0)
+
+
+def error_matrix(rows_a, rows_b, k_start, chunk, skip_tile_b=False):
+    """first-order error of sum_k Ya[i, k] Yb[j, k] from quantising both operands chunk by chunk (the products of the
+    quantised values themselves are exact in the kernel): dA B^T + A dB^T"""
+    E = np.zeros((rows_a.size, rows_b.size))
+    for c0 in range(k_start, N, chunk):
+        c1 = min(N, c0 + chunk)
+        E += quant_error(rows_a, c0, c1, False) @ Y[rows_b, c0:c1].T + Y[rows_a, c0:c1] @ quant_error(rows_b, c0, c1, skip_tile_b).T
+    return E
+
+
+def kinv_error(rule, chunk, nb=None):
+    allr = np.arange(N)
+    if rule == "columns":
+        E = np.zeros((N, N))
+        for b0 in range(0, N, nb):
+            b1 = min(N, b0 + nb)
+            rb = np.arange(b0, b1)
+            E[b0:b1, b0:b1] = error_matrix(rb, rb, b0, chunk)
+            if b1 < N:      # rows below: k from b1 on, chunk boundaries relative to b1 -- B's scale never sees its diagonal block
+                E[b1:, b0:b1] = error_matrix(np.arange(b1, N), rb, b1, chunk)
+        return np.tril(E)
+    E = np.tril(error_matrix(allr, allr, 0, chunk, skip_tile_b=(rule == "tiles")))
+    if rule == "tiles":     # diagonal tiles in FP64
+        for t0 in range(0, N, TILE):
+            E[t0:t0 + TILE, t0:t0 + TILE] = 0.0
+    return E
+
+
+def grad_error(E):
+    return max(abs(0.5 * ((E * np.tril(p, -1)).sum() * 2 + (np.diag(E) * np.diag(p)).sum())) for p in dK) / gscale
+
+
+res = {"N": N, "kernel": "SquaredExponential 2-D, a = e^0.1, l = 0.3, sigma_n = 0.05", "min_Lii": float(np.diag(L).min()),
+       "row_dynamic_range_median": float(np.median(np.abs(Y).max(axis=1) / np.maximum(np.median(np.abs(Y) + np.tril(np.full((N, N), np.inf), -1), axis=1), 1e-300))),
+       "what": "relative error of the gradient traces caused by the row-scale rule alone, first order (max over parameters / max |grad|)",
+       "rules": {}}
+for name, rule, chunk, nb in [("full", "plain", N, None), ("chunked N/4", "plain", N // 4, None), ("chunked N/8", "plain", N // 8, None),
+                              ("chunked N/16", "plain", N // 16, None),
+                              ("block columns nb = N/16, chunks N/4", "columns", N // 4, max(TILE, N // 16)),
+                              ("block columns nb = N/32, chunks N/4", "columns", N // 4, max(TILE, N // 32)),
+                              ("tiles: B scale skips its own tile, chunks N/4", "tiles", N // 4, None)]:
+    E = kinv_error(rule, chunk, nb)
+    res["rules"][name] = {"grad_rel_err": float(grad_error(E)), "kinv_max_abs_err": float(np.abs(E).max())}
+    print(name, res["rules"][name], flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open(f"gpurun_out/kinv_split_model_N{N}.json", "w"), indent=1)
