@@ -17,8 +17,9 @@ error it causes in the gradient traces 1/2 sum K^-1 o dK_p that the marginal-lik
             in FP64 (a possible single-GPU variant)
 
 Result (profiles/kinv_split_model_N4096_r2.json): every rule gives gradient errors of 1e-16 .. 5e-14 -- the 55-bit
-quantisation is NOT what limits the INT8 gradient (1e-11 .. 6e-10 measured on the GPU); the other normwise term is, the
-digit pairs s + t >= 7 the kernel drops (2^-56 of the product of the two rows' chunk maxima each).
+quantisation is NOT what limits the INT8 gradient (1e-11 .. 6e-10 measured on the GPU).  That leaves the other normwise
+term as the candidate: the digit pairs s + t >= 7 the kernel drops (2^-56 of the product of the two rows' chunk maxima
+each), which this script does not model.
 
     python tools/kinv_split_model.py [N]        (default 1536; dense SquaredExponential 2-D, sigma_n = 0.05, l = 0.3)
 """
