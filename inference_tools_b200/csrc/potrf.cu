@@ -297,6 +297,10 @@ int trtri_lower(const double* L, int64_t ldl, double* W, int64_t ldw, int n, int
 }
 
 namespace {
+// k extent per launch of the K^-1 products: N/8, at least 1024 (below that the per-launch splitting dominates), at most
+// 4096
+inline int lauum_chunk(int n) { return std::min(4096, std::max(1024, (n / 8) / 64 * 64)); }
+
 __global__ void unit_diag_kernel(double* __restrict__ Y, int64_t ld, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) Y[(int64_t)i * ld + i] = 1.0;
@@ -339,7 +343,7 @@ int trtri_rows_lower(const double* L, int64_t ldl, double* Y, int64_t ldy, int n
 // Kinv(lower tiles) = Y Y^T for Y = L^-T from trtri_rows_lower: Kinv_ij = sum_k Y_ik Y_jk, k >= max(i, j)
 int lauum_rows_lower(const double* Y, int64_t ldy, double* Kinv, int64_t ldk, int n, cudaStream_t s) {
     GemmArgs g{n, n, n, Y, ldy, Y, ldy, nullptr, 0, Kinv, ldk, nullptr, 0, 1.0, 0.0, GEMM_TRIK_A | GEMM_TRIK_B | GEMM_LOWER};
-    g.max_k = std::min(4096, std::max(1024, (n / 4) / 64 * 64));  // chunk-local row scales, as in lauum_lower
+    g.max_k = lauum_chunk(n);  // chunk-local row scales, as in lauum_lower
     return gemm_nt(g, s);
 }
 
@@ -347,11 +351,12 @@ int lauum_lower(const double* W, int64_t ldw, double* Kinv, int64_t ldk, int n, 
     // Kinv_ij = sum_k W[k][i] W[k][j], k >= max(i, j)
     GemmArgs g{n, n, n, W, ldw, W, ldw, nullptr, 0, Kinv, ldk, nullptr, 0, 1.0, 0.0,
                GEMM_A_MMAJOR | GEMM_B_NMAJOR | GEMM_TRIK_A | GEMM_TRIK_B | GEMM_LOWER};
-    // The columns of W = inv(L) decay away from the diagonal while the INT8 path keeps 55 bits below each operand row's
-    // MAXIMUM over the k extent of a launch.  Chunks of N/4 (at most 4096, at least 1024; own scales each) cut the error
-    // of K^-1 -- which the gradient trace amplifies -- 24-fold at N = 16384 for 18 % more time in this product
-    // (profiles/grad_phase_sensitivity_r2.md).
-    g.max_k = std::min(4096, std::max(1024, (n / 4) / 64 * 64));
+    // The INT8 product is accurate relative to the operand rows' MAXIMA over the k extent of a launch (quantisation to 55
+    // bits below the maximum and, dominating, the dropped digit pairs s + t >= 7: tools/kinv_split_model.py), and the
+    // rows of W = inv(L) are largest at the diagonal.  Chunks with their own scales confine that to the chunk that holds
+    // the diagonal: N/4 cut the error of K^-1 -- which the gradient trace amplifies -- 24-fold at N = 16384 for 18 % more
+    // time in this product (profiles/grad_phase_sensitivity_r2.md); N/8 is another factor 3-6 (model and measurement).
+    g.max_k = lauum_chunk(n);
     return gemm_nt(g, s);
 }
 

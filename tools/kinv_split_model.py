@@ -49,50 +49,68 @@ gscale = max(abs(g) for g in grad)
 tile_of = (np.arange(N) // TILE) * TILE
 
 
-def quant_error(rows, c0, c1, skip_tile):
-    """q(Y[rows, c0:c1]) - Y[rows, c0:c1]: each row rounded to 55 bits below its maximum over the chunk (the digit split: 7
-    base-256 digits, top digit |.| <= 127); with skip_tile the maximum skips the row's own 128-wide diagonal tile"""
-    Yc = Y[rows, c0:c1]
-    ref = np.abs(Yc)
+PAIRS = [(s_, t_) for s_ in range(7) for t_ in range(7) if 7 <= s_ + t_ <= 8]   # the leading dropped digit pairs (2^-70, 2^-78)
+
+
+def split_chunk(rows, c0, c1, skip_tile):
+    """The digit split of Y[rows, c0:c1] as gemm_i8.cu does it: per row e with max|x| 2^-e <= 127/128 over the chunk (with
+    skip_tile: over the chunk minus the row's own 128-wide diagonal tile, whose entries are left out of this operand),
+    m = round(x 2^(55-e)), 7 balanced base-256 digits.  Returns 2^e, the digit planes (float arrays of small integers) and
+    the quantisation error q - x."""
+    Yc = Y[rows, c0:c1].copy()
     if skip_tile:
         k = np.arange(c0, c1)[None, :]
-        ref = np.where(k >= (tile_of[rows] + TILE)[:, None], ref, 0.0)
-    m = ref.max(axis=1)
-    ok = m > 0
-    e = np.frexp(np.where(ok, m, 1.0) * 128.0 / 127.0)[1]
-    sc = np.ldexp(1.0, 55 - e)[:, None]
-    q = np.rint(Yc * sc) / sc
-    if skip_tile:   # values above the skipped-range maximum are clamped by the kernel's a-priori-bound mode; here: keep them exact
-        q = np.where(np.abs(Yc) > m[:, None] * (128.0 / 127.0), Yc, q)
-    return np.where(ok[:, None], q - Yc, 0.0)
+        Yc = np.where(k >= (tile_of[rows] + TILE)[:, None], Yc, 0.0)
+    mx = np.abs(Yc).max(axis=1)
+    ok = mx > 0
+    e = np.frexp(np.where(ok, mx, 1.0) * 128.0 / 127.0)[1]
+    m = np.rint(Yc * np.ldexp(1.0, 55 - e)[:, None]).astype(np.int64)
+    dq = np.where(ok[:, None], m.astype(np.float64) * np.ldexp(1.0, e - 55)[:, None] - Yc, 0.0)
+    planes = [None] * 7
+    for s_ in range(6, 0, -1):
+        low = ((m & 0xFF) ^ 0x80) - 0x80
+        planes[s_] = low.astype(np.float64)
+        m = (m - low) >> 8
+    planes[0] = m.astype(np.float64)
+    return np.where(ok, np.ldexp(1.0, e), 0.0), planes, dq, Yc
 
 
 def error_matrix(rows_a, rows_b, k_start, chunk, skip_tile_b=False):
-    """first-order error of sum_k Ya[i, k] Yb[j, k] from quantising both operands chunk by chunk (the products of the
-    quantised values themselves are exact in the kernel): dA B^T + A dB^T"""
+    """error of sum_k Ya[i, k] Yb[j, k] on the INT8 path, chunk by chunk: the quantisation of both operands (first order:
+    dA B^T + A dB^T) and the digit pairs the kernel drops (s + t >= 7; the two leading anti-diagonals are summed exactly)"""
     E = np.zeros((rows_a.size, rows_b.size))
+    D = np.zeros_like(E)
     for c0 in range(k_start, N, chunk):
         c1 = min(N, c0 + chunk)
-        E += quant_error(rows_a, c0, c1, False) @ Y[rows_b, c0:c1].T + Y[rows_a, c0:c1] @ quant_error(rows_b, c0, c1, skip_tile_b).T
-    return E
+        sa, pa, da, Ya = split_chunk(rows_a, c0, c1, False)
+        sb, pb, db, Yb = split_chunk(rows_b, c0, c1, skip_tile_b)
+        E += da @ Yb.T + Ya @ db.T
+        drop = np.zeros_like(E)
+        for s_, t_ in PAIRS:
+            drop += np.ldexp(pa[s_] @ pb[t_].T, -(14 + 8 * (s_ + t_)))
+        D -= (sa[:, None] * sb[None, :]) * drop
+    return E, D
 
 
 def kinv_error(rule, chunk, nb=None):
+    """(quantisation part, dropped-pairs part) of the error of the lower triangle of K^-1"""
     allr = np.arange(N)
     if rule == "columns":
-        E = np.zeros((N, N))
+        E, D = np.zeros((N, N)), np.zeros((N, N))
         for b0 in range(0, N, nb):
             b1 = min(N, b0 + nb)
             rb = np.arange(b0, b1)
-            E[b0:b1, b0:b1] = error_matrix(rb, rb, b0, chunk)
+            E[b0:b1, b0:b1], D[b0:b1, b0:b1] = error_matrix(rb, rb, b0, chunk)
             if b1 < N:      # rows below: k from b1 on, chunk boundaries relative to b1 -- B's scale never sees its diagonal block
-                E[b1:, b0:b1] = error_matrix(np.arange(b1, N), rb, b1, chunk)
-        return np.tril(E)
-    E = np.tril(error_matrix(allr, allr, 0, chunk, skip_tile_b=(rule == "tiles")))
+                E[b1:, b0:b1], D[b1:, b0:b1] = error_matrix(np.arange(b1, N), rb, b1, chunk)
+        return np.tril(E), np.tril(D)
+    E, D = error_matrix(allr, allr, 0, chunk, skip_tile_b=(rule == "tiles"))
+    E, D = np.tril(E), np.tril(D)
     if rule == "tiles":     # diagonal tiles in FP64
         for t0 in range(0, N, TILE):
             E[t0:t0 + TILE, t0:t0 + TILE] = 0.0
-    return E
+            D[t0:t0 + TILE, t0:t0 + TILE] = 0.0
+    return E, D
 
 
 def grad_error(E):
@@ -101,15 +119,16 @@ def grad_error(E):
 
 res = {"N": N, "kernel": "SquaredExponential 2-D, a = e^0.1, l = 0.3, sigma_n = 0.05", "min_Lii": float(np.diag(L).min()),
        "row_dynamic_range_median": float(np.median(np.abs(Y).max(axis=1) / np.maximum(np.median(np.abs(Y) + np.tril(np.full((N, N), np.inf), -1), axis=1), 1e-300))),
-       "what": "relative error of the gradient traces caused by the row-scale rule alone, first order (max over parameters / max |grad|)",
+       "what": "relative error of the gradient traces (max over parameters / max |grad|) from the INT8 product K^-1 = Y Y^T: row quantisation (first order) and the dropped digit pairs s + t = 7, 8 (exact)",
        "rules": {}}
 for name, rule, chunk, nb in [("full", "plain", N, None), ("chunked N/4", "plain", N // 4, None), ("chunked N/8", "plain", N // 8, None),
                               ("chunked N/16", "plain", N // 16, None),
                               ("block columns nb = N/16, chunks N/4", "columns", N // 4, max(TILE, N // 16)),
                               ("block columns nb = N/32, chunks N/4", "columns", N // 4, max(TILE, N // 32)),
                               ("tiles: B scale skips its own tile, chunks N/4", "tiles", N // 4, None)]:
-    E = kinv_error(rule, chunk, nb)
-    res["rules"][name] = {"grad_rel_err": float(grad_error(E)), "kinv_max_abs_err": float(np.abs(E).max())}
+    E, D = kinv_error(rule, chunk, nb)
+    res["rules"][name] = {"grad_rel_err_quantisation": float(grad_error(E)), "grad_rel_err_dropped_pairs": float(grad_error(D)),
+                          "grad_rel_err_total": float(grad_error(E + D)), "kinv_max_abs_err": float(np.abs(E + D).max())}
     print(name, res["rules"][name], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open(f"gpurun_out/kinv_split_model_N{N}.json", "w"), indent=1)
