@@ -5,8 +5,9 @@ The digit split keeps 55 bits below a row's MAXIMUM over the k range it is split
 largest entries at and next to the diagonal, so when the scale of an operand row is taken over a k range that contains
 its diagonal, the small entries far from the diagonal keep fewer bits -- and those are the entries every off-diagonal
 block of K^-1 is built from.  This script quantises Y row by row under different scale rules (no int8 arithmetic is
-needed: the products of the quantised values are exact in the kernel), forms the first-order error of K^-1 and reports the
-error it causes in the gradient traces 1/2 sum K^-1 o dK_p that the marginal-likelihood gradient is made of:
+needed for this part), forms the first-order error of K^-1, adds the digit pairs s + t >= 7 that gemm_i8_kernel drops
+(exact integer digit planes, as split_rows_kernel writes them) and reports the error both cause in the gradient traces
+1/2 sum K^-1 o dK_p that the marginal-likelihood gradient is made of:
 
   full      one scale per row over the whole k extent (round 1)
   chunked   scales per k-chunk of N/4 (shipped: lauum_lower, potrf.cu)
@@ -16,12 +17,10 @@ error it causes in the gradient traces 1/2 sum K^-1 o dK_p that the marginal-lik
   tiles     as chunked, but a B row's scale in the chunk that holds its diagonal skips its own 128-wide tile; diagonal tiles
             in FP64 (a possible single-GPU variant)
 
-Result (profiles/kinv_split_model_N4096_r2.json): every rule gives gradient errors of 1e-16 .. 5e-14 -- the 55-bit
-quantisation is NOT what limits the INT8 gradient (1e-11 .. 6e-10 measured on the GPU).  That leaves the other normwise
-term as the candidate: the digit pairs s + t >= 7 the kernel drops (2^-56 of the product of the two rows' chunk maxima
-each), which this script does not model.
-
-    python tools/kinv_split_model.py [N]        (default 1536; dense SquaredExponential 2-D, sigma_n = 0.05, l = 0.3)
+Result (profiles/kinv_split_model_N*_r2.json): the 55-bit quantisation contributes 1e-16 .. 5e-14 to the gradient under every
+rule -- it is NOT what limits the INT8 gradient.  The digit pairs s + t >= 7 the kernel drops (2^-56 of the product of the
+two rows' chunk maxima each; the anti-diagonals 7 and 8 are summed exactly here) are: 8.9e-11 with one scale per row,
+2.8e-12 with chunks of N/4, 8.5e-13 with N/8, 5.5e-13 with the tiles rule at N = 4096.
 """
 import json
 import os
