@@ -85,3 +85,22 @@ def test_int32_accumulators_cannot_overflow_within_one_chunk():
     """7 products of worst-case digits over the longest k chunk the kernel issues (MAX_K = 16384)."""
     assert 7 * 16384 * 128 * 128 < 2**31
     assert 8 * 16384 * 128 * 128 >= 2**31                        # which is why longer k extents are chunked
+
+
+def test_kinv_product_error_is_the_dropped_digit_pairs_of_the_diagonal_chunk(tmp_path):
+    """tools/kinv_split_model.py (the digit split applied to K^-1 = W^T W of a dense SquaredExponential set, exact integer
+    digit planes): the 55-bit quantisation is negligible, the dropped digit pairs s + t >= 7 set the gradient's INT8 error,
+    and shorter k-chunks / scales that skip the diagonal tile shrink it -- the reasoning behind lauum_chunk (potrf.cu)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "kinv_split_model.py"), "768"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    res = json.load(open(tmp_path / "gpurun_out" / "kinv_split_model_N768.json"))["rules"]
+    full, c4, c8 = res["full"], res["chunked N/4"], res["chunked N/8"]
+    for rule in (full, c4, c8):
+        assert rule["grad_rel_err_quantisation"] < 1e-14
+        assert rule["grad_rel_err_dropped_pairs"] > 20 * rule["grad_rel_err_quantisation"]
+    assert c4["grad_rel_err_total"] < full["grad_rel_err_total"]
+    assert c8["grad_rel_err_total"] < 0.5 * c4["grad_rel_err_total"]
+    assert res["tiles: B scale skips its own tile, chunks N/4"]["grad_rel_err_total"] < 0.5 * c4["grad_rel_err_total"]
